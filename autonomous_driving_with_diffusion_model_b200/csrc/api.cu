@@ -1,0 +1,855 @@
+// libb200plan: handle, weight packing, denoiser program, whole-plan CUDA graph.  Public ABI: include/b200plan.h.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2p {
+int upload_freq_table(const float* f, int n);
+
+enum { BUF_X = -2, BUF_NONE = -1 };
+constexpr size_t NPOS = (size_t)-1;
+
+struct Slot {
+  std::string key;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+  std::vector<float> host;
+  bool set = false;
+};
+
+struct LayerOp {
+  int in0 = BUF_NONE, in1 = BUF_NONE;
+  int C0 = 0, C1 = 0, Lin = 0, Lout = 0, Cout = 0, taps = 1, stride = 1, pad = 0, transposed = 0;
+  size_t W = NPOS, bias = NPOS, gamma = NPOS, beta = NPOS;
+  int temb_off = -1;
+  int res_id = BUF_NONE;
+  int rin0 = BUF_NONE, rin1 = BUF_NONE, RC0 = 0, RC1 = 0;
+  size_t resW = NPOS, resB = NPOS;
+  size_t headW = NPOS, headB = NPOS;
+  int head_dim = 0;
+  int out = BUF_NONE;
+};
+
+struct Buf { int L, C; size_t off; };  // per-sample floats = L*C; off = prefix sum of per-sample floats
+
+struct GraphKey {
+  int B, T, kind, has_target, has_noise, has_traj, has_mask;
+  b2p_plan_config pc;
+  bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; int64_t launches; };
+
+}  // namespace b2p
+
+using namespace b2p;
+
+struct b2p_handle_s {
+  b2p_model_config cfg;
+  int device = 0;
+  std::vector<Slot> slots;
+  std::unordered_map<std::string, int> index;
+  bool finalized = false;
+  std::string err;
+  int64_t last_launches = 0;
+  int64_t flops_per_sample = 0;
+
+  // architecture
+  int H = 16, D = 7, dim = 64, nlev = 4;
+  int chans[9];
+  int temb_total = 0;
+  std::vector<LayerOp> ops;
+  std::vector<Buf> bufs;
+  size_t buf_floats_per_sample = 0;
+  int head_dim = 7;
+
+  // packed weights
+  std::vector<float> pack_host;
+  float* d_pack = nullptr;
+  size_t o_w1t, o_b1, o_w3t, o_b3, o_wc0t, o_bc0, o_wc2t, o_bc2, o_tembW, o_tembB;
+  TrajPredWeights tp{};
+  bool has_tp = false;
+
+  // workspace (activation buffers) for `cap` denoiser rows
+  int cap = 0;
+  float* d_ws = nullptr;
+  float *d_time_embed = nullptr, *d_mish_cond = nullptr, *d_temb = nullptr, *d_act = nullptr;
+  int64_t* d_t = nullptr;
+
+  // static plan buffers
+  int plan_capB = 0, plan_capT = 0;
+  float *p_x = nullptr, *p_feat = nullptr, *p_target = nullptr, *p_cond = nullptr, *p_noise = nullptr, *p_traj = nullptr,
+        *p_mask = nullptr, *p_mo = nullptr, *p_action = nullptr, *p_out = nullptr;
+  int64_t* p_tsteps = nullptr;
+  std::vector<GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
+
+  int fail(int code, const std::string& m) { err = m; return code; }
+};
+
+namespace {
+
+struct Packer {
+  std::vector<float>& v;
+  size_t push(const float* p, size_t n) {
+    size_t off = (v.size() + 63) & ~(size_t)63;
+    v.resize(off + n);
+    if (p) memcpy(v.data() + off, p, n * sizeof(float));
+    return off;
+  }
+  size_t alloc(size_t n) { return push(nullptr, n); }
+};
+
+void add_slot(b2p_handle_s* h, const std::string& key, std::vector<int64_t> shape) {
+  Slot s;
+  s.key = key; s.shape = shape; s.numel = 1;
+  for (auto d : shape) s.numel *= d;
+  h->index[key] = (int)h->slots.size();
+  h->slots.push_back(std::move(s));
+}
+void add_conv_block_slots(b2p_handle_s* h, const std::string& p, int cin, int cout, int k) {
+  add_slot(h, p + ".block.0.weight", {cout, cin, k});
+  add_slot(h, p + ".block.0.bias", {cout});
+  add_slot(h, p + ".block.2.weight", {cout});
+  add_slot(h, p + ".block.2.bias", {cout});
+}
+void add_res_block_slots(b2p_handle_s* h, const std::string& p, int cin, int cout) {
+  add_conv_block_slots(h, p + ".blocks.0", cin, cout, 5);
+  add_conv_block_slots(h, p + ".blocks.1", cout, cout, 5);
+  add_slot(h, p + ".time_mlp.1.weight", {cout, 2 * h->dim});
+  add_slot(h, p + ".time_mlp.1.bias", {cout});
+  if (cin != cout) {
+    add_slot(h, p + ".residual_conv.weight", {cout, cin, 1});
+    add_slot(h, p + ".residual_conv.bias", {cout});
+  }
+}
+
+const float* W(b2p_handle_s* h, const std::string& key) { return h->slots[h->index.at(key)].host.data(); }
+
+// Conv1d weight [Cout][Cin][k] -> [k][Cin][Cout]
+size_t pack_conv(b2p_handle_s* h, Packer& pk, const std::string& key, int cout, int cin, int k) {
+  const float* w = W(h, key);
+  size_t off = pk.alloc((size_t)k * cin * cout);
+  float* o = pk.v.data() + off;
+  for (int co = 0; co < cout; ++co)
+    for (int c = 0; c < cin; ++c)
+      for (int j = 0; j < k; ++j) o[((size_t)j * cin + c) * cout + co] = w[((size_t)co * cin + c) * k + j];
+  return off;
+}
+// ConvTranspose1d weight [Cin][Cout][k] -> [k][Cin][Cout]
+size_t pack_convT(b2p_handle_s* h, Packer& pk, const std::string& key, int cin, int cout, int k) {
+  const float* w = W(h, key);
+  size_t off = pk.alloc((size_t)k * cin * cout);
+  float* o = pk.v.data() + off;
+  for (int c = 0; c < cin; ++c)
+    for (int co = 0; co < cout; ++co)
+      for (int j = 0; j < k; ++j) o[((size_t)j * cin + c) * cout + co] = w[((size_t)c * cout + co) * k + j];
+  return off;
+}
+// Linear weight [out][in] -> [in][out_ld] placed at column col0 of a wider matrix
+void pack_linear_T(const float* w, int out, int in, float* dst, int ld, int col0) {
+  for (int o = 0; o < out; ++o)
+    for (int i = 0; i < in; ++i) dst[(size_t)i * ld + col0 + o] = w[(size_t)o * in + i];
+}
+size_t pack_vec(b2p_handle_s* h, Packer& pk, const std::string& key, size_t n) { return pk.push(W(h, key), n); }
+
+int new_buf(b2p_handle_s* h, int L, int C) {
+  Buf b{L, C, h->buf_floats_per_sample};
+  h->buf_floats_per_sample += (size_t)L * C;
+  h->bufs.push_back(b);
+  return (int)h->bufs.size() - 1;
+}
+
+int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
+
+// ---- build the slot table (state_dict contract) ----
+void build_slots(b2p_handle_s* h) {
+  const int dim = h->dim;
+  if (h->cfg.guidance == B2P_FREE_GUIDANCE) {
+    add_slot(h, "cond_mlp.0.weight", {dim, 2}); add_slot(h, "cond_mlp.0.bias", {dim});
+    add_slot(h, "cond_mlp.2.weight", {dim, dim}); add_slot(h, "cond_mlp.2.bias", {dim});
+  }
+  add_slot(h, "time_mlp.1.weight", {4 * dim, dim}); add_slot(h, "time_mlp.1.bias", {4 * dim});
+  add_slot(h, "time_mlp.3.weight", {dim, 4 * dim}); add_slot(h, "time_mlp.3.bias", {dim});
+  const int n = h->nlev;
+  for (int i = 0; i < n; ++i) {
+    int ci = h->chans[i], co = h->chans[i + 1];
+    std::string p = "downs." + std::to_string(i);
+    add_res_block_slots(h, p + ".0", ci, co);
+    add_res_block_slots(h, p + ".1", co, co);
+    if (i < n - 1) { add_slot(h, p + ".3.conv.weight", {co, co, 3}); add_slot(h, p + ".3.conv.bias", {co}); }
+  }
+  for (int u = 0; u < n - 1; ++u) {
+    int ci = h->chans[n - 1 - u], co = h->chans[n - u];  // (dim_in, dim_out) of reversed(in_out[1:])
+    std::string p = "ups." + std::to_string(u);
+    add_res_block_slots(h, p + ".0", co * 2, ci);
+    add_res_block_slots(h, p + ".1", ci, ci);
+    add_slot(h, p + ".3.conv.weight", {ci, ci, 4}); add_slot(h, p + ".3.conv.bias", {ci});
+  }
+  int mid = h->chans[n];
+  add_res_block_slots(h, "mid_block1", mid, mid);
+  add_res_block_slots(h, "mid_block2", mid, mid);
+  int fin = h->chans[1];
+  if (h->cfg.guidance == B2P_CLASSIFIER_GUIDANCE) {
+    add_conv_block_slots(h, "act_conv.0", fin, fin, 5);
+    add_slot(h, "act_conv.1.weight", {3, fin, 1}); add_slot(h, "act_conv.1.bias", {3});
+    const int hd = 64;
+    add_slot(h, "state_pred.input_proj.weight", {hd, 3}); add_slot(h, "state_pred.input_proj.bias", {hd});
+    for (int l = 0; l < 2; ++l) {
+      std::string p = "state_pred.encoder_traj.layers." + std::to_string(l);
+      add_slot(h, p + ".self_attn.in_proj_weight", {3 * hd, hd}); add_slot(h, p + ".self_attn.in_proj_bias", {3 * hd});
+      add_slot(h, p + ".self_attn.out_proj.weight", {hd, hd}); add_slot(h, p + ".self_attn.out_proj.bias", {hd});
+      add_slot(h, p + ".linear1.weight", {4 * hd, hd}); add_slot(h, p + ".linear1.bias", {4 * hd});
+      add_slot(h, p + ".linear2.weight", {hd, 4 * hd}); add_slot(h, p + ".linear2.bias", {hd});
+      add_slot(h, p + ".norm1.weight", {hd}); add_slot(h, p + ".norm1.bias", {hd});
+      add_slot(h, p + ".norm2.weight", {hd}); add_slot(h, p + ".norm2.bias", {hd});
+    }
+    add_slot(h, "state_pred.encoder_traj.norm.weight", {hd}); add_slot(h, "state_pred.encoder_traj.norm.bias", {hd});
+    add_slot(h, "state_pred.output_proj.weight", {h->D - 3, hd}); add_slot(h, "state_pred.output_proj.bias", {h->D - 3});
+  } else {
+    add_conv_block_slots(h, "final_conv.0", fin, fin, 5);
+    add_slot(h, "final_conv.1.weight", {h->D, fin, 1}); add_slot(h, "final_conv.1.bias", {h->D});
+  }
+}
+
+// ---- residual block = two fused launches ----
+struct BlockBuild { int temb_off; };
+int add_res_block(b2p_handle_s* h, Packer& pk, const std::string& p, int in0, int in1, int C0, int C1, int cout, int L,
+                  int& temb_cursor, std::vector<float>& tembW, std::vector<float>& tembB) {
+  const int cin = C0 + C1;
+  LayerOp a;
+  a.in0 = in0; a.in1 = in1; a.C0 = C0; a.C1 = C1; a.Lin = a.Lout = L; a.Cout = cout; a.taps = 5; a.stride = 1; a.pad = 2;
+  a.W = pack_conv(h, pk, p + ".blocks.0.block.0.weight", cout, cin, 5);
+  a.bias = pack_vec(h, pk, p + ".blocks.0.block.0.bias", cout);
+  a.gamma = pack_vec(h, pk, p + ".blocks.0.block.2.weight", cout);
+  a.beta = pack_vec(h, pk, p + ".blocks.0.block.2.bias", cout);
+  a.temb_off = temb_cursor;
+  // this block's Linear(2*dim -> cout) becomes columns [temb_cursor, temb_cursor+cout) of the shared GEMM
+  pack_linear_T(W(h, p + ".time_mlp.1.weight"), cout, 2 * h->dim, tembW.data(), h->temb_total, temb_cursor);
+  memcpy(tembB.data() + temb_cursor, W(h, p + ".time_mlp.1.bias"), sizeof(float) * cout);
+  temb_cursor += cout;
+  a.out = new_buf(h, L, cout);
+  h->ops.push_back(a);
+
+  LayerOp b;
+  b.in0 = a.out; b.C0 = cout; b.Lin = b.Lout = L; b.Cout = cout; b.taps = 5; b.stride = 1; b.pad = 2;
+  b.W = pack_conv(h, pk, p + ".blocks.1.block.0.weight", cout, cout, 5);
+  b.bias = pack_vec(h, pk, p + ".blocks.1.block.0.bias", cout);
+  b.gamma = pack_vec(h, pk, p + ".blocks.1.block.2.weight", cout);
+  b.beta = pack_vec(h, pk, p + ".blocks.1.block.2.bias", cout);
+  if (cin != cout) {
+    b.rin0 = in0; b.rin1 = in1; b.RC0 = C0; b.RC1 = C1;
+    b.resW = pack_conv(h, pk, p + ".residual_conv.weight", cout, cin, 1);
+    b.resB = pack_vec(h, pk, p + ".residual_conv.bias", cout);
+  } else {
+    b.res_id = in0;
+  }
+  b.out = new_buf(h, L, cout);
+  h->ops.push_back(b);
+  // FLOPs: two k=5 convs + time Linear + optional 1x1
+  h->flops_per_sample += 2LL * cout * cin * 5 * L + 2LL * cout * cout * 5 * L + 2LL * cout * 2 * h->dim;
+  if (cin != cout) h->flops_per_sample += 2LL * cout * cin * L;
+  return b.out;
+}
+
+int build_program(b2p_handle_s* h) {
+  h->ops.clear(); h->bufs.clear(); h->buf_floats_per_sample = 0; h->flops_per_sample = 0;
+  h->pack_host.clear();
+  Packer pk{h->pack_host};
+  const int dim = h->dim, n = h->nlev;
+  // embedding MLPs, transposed for coalesced reads
+  {
+    std::vector<float> t((size_t)dim * 4 * dim);
+    pack_linear_T(W(h, "time_mlp.1.weight"), 4 * dim, dim, t.data(), 4 * dim, 0);
+    h->o_w1t = pk.push(t.data(), t.size());
+    h->o_b1 = pack_vec(h, pk, "time_mlp.1.bias", 4 * dim);
+    pack_linear_T(W(h, "time_mlp.3.weight"), dim, 4 * dim, t.data(), dim, 0);
+    h->o_w3t = pk.push(t.data(), t.size());
+    h->o_b3 = pack_vec(h, pk, "time_mlp.3.bias", dim);
+    h->flops_per_sample += 2LL * dim * 4 * dim * 2;
+    if (h->cfg.guidance == B2P_FREE_GUIDANCE) {
+      std::vector<float> c((size_t)dim * dim);
+      pack_linear_T(W(h, "cond_mlp.0.weight"), dim, 2, c.data(), dim, 0);
+      h->o_wc0t = pk.push(c.data(), 2 * dim);
+      h->o_bc0 = pack_vec(h, pk, "cond_mlp.0.bias", dim);
+      pack_linear_T(W(h, "cond_mlp.2.weight"), dim, dim, c.data(), dim, 0);
+      h->o_wc2t = pk.push(c.data(), (size_t)dim * dim);
+      h->o_bc2 = pack_vec(h, pk, "cond_mlp.2.bias", dim);
+      h->flops_per_sample += 2LL * dim * 2 + 2LL * dim * dim;
+    }
+  }
+  std::vector<float> tembW((size_t)2 * dim * h->temb_total), tembB(h->temb_total);
+  int cursor = 0;
+  int L = h->H;
+  int x = BUF_X, xc = h->D;
+  std::vector<int> skips, skipC, skipL;
+  for (int i = 0; i < n; ++i) {
+    int co = h->chans[i + 1];
+    std::string p = "downs." + std::to_string(i);
+    x = add_res_block(h, pk, p + ".0", x, BUF_NONE, xc, 0, co, L, cursor, tembW, tembB);
+    x = add_res_block(h, pk, p + ".1", x, BUF_NONE, co, 0, co, L, cursor, tembW, tembB);
+    xc = co;
+    skips.push_back(x); skipC.push_back(co); skipL.push_back(L);
+    if (i < n - 1) {
+      LayerOp d;
+      d.in0 = x; d.C0 = co; d.Lin = L; d.Lout = L / 2; d.Cout = co; d.taps = 3; d.stride = 2; d.pad = 1;
+      d.W = pack_conv(h, pk, p + ".3.conv.weight", co, co, 3);
+      d.bias = pack_vec(h, pk, p + ".3.conv.bias", co);
+      d.out = new_buf(h, L / 2, co);
+      h->ops.push_back(d);
+      h->flops_per_sample += 2LL * co * co * 3 * (L / 2);
+      x = d.out; L /= 2;
+    }
+  }
+  x = add_res_block(h, pk, "mid_block1", x, BUF_NONE, xc, 0, xc, L, cursor, tembW, tembB);
+  x = add_res_block(h, pk, "mid_block2", x, BUF_NONE, xc, 0, xc, L, cursor, tembW, tembB);
+  for (int u = 0; u < n - 1; ++u) {
+    int ci = h->chans[n - 1 - u];
+    std::string p = "ups." + std::to_string(u);
+    int sk = skips.back(), sc = skipC.back();
+    skips.pop_back(); skipC.pop_back(); skipL.pop_back();
+    x = add_res_block(h, pk, p + ".0", x, sk, xc, sc, ci, L, cursor, tembW, tembB);  // cat((x, skip), dim=1)
+    x = add_res_block(h, pk, p + ".1", x, BUF_NONE, ci, 0, ci, L, cursor, tembW, tembB);
+    xc = ci;
+    LayerOp t;
+    t.in0 = x; t.C0 = ci; t.Lin = L; t.Lout = 2 * L; t.Cout = ci; t.taps = 4; t.stride = 2; t.pad = 1; t.transposed = 1;
+    t.W = pack_convT(h, pk, p + ".3.conv.weight", ci, ci, 4);
+    t.bias = pack_vec(h, pk, p + ".3.conv.bias", ci);
+    t.out = new_buf(h, 2 * L, ci);
+    h->ops.push_back(t);
+    h->flops_per_sample += 2LL * ci * ci * 4 * L;
+    x = t.out; L *= 2;
+  }
+  if (cursor != h->temb_total) return B2P_ERR_INVALID_ARG;
+  {  // head: Conv1dBlock(fin, fin, 5) + 1x1 conv, fused
+    const bool cls = h->cfg.guidance == B2P_CLASSIFIER_GUIDANCE;
+    std::string p = cls ? "act_conv" : "final_conv";
+    int fin = h->chans[1];
+    if (fin != 64) return B2P_ERR_INVALID_ARG;  // fused head needs the whole channel vector in one tile
+    LayerOp f;
+    f.in0 = x; f.C0 = fin; f.Lin = f.Lout = L; f.Cout = fin; f.taps = 5; f.stride = 1; f.pad = 2;
+    f.W = pack_conv(h, pk, p + ".0.block.0.weight", fin, fin, 5);
+    f.bias = pack_vec(h, pk, p + ".0.block.0.bias", fin);
+    f.gamma = pack_vec(h, pk, p + ".0.block.2.weight", fin);
+    f.beta = pack_vec(h, pk, p + ".0.block.2.bias", fin);
+    h->head_dim = cls ? 3 : h->D;
+    std::vector<float> hw((size_t)fin * h->head_dim);
+    pack_linear_T(W(h, p + ".1.weight"), h->head_dim, fin, hw.data(), h->head_dim, 0);
+    f.headW = pk.push(hw.data(), hw.size());
+    f.headB = pack_vec(h, pk, p + ".1.bias", h->head_dim);
+    f.head_dim = h->head_dim;
+    h->ops.push_back(f);
+    h->flops_per_sample += 2LL * fin * fin * 5 * L + 2LL * h->head_dim * fin * L;
+  }
+  h->o_tembW = pk.push(tembW.data(), tembW.size());
+  h->o_tembB = pk.push(tembB.data(), tembB.size());
+  return B2P_OK;
+}
+
+void build_trajpred(b2p_handle_s* h, Packer& pk, std::vector<size_t>& offs) {
+  // offsets recorded in order; resolved to device pointers after upload
+  const int hd = 64, S = h->H - 1;
+  auto lin_t = [&](const std::string& key, int out, int in) {
+    std::vector<float> t((size_t)in * out);
+    pack_linear_T(W(h, key), out, in, t.data(), out, 0);
+    return pk.push(t.data(), t.size());
+  };
+  offs.push_back(lin_t("state_pred.input_proj.weight", hd, 3));
+  offs.push_back(pack_vec(h, pk, "state_pred.input_proj.bias", hd));
+  {  // positional table: SinusoidalPosEmb(64)(arange(S)) (modeling/helpers.py:54)
+    std::vector<float> pos((size_t)S * hd);
+    const int half = hd / 2;
+    float sc = (float)(-(log(10000.0) / (half - 1)));
+    for (int s = 0; s < S; ++s)
+      for (int i = 0; i < half; ++i) {
+        float f = expf((float)i * sc);
+        float arg = (float)s * f;
+        pos[(size_t)s * hd + i] = sinf(arg);
+        pos[(size_t)s * hd + half + i] = cosf(arg);
+      }
+    offs.push_back(pk.push(pos.data(), pos.size()));
+  }
+  for (int l = 0; l < 2; ++l) {
+    std::string p = "state_pred.encoder_traj.layers." + std::to_string(l);
+    offs.push_back(lin_t(p + ".self_attn.in_proj_weight", 3 * hd, hd));
+    offs.push_back(pack_vec(h, pk, p + ".self_attn.in_proj_bias", 3 * hd));
+    offs.push_back(lin_t(p + ".self_attn.out_proj.weight", hd, hd));
+    offs.push_back(pack_vec(h, pk, p + ".self_attn.out_proj.bias", hd));
+    offs.push_back(lin_t(p + ".linear1.weight", 4 * hd, hd));
+    offs.push_back(pack_vec(h, pk, p + ".linear1.bias", 4 * hd));
+    offs.push_back(lin_t(p + ".linear2.weight", hd, 4 * hd));
+    offs.push_back(pack_vec(h, pk, p + ".linear2.bias", hd));
+    offs.push_back(pack_vec(h, pk, p + ".norm1.weight", hd));
+    offs.push_back(pack_vec(h, pk, p + ".norm1.bias", hd));
+    offs.push_back(pack_vec(h, pk, p + ".norm2.weight", hd));
+    offs.push_back(pack_vec(h, pk, p + ".norm2.bias", hd));
+    offs.push_back(pack_vec(h, pk, p + ".self_attn.in_proj_weight", (size_t)3 * hd * hd));
+    offs.push_back(pack_vec(h, pk, p + ".self_attn.out_proj.weight", (size_t)hd * hd));
+    offs.push_back(pack_vec(h, pk, p + ".linear1.weight", (size_t)4 * hd * hd));
+    offs.push_back(pack_vec(h, pk, p + ".linear2.weight", (size_t)4 * hd * hd));
+  }
+  offs.push_back(pack_vec(h, pk, "state_pred.encoder_traj.norm.weight", hd));
+  offs.push_back(pack_vec(h, pk, "state_pred.encoder_traj.norm.bias", hd));
+  offs.push_back(lin_t("state_pred.output_proj.weight", h->D - 3, hd));
+  offs.push_back(pack_vec(h, pk, "state_pred.output_proj.bias", h->D - 3));
+  offs.push_back(pack_vec(h, pk, "state_pred.output_proj.weight", (size_t)(h->D - 3) * hd));
+  offs.push_back(pack_vec(h, pk, "state_pred.input_proj.weight", (size_t)hd * 3));
+}
+
+void resolve_trajpred(b2p_handle_s* h, const std::vector<size_t>& o) {
+  const float* b = h->d_pack;
+  size_t i = 0;
+  TrajPredWeights& w = h->tp;
+  w.in_w = b + o[i++]; w.in_b = b + o[i++]; w.pos = b + o[i++];
+  w.n_layers = 2;
+  for (int l = 0; l < 2; ++l) {
+    auto& y = w.layer[l];
+    y.qkv_wt = b + o[i++]; y.qkv_b = b + o[i++]; y.out_wt = b + o[i++]; y.out_b = b + o[i++];
+    y.l1_wt = b + o[i++]; y.l1_b = b + o[i++]; y.l2_wt = b + o[i++]; y.l2_b = b + o[i++];
+    y.n1_g = b + o[i++]; y.n1_b = b + o[i++]; y.n2_g = b + o[i++]; y.n2_b = b + o[i++];
+    y.qkv_w = b + o[i++]; y.out_w = b + o[i++]; y.l1_w = b + o[i++]; y.l2_w = b + o[i++];
+  }
+  w.fn_g = b + o[i++]; w.fn_b = b + o[i++]; w.out_wt = b + o[i++]; w.out_b = b + o[i++]; w.out_w = b + o[i++];
+  w.in_w_raw = b + o[i++];
+  h->has_tp = true;
+}
+
+void drop_graphs(b2p_handle_s* h) {
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
+int ensure_workspace(b2p_handle_s* h, int rows) {
+  if (rows <= h->cap) return B2P_OK;
+  drop_graphs(h);
+  if (h->d_ws) { B2P_CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; }
+  int cap = rows;
+  size_t per = (size_t)h->dim + 2 * h->dim + h->temb_total + h->buf_floats_per_sample;
+  size_t floats = per * cap + 64 * 8;
+  B2P_CUDA_TRY(cudaMalloc((void**)&h->d_ws, floats * sizeof(float) + sizeof(int64_t) * (cap + 8)));
+  float* p = h->d_ws;
+  auto take = [&](size_t n) { float* r = p; p += (n + 63) & ~(size_t)63; return r; };
+  h->d_time_embed = take((size_t)cap * h->dim);
+  h->d_mish_cond = take((size_t)cap * 2 * h->dim);
+  h->d_temb = take((size_t)cap * h->temb_total);
+  h->d_act = take((size_t)cap * h->buf_floats_per_sample);
+  h->d_t = reinterpret_cast<int64_t*>(h->d_ws + floats);
+  h->cap = cap;
+  return B2P_OK;
+}
+
+inline const float* buf_ptr(b2p_handle_s* h, int id, const float* x) {
+  if (id == BUF_X) return x;
+  if (id == BUF_NONE) return nullptr;
+  return h->d_act + h->bufs[id].off * (size_t)h->cap;
+}
+
+// the denoiser on `rows` batch rows; x rows may repeat with period x_period (CFG feeds [x; x])
+int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, int feat_rows, const int64_t* t, int t_count,
+             const float* cond, float* head_out, float* time_embed_out, int rows, cudaStream_t s, int64_t* launches) {
+  if (!h->finalized) return h->fail(B2P_ERR_NOT_FINALIZED, "weights not finalized");
+  int rc = ensure_workspace(h, rows);
+  if (rc) return rc;
+  const float* P = h->d_pack;
+  EmbedArgs e{};
+  e.t = t; e.t_count = t_count; e.feat = feat; e.feat_rows = feat_rows; e.cond = cond;
+  e.use_cond = h->cfg.guidance == B2P_FREE_GUIDANCE;
+  e.w1t = P + h->o_w1t; e.b1 = P + h->o_b1; e.w3t = P + h->o_w3t; e.b3 = P + h->o_b3;
+  if (e.use_cond) { e.wc0t = P + h->o_wc0t; e.bc0 = P + h->o_bc0; e.wc2t = P + h->o_wc2t; e.bc2 = P + h->o_bc2; }
+  e.time_embed = time_embed_out ? time_embed_out : h->d_time_embed;
+  e.mish_cond = h->d_mish_cond; e.B = rows; e.dim = h->dim;
+  if ((rc = launch_embed(e, s))) return rc;
+  ++*launches;
+  {  // all 16 block time-MLPs as one GEMM [rows,128] x [128, temb_total]
+    ConvArgs a{};
+    a.x0 = h->d_mish_cond; a.C0 = 2 * h->dim; a.Lin = a.Lout = 1; a.log2Lout = 0; a.nrows = rows; a.Cout = h->temb_total;
+    a.taps = 1; a.jmin = a.jmax = 0; a.stride = 1; a.W = P + h->o_tembW; a.bias = P + h->o_tembB; a.out = h->d_temb;
+    if ((rc = launch_conv_ffma(a, s))) return rc;
+    ++*launches;
+  }
+  for (const LayerOp& op : h->ops) {
+    ConvArgs a{};
+    a.x0 = buf_ptr(h, op.in0, x); a.x1 = buf_ptr(h, op.in1, x); a.C0 = op.C0; a.C1 = op.C1;
+    a.x0_period = (op.in0 == BUF_X) ? x_period : 0;
+    a.Lin = op.Lin; a.Lout = op.Lout; a.log2Lout = ilog2(op.Lout); a.nrows = rows * op.Lout; a.Cout = op.Cout;
+    a.taps = op.taps; a.stride = op.stride; a.pad = op.pad; a.transposed = op.transposed;
+    // taps that can reach a valid input position for at least one output position
+    a.jmin = 0; a.jmax = op.taps - 1;
+    if (!op.transposed && op.stride == 1) {
+      a.jmin = op.pad - (op.Lout - 1) > 0 ? op.pad - (op.Lout - 1) : 0;
+      a.jmax = op.pad + op.Lin - 1 < op.taps - 1 ? op.pad + op.Lin - 1 : op.taps - 1;
+    }
+    a.W = P + op.W; a.bias = P + op.bias;
+    if (op.gamma != NPOS) { a.gn_gamma = P + op.gamma; a.gn_beta = P + op.beta; a.cg = op.Cout / 8; }
+    if (op.temb_off >= 0) { a.temb = h->d_temb + op.temb_off; a.temb_stride = h->temb_total; }
+    a.res_id = buf_ptr(h, op.res_id, x);
+    if (op.resW != NPOS) {
+      a.rx0 = buf_ptr(h, op.rin0, x); a.rx1 = buf_ptr(h, op.rin1, x); a.RC0 = op.RC0; a.RC1 = op.RC1;
+      a.rx0_period = (op.rin0 == BUF_X) ? x_period : 0;
+      a.resW = P + op.resW; a.resB = P + op.resB;
+    }
+    if (op.headW != NPOS) { a.headW = P + op.headW; a.headB = P + op.headB; a.head_dim = op.head_dim; a.head_out = head_out; }
+    a.out = op.out == BUF_NONE ? nullptr : const_cast<float*>(buf_ptr(h, op.out, x));
+    if ((rc = launch_conv_ffma(a, s))) return h->fail(rc, "conv launch failed");
+    ++*launches;
+  }
+  return B2P_OK;
+}
+
+}  // namespace
+
+// ================================================= C ABI ====================================================
+extern "C" {
+
+int b2p_abi_version(void) { return B2P_ABI_VERSION; }
+
+const char* b2p_status_string(int st) {
+  switch (st) {
+    case B2P_OK: return "ok";
+    case B2P_ERR_INVALID_ARG: return "invalid argument";
+    case B2P_ERR_UNKNOWN_WEIGHT: return "unknown state_dict key";
+    case B2P_ERR_BAD_SHAPE: return "weight numel mismatch";
+    case B2P_ERR_NOT_FINALIZED: return "weights not finalized";
+    case B2P_ERR_MISSING_WEIGHT: return "missing weights";
+    case B2P_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+    case B2P_ERR_STATE: return "invalid call sequence";
+    default: return st > 0 ? cudaGetErrorString((cudaError_t)st) : "unknown";
+  }
+}
+
+const char* b2p_last_error(b2p_handle h) { return h ? h->err.c_str() : ""; }
+
+int b2p_create(const b2p_model_config* cfg, int device, b2p_handle* out) {
+  if (!cfg || !out) return B2P_ERR_INVALID_ARG;
+  if (cfg->n_mults < 2 || cfg->n_mults > 6 || cfg->dim % 64 != 0 || cfg->dim > 256 || cfg->transition_dim < 4 ||
+      cfg->transition_dim > 16 || cfg->guidance < 0 || cfg->guidance > 2)
+    return B2P_ERR_INVALID_ARG;
+  int down = 1 << (cfg->n_mults - 1);
+  if (cfg->horizon % down != 0 || cfg->horizon > 64 || (cfg->horizon & (cfg->horizon - 1)) != 0) return B2P_ERR_INVALID_ARG;
+  if ((cfg->horizon * cfg->transition_dim) % 4 != 0) return B2P_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return B2P_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  B2P_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return B2P_ERR_NO_DEVICE;  // sm_100a cubin only: no fallback
+  B2P_CUDA_TRY(cudaSetDevice(device));
+  b2p_handle_s* h = new b2p_handle_s();
+  h->cfg = *cfg; h->device = device;
+  h->H = cfg->horizon; h->D = cfg->transition_dim; h->dim = cfg->dim; h->nlev = cfg->n_mults;
+  h->chans[0] = h->D;
+  h->temb_total = 0;
+  for (int i = 0; i < h->nlev; ++i) {
+    h->chans[i + 1] = cfg->dim * cfg->dim_mults[i];
+    if (h->chans[i + 1] % 64 != 0) { delete h; return B2P_ERR_INVALID_ARG; }
+  }
+  for (int i = 0; i < h->nlev; ++i) h->temb_total += 2 * h->chans[i + 1];       // downs
+  h->temb_total += 2 * h->chans[h->nlev];                                         // mid
+  for (int u = 0; u < h->nlev - 1; ++u) h->temb_total += 2 * h->chans[h->nlev - 1 - u];  // ups
+  build_slots(h);
+  {  // sinusoidal frequencies, fp32 as torch computes them (modeling/helpers.py:69-71)
+    int half = h->dim / 2;
+    std::vector<float> f(half);
+    float sc = (float)(-(log(10000.0) / (half - 1)));
+    for (int i = 0; i < half; ++i) f[i] = expf((float)i * sc);
+    int rc = upload_freq_table(f.data(), half);
+    if (rc) { delete h; return rc; }
+  }
+  cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+  *out = h;
+  return B2P_OK;
+}
+
+int b2p_destroy(b2p_handle h) {
+  if (!h) return B2P_OK;
+  cudaSetDevice(h->device);
+  drop_graphs(h);
+  if (h->d_pack) cudaFree(h->d_pack);
+  if (h->d_ws) cudaFree(h->d_ws);
+  if (h->p_x) cudaFree(h->p_x);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  delete h;
+  return B2P_OK;
+}
+
+int b2p_num_weights(b2p_handle h) { return h ? (int)h->slots.size() : 0; }
+
+int b2p_weight_info(b2p_handle h, int i, const char** key, int64_t* numel) {
+  if (!h || i < 0 || i >= (int)h->slots.size()) return B2P_ERR_INVALID_ARG;
+  if (key) *key = h->slots[i].key.c_str();
+  if (numel) *numel = h->slots[i].numel;
+  return B2P_OK;
+}
+
+int b2p_load_weight(b2p_handle h, const char* key, const float* data, int64_t numel) {
+  if (!h || !key || !data) return B2P_ERR_INVALID_ARG;
+  auto it = h->index.find(key);
+  if (it == h->index.end()) return h->fail(B2P_ERR_UNKNOWN_WEIGHT, std::string("unknown key ") + key);
+  Slot& s = h->slots[it->second];
+  if (s.numel != numel) return h->fail(B2P_ERR_BAD_SHAPE, std::string("numel mismatch for ") + key);
+  s.host.assign(data, data + numel);
+  s.set = true;
+  h->finalized = false;
+  return B2P_OK;
+}
+
+int b2p_finalize_weights(b2p_handle h) {
+  if (!h) return B2P_ERR_INVALID_ARG;
+  for (auto& s : h->slots)
+    if (!s.set) return h->fail(B2P_ERR_MISSING_WEIGHT, "missing key " + s.key);
+  B2P_CUDA_TRY(cudaSetDevice(h->device));
+  int rc = build_program(h);
+  if (rc) return h->fail(rc, "unsupported architecture");
+  std::vector<size_t> tp_offs;
+  if (h->cfg.guidance == B2P_CLASSIFIER_GUIDANCE) {
+    Packer pk{h->pack_host};
+    build_trajpred(h, pk, tp_offs);
+  }
+  drop_graphs(h);
+  if (h->d_pack) { B2P_CUDA_TRY(cudaFree(h->d_pack)); h->d_pack = nullptr; }
+  B2P_CUDA_TRY(cudaMalloc((void**)&h->d_pack, h->pack_host.size() * sizeof(float)));
+  B2P_CUDA_TRY(cudaMemcpy(h->d_pack, h->pack_host.data(), h->pack_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (!tp_offs.empty()) resolve_trajpred(h, tp_offs);
+  // workspace offsets depend on the buffer table: force re-allocation
+  if (h->d_ws) { B2P_CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; h->cap = 0; }
+  h->finalized = true;
+  return B2P_OK;
+}
+
+int b2p_set_precision(b2p_handle h, int precision) {
+  if (!h || precision < 0 || precision > 2) return B2P_ERR_INVALID_ARG;
+  if (precision != B2P_PREC_FP32) return h->fail(B2P_ERR_INVALID_ARG, "tensor-core precisions are not built in this version");
+  h->cfg.precision = precision;
+  drop_graphs(h);
+  return B2P_OK;
+}
+
+int64_t b2p_last_launch_count(b2p_handle h) { return h ? h->last_launches : 0; }
+int64_t b2p_unet_flops_per_sample(b2p_handle h) { return h ? h->flops_per_sample : 0; }
+int64_t b2p_weight_bytes(b2p_handle h) { return h ? (int64_t)(h->pack_host.size() * sizeof(float)) : 0; }
+
+int b2p_unet_forward(b2p_handle h, const float* x, const float* feat, int32_t feat_rows, const int64_t* t, int32_t t_count,
+                     const float* cond, float* out, float* action_out, float* time_embed_out, int32_t B, void* stream) {
+  if (!h || !x || !feat || !t || B <= 0) return B2P_ERR_INVALID_ARG;
+  if (feat_rows <= 0 || B % feat_rows != 0 || t_count <= 0 || B % t_count != 0) return h->fail(B2P_ERR_INVALID_ARG, "feat/t rows must divide B");
+  B2P_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t n = 0;
+  int rc;
+  if (h->cfg.guidance != B2P_CLASSIFIER_GUIDANCE) {
+    if (!out) return B2P_ERR_INVALID_ARG;
+    rc = run_unet(h, x, 0, feat, feat_rows, t, t_count, cond, out, time_embed_out, B, s, &n);
+  } else {
+    rc = ensure_workspace(h, B);
+    if (rc) return rc;
+    // action lands in a scratch [B,H,3] unless the caller wants it
+    float* act = action_out;
+    float* scratch = nullptr;
+    if (!act) { B2P_CUDA_TRY(cudaMallocAsync((void**)&scratch, sizeof(float) * B * h->H * 3, s)); act = scratch; }
+    float* te = time_embed_out ? time_embed_out : h->d_time_embed;
+    rc = run_unet(h, x, 0, feat, feat_rows, t, t_count, cond, act, te, B, s, &n);
+    if (!rc && out) {
+      // out = cat[ cat[0, state_pred(action[:, :-1], te)], action ]  (modeling/temporal.py:237-241)
+      rc = launch_state_pred(h->tp, act, te, out, 1, B, h->H, h->D, s);
+      ++n;
+    }
+    if (scratch) B2P_CUDA_TRY(cudaFreeAsync(scratch, s));
+  }
+  h->last_launches = n;
+  return rc;
+}
+
+int b2p_state_pred(b2p_handle h, const float* action, const float* time_embed, float* state, int32_t B, void* stream) {
+  if (!h || !action || !time_embed || !state || B <= 0) return B2P_ERR_INVALID_ARG;
+  if (!h->finalized || !h->has_tp) return h->fail(B2P_ERR_STATE, "model has no state predictor");
+  B2P_CUDA_TRY(cudaSetDevice(h->device));
+  // state [B, H-1, D-3]: dense rows, no zero row, no action columns
+  return launch_state_pred(h->tp, action, time_embed, state, 0, B, h->H, h->D, (cudaStream_t)stream);
+}
+
+int b2p_state_pred_vjp(b2p_handle h, const float* action, const float* time_embed, const float* grad_state, float* grad_action,
+                       int32_t B, void* stream) {
+  if (!h || !action || !time_embed || !grad_state || !grad_action || B <= 0) return B2P_ERR_INVALID_ARG;
+  if (!h->finalized || !h->has_tp) return h->fail(B2P_ERR_STATE, "model has no state predictor");
+  B2P_CUDA_TRY(cudaSetDevice(h->device));
+  return launch_state_pred_vjp(h->tp, action, time_embed, grad_state, grad_action, B, h->H, h->D, (cudaStream_t)stream);
+}
+
+int b2p_classifier_guidance(b2p_handle h, float* model_output, const float* time_embed, const float* target, float grad_scale,
+                            float classifier_scale, int32_t B, void* stream) {
+  if (!h || !model_output || !time_embed || !target || B <= 0) return B2P_ERR_INVALID_ARG;
+  if (!h->finalized || !h->has_tp) return h->fail(B2P_ERR_STATE, "model has no state predictor");
+  B2P_CUDA_TRY(cudaSetDevice(h->device));
+  return launch_classifier_guidance(h->tp, model_output, time_embed, target, grad_scale, classifier_scale, B, h->H, h->D,
+                                    (cudaStream_t)stream);
+}
+
+// ------------------------------------------------ plan ---------------------------------------------------
+static int ensure_plan_buffers(b2p_handle h, int B, int T) {
+  if (B <= h->plan_capB && T <= h->plan_capT) return B2P_OK;
+  drop_graphs(h);
+  if (h->p_x) { B2P_CUDA_TRY(cudaFree(h->p_x)); h->p_x = nullptr; }
+  int cb = B > h->plan_capB ? B : h->plan_capB, ct = T > h->plan_capT ? T : h->plan_capT;
+  size_t hd = (size_t)h->H * h->D;
+  size_t floats = (size_t)cb * (hd * 6 + h->dim + 2 + 4 + (size_t)h->H * 3) + (size_t)ct * cb * hd + 64 * 16;
+  B2P_CUDA_TRY(cudaMalloc((void**)&h->p_x, floats * sizeof(float) + sizeof(int64_t) * (ct + 8)));
+  float* p = h->p_x;
+  auto take = [&](size_t n) { float* r = p; p += (n + 63) & ~(size_t)63; return r; };
+  take(cb * hd);  // p_x itself
+  h->p_feat = take((size_t)cb * h->dim);
+  h->p_target = take((size_t)cb * 2);
+  h->p_cond = take((size_t)cb * 4);
+  h->p_traj = take(cb * hd);
+  h->p_mask = take(cb * hd);
+  h->p_mo = take(2 * cb * hd);
+  h->p_action = take((size_t)cb * h->H * 3);
+  h->p_out = take(cb * hd);
+  h->p_noise = take((size_t)ct * cb * hd);
+  h->p_tsteps = reinterpret_cast<int64_t*>(h->p_x + floats);
+  h->plan_capB = cb; h->plan_capT = ct;
+  return B2P_OK;
+}
+
+// enqueue the T-step loop on s, reading/writing the handle's static plan buffers
+static int enqueue_plan(b2p_handle h, const b2p_plan_config& pc, const GraphKey& k, cudaStream_t s, int64_t* launches) {
+  const int B = k.B, T = k.T;
+  const size_t hd = (size_t)h->H * h->D;
+  std::vector<float> ac(pc.sched.num_train_timesteps);
+  static const char* kSched[3] = {"squaredcos_cap_v2", "linear", "scaled_linear"};
+  if (pc.sched.beta_schedule < 0 || pc.sched.beta_schedule > 2) return B2P_ERR_INVALID_ARG;
+  int rc = b2p_alphas_cumprod(kSched[pc.sched.beta_schedule], pc.sched.num_train_timesteps, pc.sched.beta_start,
+                              pc.sched.beta_end, ac.data());
+  if (rc) return rc;
+  const int g = h->cfg.guidance;
+  const bool inpaint = pc.sched.kind == B2P_SCHED_INPAINT_DDIM || pc.sched.kind == B2P_SCHED_INPAINT_DDPM;
+  for (int i = 0; i < T; ++i) {
+    int t = (T - 1 - i) * (pc.sched.num_train_timesteps / T);
+    b2p_step_coeffs kc;
+    if ((rc = b2p_step_coeffs_compute(&pc.sched, ac.data(), T, t, pc.eta, &kc))) return rc;
+    const int64_t* tp = h->p_tsteps + i;
+    const float* mo = h->p_mo;
+    const float* mo_u = nullptr;
+    if (g == B2P_FREE_GUIDANCE) {
+      // rows [0,B) conditional, [B,2B) unconditional (interact.py:119-127, 134-141)
+      if ((rc = run_unet(h, h->p_x, B, h->p_feat, B, tp, 1, h->p_cond, h->p_mo, nullptr, 2 * B, s, launches))) return rc;
+      mo_u = h->p_mo + (size_t)B * hd;
+    } else if (g == B2P_CLASSIFIER_GUIDANCE) {
+      if ((rc = run_unet(h, h->p_x, 0, h->p_feat, B, tp, 1, nullptr, h->p_action, h->d_time_embed, B, s, launches))) return rc;
+      if ((rc = launch_state_pred(h->tp, h->p_action, h->d_time_embed, h->p_mo, 1, B, h->H, h->D, s))) return rc;
+      ++*launches;
+      if (!inpaint && k.has_target) {
+        if ((rc = launch_classifier_guidance(h->tp, h->p_mo, h->d_time_embed, h->p_target, kc.guidance_grad_scale,
+                                             pc.classifier_scale, B, h->H, h->D, s))) return rc;
+        ++*launches;
+      }
+    } else {
+      if ((rc = run_unet(h, h->p_x, 0, h->p_feat, B, tp, 1, nullptr, h->p_mo, nullptr, B, s, launches))) return rc;
+    }
+    int flags = B2P_STEP_ZERO_FIRST_WAYPOINT;
+    bool last = (i == T - 1);
+    if (last && pc.postprocess) flags |= B2P_STEP_FINAL_POSTPROCESS;
+    SchedLaunch L{pc.sched, kc, mo, mo_u, pc.free_scale, h->p_x, k.has_noise ? h->p_noise + (size_t)i * B * hd : nullptr,
+                  (inpaint && k.has_traj) ? h->p_traj : nullptr, (inpaint && k.has_mask) ? h->p_mask : nullptr,
+                  last ? h->p_out : h->p_x, nullptr, B, h->H, h->D, pc.eta, pc.magic_num, flags};
+    if ((rc = launch_sched_step(L, s))) return rc;
+    ++*launches;
+  }
+  return B2P_OK;
+}
+
+__global__ void zero_first_waypoint_kernel(float* x, int B, int HD) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * 3) x[(size_t)(i / 3) * HD + (i % 3)] = 0.f;
+}
+
+static int plan_impl(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const float* feat, const float* target,
+                     const float* noise, const float* traj, const float* mask, float* out, int B, cudaStream_t s, bool host) {
+  if (!h || !pc || !x_init || !feat || !out || B <= 0) return B2P_ERR_INVALID_ARG;
+  if (!h->finalized) return h->fail(B2P_ERR_NOT_FINALIZED, "weights not finalized");
+  const int T = pc->num_inference_steps;
+  if (T <= 0 || T > pc->sched.num_train_timesteps) return h->fail(B2P_ERR_INVALID_ARG, "bad num_inference_steps");
+  const int g = h->cfg.guidance;
+  if (g == B2P_FREE_GUIDANCE && !target) return h->fail(B2P_ERR_INVALID_ARG, "FREE_GUIDANCE needs a target");
+  const bool ddpm = pc->sched.kind == B2P_SCHED_GUIDANCE_DDPM || pc->sched.kind == B2P_SCHED_INPAINT_DDPM;
+  const bool inpaint = pc->sched.kind == B2P_SCHED_INPAINT_DDIM || pc->sched.kind == B2P_SCHED_INPAINT_DDPM;
+  if ((ddpm || (inpaint && traj && mask) || pc->eta > 0.f) && !noise && T > 1)
+    return h->fail(B2P_ERR_INVALID_ARG, "this scheduler consumes noise: pass noise [T,B,H,D]");
+  B2P_CUDA_TRY(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = ensure_plan_buffers(h, B, T))) return rc;
+  if ((rc = ensure_workspace(h, g == B2P_FREE_GUIDANCE ? 2 * B : B))) return rc;
+  const size_t hd = (size_t)h->H * h->D;
+  const cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  B2P_CUDA_TRY(cudaMemcpyAsync(h->p_x, x_init, sizeof(float) * B * hd, kind, s));
+  B2P_CUDA_TRY(cudaMemcpyAsync(h->p_feat, feat, sizeof(float) * B * h->dim, kind, s));
+  if (target) {
+    B2P_CUDA_TRY(cudaMemcpyAsync(h->p_target, target, sizeof(float) * B * 2, kind, s));
+    if (g == B2P_FREE_GUIDANCE) {  // cond = cat[target, zeros]
+      B2P_CUDA_TRY(cudaMemcpyAsync(h->p_cond, target, sizeof(float) * B * 2, kind, s));
+      B2P_CUDA_TRY(cudaMemsetAsync(h->p_cond + (size_t)B * 2, 0, sizeof(float) * B * 2, s));
+    }
+  }
+  if (noise) B2P_CUDA_TRY(cudaMemcpyAsync(h->p_noise, noise, sizeof(float) * T * B * hd, kind, s));
+  if (traj) B2P_CUDA_TRY(cudaMemcpyAsync(h->p_traj, traj, sizeof(float) * B * hd, kind, s));
+  if (mask) B2P_CUDA_TRY(cudaMemcpyAsync(h->p_mask, mask, sizeof(float) * B * hd, kind, s));
+  zero_first_waypoint_kernel<<<(B * 3 + 127) / 128, 128, 0, s>>>(h->p_x, B, (int)hd);  // interact.py:129
+
+  GraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.B = B; key.T = T; key.kind = pc->sched.kind; key.has_target = target != nullptr; key.has_noise = noise != nullptr;
+  key.has_traj = traj != nullptr; key.has_mask = mask != nullptr; key.pc = *pc;
+  int64_t launches = 1;
+  if (pc->use_graph) {
+    GraphEntry* ge = nullptr;
+    for (auto& e : h->graphs) if (e.key == key) { ge = &e; break; }
+    if (!ge) {
+      std::vector<int64_t> ts(T);
+      b2p_timesteps(pc->sched.num_train_timesteps, T, ts.data());
+      B2P_CUDA_TRY(cudaMemcpyAsync(h->p_tsteps, ts.data(), sizeof(int64_t) * T, cudaMemcpyHostToDevice, s));
+      B2P_CUDA_TRY(cudaStreamSynchronize(s));
+      cudaGraph_t graph;
+      int64_t nl = 0;
+      B2P_CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue_plan(h, *pc, key, h->cap_stream, &nl);
+      cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+      if (rc) { if (ce == cudaSuccess) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return (int)ce;
+      cudaGraphExec_t exec;
+      ce = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) return (int)ce;
+      h->graphs.push_back(GraphEntry{key, exec, nl});
+      ge = &h->graphs.back();
+    }
+    B2P_CUDA_TRY(cudaGraphLaunch(ge->exec, s));
+    launches += ge->launches;
+  } else {
+    std::vector<int64_t> ts(T);
+    b2p_timesteps(pc->sched.num_train_timesteps, T, ts.data());
+    B2P_CUDA_TRY(cudaMemcpyAsync(h->p_tsteps, ts.data(), sizeof(int64_t) * T, cudaMemcpyHostToDevice, s));
+    B2P_CUDA_TRY(cudaStreamSynchronize(s));  // ts is a stack vector
+    if ((rc = enqueue_plan(h, *pc, key, s, &launches))) return rc;
+  }
+  B2P_CUDA_TRY(cudaMemcpyAsync(out, h->p_out, sizeof(float) * B * hd, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+  if (host) B2P_CUDA_TRY(cudaStreamSynchronize(s));
+  h->last_launches = launches;
+  return B2P_OK;
+}
+
+int b2p_plan(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const float* feat, const float* target,
+             const float* noise, const float* target_traj, const float* target_mask, float* out, int32_t B, void* stream) {
+  return plan_impl(h, pc, x_init, feat, target, noise, target_traj, target_mask, out, B, (cudaStream_t)stream, false);
+}
+
+int b2p_plan_host(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const float* feat, const float* target,
+                  const float* noise, const float* target_traj, const float* target_mask, float* out, int32_t B) {
+  if (!h) return B2P_ERR_INVALID_ARG;
+  return plan_impl(h, pc, x_init, feat, target, noise, target_traj, target_mask, out, B, h->cap_stream, true);
+}
+
+}  // extern "C"

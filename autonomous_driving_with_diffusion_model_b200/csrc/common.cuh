@@ -1,0 +1,109 @@
+// Internal declarations shared by the .cu files of libb200plan.  Not part of the public ABI (include/b200plan.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b200plan.h"
+
+#define B2P_CUDA_TRY(expr)                    \
+  do {                                        \
+    cudaError_t _e = (expr);                  \
+    if (_e != cudaSuccess) return (int)_e;    \
+  } while (0)
+
+namespace b2p {
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused conv layer on channels-last activations [rows = (sample, position), channels].
+// out[b, l, co] = epilogue( sum_{j, c} W[j][c][co] * in[b, pos(l, j), c] + bias[co] )
+//   plain conv :   pos = l*stride + j - pad                (Conv1d,  modeling/helpers.py:77-83, 95-112)
+//   transposed :   pos = (l + pad - j)/stride if divisible (ConvTranspose1d k4 s2 p1, modeling/helpers.py:86-92)
+// The input may be the channel concatenation of two tensors (skip connection, modeling/temporal.py:227).
+// Epilogue (all optional): GroupNorm(8)+Mish, + temb[b, co], + residual (identity or 1x1 conv of `res` inputs),
+// fused 1x1 head (final_conv.1 / act_conv.1) written as [rows, head_dim].
+// ---------------------------------------------------------------------------------------------------------
+struct ConvArgs {
+  const float* x0; const float* x1;   // inputs; x1 may be null
+  int C0, C1;                         // channels of x0 / x1
+  int x0_period, rx0_period;          // >0: sample b reads x0 row (b % period)  (CFG feeds [x; x] without a copy)
+  int Lin, Lout, log2Lout;            // positions per sample
+  int nrows;                          // B * Lout
+  int Cout;
+  int taps, jmin, jmax;               // kernel taps; only taps in [jmin, jmax] can touch a valid position
+  int stride, pad, transposed;
+  const float* W;                     // packed [taps][C0+C1][Cout]
+  const float* bias;                  // [Cout]
+  const float* gn_gamma; const float* gn_beta;  // null => no GroupNorm/Mish
+  int cg;                             // channels per group (Cout/8)
+  const float* temb; int temb_stride; // + temb[b*temb_stride + co]
+  const float* res_id;                // identity residual [nrows, Cout]
+  const float* rx0; const float* rx1; int RC0, RC1;  // residual 1x1 conv inputs (same Lout rows)
+  const float* resW; const float* resB;              // [RC0+RC1][Cout], [Cout]
+  const float* headW; const float* headB; int head_dim; float* head_out;  // [64][head_dim]
+  float* out;                         // [nrows, Cout] (may be null when only the head is wanted)
+};
+
+int launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
+
+// time / condition embedding (modeling/temporal.py:205-213 + the Mish in front of every block's time_mlp)
+struct EmbedArgs {
+  const int64_t* t; int t_count;      // timesteps, repeated to B
+  const float* feat; int feat_rows;   // [feat_rows, dim], repeated to B
+  const float* cond;                  // [B,2] or null (zeros)
+  int use_cond;                       // FREE_GUIDANCE
+  const float* w1t; const float* b1;  // time_mlp.1 transposed [dim][4dim]
+  const float* w3t; const float* b3;  // time_mlp.3 transposed [4dim][dim]
+  const float* wc0t; const float* bc0; const float* wc2t; const float* bc2;  // cond_mlp transposed
+  float* time_embed;                  // [B, dim]
+  float* mish_cond;                   // [B, 2*dim] = Mish(cat[time_embed, feat])
+  int B, dim;
+};
+int launch_embed(const EmbedArgs& a, cudaStream_t s);
+
+// scheduler
+struct SchedLaunch {
+  b2p_sched_config sc; b2p_step_coeffs k;
+  const float* mo; const float* mo_u; float cfg_scale;
+  const float* sample; const float* noise; const float* traj; const float* mask;
+  float* prev; float* x0; int B, H, D; float eta, magic; int flags;
+};
+int launch_sched_step(const SchedLaunch& a, cudaStream_t s);
+
+// TrajPredict forward / classifier guidance (trajpred.cu)
+struct TrajPredWeights {
+  const float* in_w; const float* in_b;          // [3][64] transposed, [64]
+  const float* pos;                              // [S][64] sinusoidal table
+  struct Layer {
+    const float* qkv_wt; const float* qkv_b;     // [64][192], [192]
+    const float* out_wt; const float* out_b;     // [64][64]
+    const float* l1_wt; const float* l1_b;       // [64][256]
+    const float* l2_wt; const float* l2_b;       // [256][64]
+    const float* n1_g; const float* n1_b; const float* n2_g; const float* n2_b;
+    // un-transposed copies for the backward pass
+    const float* qkv_w; const float* out_w; const float* l1_w; const float* l2_w;
+  } layer[4];
+  int n_layers;
+  const float* fn_g; const float* fn_b;          // final LayerNorm
+  const float* out_wt; const float* out_b;       // [64][4] transposed
+  const float* out_w;                            // [4][64]
+  const float* in_w_raw;                         // [64][3]
+};
+// full_output == 0: out = state [B, H-1, D-3];  == 1: out = cat[cat[0, state], action] [B, H, D] (temporal.py:237-241)
+int launch_state_pred(const TrajPredWeights& w, const float* action, const float* time_embed, float* out, int full_output,
+                      int B, int H, int D, cudaStream_t s);
+int launch_state_pred_vjp(const TrajPredWeights& w, const float* action, const float* time_embed, const float* grad_state,
+                          float* grad_action, int B, int H, int D, cudaStream_t s);
+int launch_classifier_guidance(const TrajPredWeights& w, float* model_output, const float* time_embed, const float* target,
+                               float grad_scale, float scale, int B, int H, int D, cudaStream_t s);
+
+__device__ __forceinline__ float mish_f(float x) {
+  // x * tanh(softplus(x)), softplus threshold 20 (nn.Mish); tanh(log1p(e^x)) == n/(n+2), n = e^x (e^x + 2)
+  if (x > 20.f) return x;
+  float e = expf(x);
+  float n = e * (e + 2.f);
+  return x * (n / (n + 2.f));
+}
+
+}  // namespace b2p

@@ -1,0 +1,244 @@
+// Fused scheduler step: CFG mix + x0/eps + clamp/threshold + DDIM/DDPM update + noise + inpainting blend +
+// first-waypoint overwrite + final post-process, one elementwise launch (K1 in SURVEY.md Appendix C).
+// Replaces scheduler/guidance_ddim_scheduler.py:60-173, guidance_ddpm_scheduler.py:59-178,
+// inpainting_ddim_scheduler.py:10-153, inpainting_ddpm_scheduler.py:10-146, interact.py:142-144,164,166-167.
+// Arithmetic uses the round-to-nearest intrinsics in the reference's operation order (no FMA contraction), so the
+// result is bit-identical to the fp32 CPU oracle.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b2p {
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float dvd(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+struct SchedK {
+  const float* mo; const float* mo_u; float cfg_scale;
+  const float* sample; const float* noise; const float* traj; const float* mask;
+  float* prev; float* x0_out;
+  const float* thr_s;  // per-sample dynamic threshold s (clip_mode 3)
+  int n, HD, D;
+  int ddpm, inpaint, pred, clip_mode;  // clip_mode: 0 none, 1 clamp(+-range), 2 threshold with s==1, 3 dynamic
+  float clip_range;
+  int noise_on;       // t > 0
+  int use_clipped;
+  float eta, magic; int flags;
+  b2p_step_coeffs k;
+};
+
+__device__ __forceinline__ float x0_of(const SchedK& a, float m, float x) {
+  if (a.pred == B2P_PRED_SAMPLE) return m;
+  if (a.pred == B2P_PRED_EPSILON) return dvd(sub(x, mul(a.k.sqrt_beta_prod_t, m)), a.k.sqrt_alpha_prod_t);
+  return sub(mul(a.k.sqrt_alpha_prod_t, x), mul(a.k.sqrt_beta_prod_t, m));
+}
+
+__device__ __forceinline__ float step_one(const SchedK& a, int idx, float m, float mu, float x, float nz, float tj, float mk,
+                                          float* x0_store) {
+  if (a.mo_u) m = add(mu, mul(a.cfg_scale, sub(m, mu)));  // u + s*(c - u)
+  float x0 = x0_of(a, m, x);
+  float eps = 0.f;
+  if (!a.ddpm) {
+    if (a.pred == B2P_PRED_SAMPLE) eps = dvd(sub(x, mul(a.k.sqrt_alpha_prod_t, x0)), a.k.sqrt_beta_prod_t);  // un-clamped x0
+    else if (a.pred == B2P_PRED_EPSILON) eps = m;
+    else eps = add(mul(a.k.sqrt_alpha_prod_t, m), mul(a.k.sqrt_beta_prod_t, x));
+  }
+  if (a.clip_mode == 1) x0 = clampf(x0, -a.clip_range, a.clip_range);
+  else if (a.clip_mode == 2) x0 = dvd(clampf(x0, -1.f, 1.f), 1.f);
+  else if (a.clip_mode == 3) { float s = a.thr_s[idx / a.HD]; x0 = dvd(clampf(x0, -s, s), s); }
+  *x0_store = x0;
+  float prev;
+  if (!a.ddpm) {
+    if (a.use_clipped) eps = dvd(sub(x, mul(a.k.sqrt_alpha_prod_t, x0)), a.k.sqrt_beta_prod_t);
+    float dir = mul(a.k.dir_coeff, eps);
+    prev = add(mul(a.k.sqrt_alpha_prod_t_prev, x0), dir);
+    if (a.inpaint) prev = add(prev, a.k.variance);  // quirk: scalar sigma_t^2 added as an offset
+  } else {
+    prev = add(mul(a.k.x0_coeff, x0), mul(a.k.sample_coeff, x));
+    float var_term = a.noise_on ? mul(a.k.std_dev_t, nz) : 0.f;
+    prev = add(prev, var_term);
+  }
+  if (a.inpaint && a.traj && a.mask) {
+    float kn = a.noise_on ? nz : 0.f;
+    float known = add(mul(a.k.sqrt_alpha_prod_t_prev, tj), mul(a.k.sqrt_one_minus_alpha_prod_t_prev, kn));
+    prev = add(mul(mk, known), mul(sub(1.0f, mk), prev));
+  }
+  if (!a.ddpm && a.eta > 0.f) prev = add(prev, mul(a.k.std_dev_t, nz));
+  int pos = idx % a.HD;
+  if ((a.flags & B2P_STEP_ZERO_FIRST_WAYPOINT) && pos < 3) prev = 0.f;
+  if (a.flags & B2P_STEP_FINAL_POSTPROCESS) {
+    prev = clampf(prev, -1.f, 1.f);
+    if (pos % a.D < 2) prev = mul(prev, a.magic);
+  }
+  return prev;
+}
+
+__global__ void __launch_bounds__(256) sched_step_kernel(SchedK a) {
+  int i4 = blockIdx.x * blockDim.x + threadIdx.x;
+  int base = i4 * 4;
+  if (base >= a.n) return;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 m = __ldg(reinterpret_cast<const float4*>(a.mo) + i4);
+  float4 mu = a.mo_u ? __ldg(reinterpret_cast<const float4*>(a.mo_u) + i4) : z;
+  float4 x = __ldg(reinterpret_cast<const float4*>(a.sample) + i4);
+  float4 nz = a.noise ? __ldg(reinterpret_cast<const float4*>(a.noise) + i4) : z;
+  float4 tj = a.traj ? __ldg(reinterpret_cast<const float4*>(a.traj) + i4) : z;
+  float4 mk = a.mask ? __ldg(reinterpret_cast<const float4*>(a.mask) + i4) : z;
+  float4 o, x0;
+  o.x = step_one(a, base + 0, m.x, mu.x, x.x, nz.x, tj.x, mk.x, &x0.x);
+  o.y = step_one(a, base + 1, m.y, mu.y, x.y, nz.y, tj.y, mk.y, &x0.y);
+  o.z = step_one(a, base + 2, m.z, mu.z, x.z, nz.z, tj.z, mk.z, &x0.z);
+  o.w = step_one(a, base + 3, m.w, mu.w, x.w, nz.w, tj.w, mk.w, &x0.w);
+  reinterpret_cast<float4*>(a.prev)[i4] = o;
+  if (a.x0_out) reinterpret_cast<float4*>(a.x0_out)[i4] = x0;
+}
+
+// Dynamic thresholding (sample_max_value > 1): per-sample quantile of |x0| with torch.quantile's linear
+// interpolation (guidance_ddim_scheduler.py:23-58; quirk 8: over all H*D elements).  One CTA per sample,
+// rank-by-counting (n = H*D = 112 is tiny).
+__global__ void __launch_bounds__(128) threshold_s_kernel(SchedK a, float ratio, float max_value, float* s_out) {
+  extern __shared__ float v[];
+  int b = blockIdx.x, n = a.HD;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int idx = b * n + i;
+    float m = a.mo[idx];
+    if (a.mo_u) { float mu = a.mo_u[idx]; m = add(mu, mul(a.cfg_scale, sub(m, mu))); }
+    v[i] = fabsf(x0_of(a, m, a.sample[idx]));
+  }
+  __syncthreads();
+  float rank = mul(ratio, (float)(n - 1));
+  int lo = (int)floorf(rank);
+  int hi = min(lo + 1, n - 1);
+  float w = sub(rank, (float)lo);
+  __shared__ float sel[2];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float vi = v[i];
+    int r = 0;
+    for (int j = 0; j < n; ++j) { float vj = v[j]; r += (vj < vi) || (vj == vi && j < i); }
+    if (r == lo) sel[0] = vi;
+    if (r == hi) sel[1] = vi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float lo_v = sel[0], hi_v = sel[1];
+    float d = sub(hi_v, lo_v);
+    // at::lerp: w < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w)
+    float q = (w < 0.5f) ? add(lo_v, mul(w, d)) : sub(hi_v, mul(d, sub(1.f, w)));
+    s_out[b] = fminf(fmaxf(q, 1.f), max_value);
+  }
+}
+
+int launch_sched_step(const SchedLaunch& L, cudaStream_t s) {
+  if (!L.mo || !L.sample || !L.prev || L.B <= 0) return B2P_ERR_INVALID_ARG;
+  int n = L.B * L.H * L.D;
+  if ((L.H * L.D) % 4 != 0) return B2P_ERR_INVALID_ARG;
+  SchedK a;
+  memset(&a, 0, sizeof(a));
+  a.mo = L.mo; a.mo_u = L.mo_u; a.cfg_scale = L.cfg_scale; a.sample = L.sample; a.noise = L.noise;
+  a.traj = L.traj; a.mask = L.mask; a.prev = L.prev; a.x0_out = L.x0; a.n = n; a.HD = L.H * L.D; a.D = L.D;
+  a.ddpm = (L.sc.kind == B2P_SCHED_GUIDANCE_DDPM || L.sc.kind == B2P_SCHED_INPAINT_DDPM);
+  a.inpaint = (L.sc.kind == B2P_SCHED_INPAINT_DDIM || L.sc.kind == B2P_SCHED_INPAINT_DDPM);
+  a.pred = L.sc.prediction_type;
+  a.clip_mode = L.sc.thresholding ? (L.sc.sample_max_value == 1.0f ? 2 : 3) : (L.sc.clip_sample ? 1 : 0);
+  a.clip_range = L.sc.clip_sample_range;
+  a.noise_on = L.k.t > 0;
+  a.use_clipped = (L.flags & B2P_STEP_USE_CLIPPED_OUTPUT) ? 1 : 0;
+  a.eta = L.eta; a.magic = L.magic; a.flags = L.flags; a.k = L.k;
+  bool needs_noise = (a.ddpm && a.noise_on) || (a.inpaint && a.traj && a.mask && a.noise_on) || (!a.ddpm && a.eta > 0.f);
+  if (needs_noise && !L.noise) return B2P_ERR_INVALID_ARG;
+  float* thr = nullptr;
+  if (a.clip_mode == 3) {
+    B2P_CUDA_TRY(cudaMallocAsync((void**)&thr, sizeof(float) * L.B, s));
+    threshold_s_kernel<<<L.B, 128, sizeof(float) * a.HD, s>>>(a, L.sc.dynamic_thresholding_ratio, L.sc.sample_max_value, thr);
+    a.thr_s = thr;
+  }
+  int n4 = n / 4;
+  sched_step_kernel<<<(n4 + 255) / 256, 256, 0, s>>>(a);
+  if (thr) B2P_CUDA_TRY(cudaFreeAsync(thr, s));
+  return (int)cudaGetLastError();
+}
+
+}  // namespace b2p
+
+// ------------------------------------------------------------------------------------------------------------
+// Host-side scalar arithmetic of the diffusers base classes (restated 0.28.0), fp32, in the
+// reference's operation order.  Built with -ffp-contract=off.
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int b2p_alphas_cumprod(const char* schedule, int32_t n, float beta_start, float beta_end, float* out) {
+  if (!schedule || !out || n <= 0) return B2P_ERR_INVALID_ARG;
+  std::vector<float> betas(n);
+  std::string s(schedule);
+  if (s == "squaredcos_cap_v2") {
+    auto bar = [](double u) { double c = cos((u + 0.008) / 1.008 * M_PI / 2); return c * c; };
+    for (int i = 0; i < n; ++i) {
+      double b = 1.0 - bar((double)(i + 1) / n) / bar((double)i / n);
+      betas[i] = (float)(b < 0.999 ? b : 0.999);
+    }
+  } else if (s == "linear" || s == "scaled_linear") {
+    // torch.linspace(start, end, n, dtype=float32): step = (end-start)/(n-1) in fp32, symmetric fill from both ends
+    float a = beta_start, b = beta_end;
+    if (s == "scaled_linear") { a = (float)sqrt((double)beta_start); b = (float)sqrt((double)beta_end); }
+    float step = n > 1 ? (b - a) / (float)(n - 1) : 0.f;
+    int half = n / 2;
+    for (int i = 0; i < n; ++i) betas[i] = (i < half) ? a + step * (float)i : b - step * (float)(n - 1 - i);
+    if (s == "scaled_linear") for (int i = 0; i < n; ++i) betas[i] = betas[i] * betas[i];
+  } else {
+    return B2P_ERR_INVALID_ARG;
+  }
+  // torch.cumprod on CPU accumulates fp32 inputs in double (at::acc_type) and rounds every output to fp32
+  double p = 1.0;
+  for (int i = 0; i < n; ++i) { float al = 1.0f - betas[i]; p *= (double)al; out[i] = (float)p; }
+  return B2P_OK;
+}
+
+extern "C" int b2p_timesteps(int32_t n_train, int32_t n_inf, int64_t* out) {
+  if (!out || n_inf <= 0 || n_inf > n_train) return B2P_ERR_INVALID_ARG;
+  int64_t ratio = n_train / n_inf;
+  for (int i = 0; i < n_inf; ++i) out[i] = (int64_t)(n_inf - 1 - i) * ratio;
+  return B2P_OK;
+}
+
+extern "C" int b2p_step_coeffs_compute(const b2p_sched_config* sc, const float* ac, int32_t n_inf, int32_t t, float eta,
+                                       b2p_step_coeffs* o) {
+  if (!sc || !ac || !o || n_inf <= 0 || t < 0 || t >= sc->num_train_timesteps) return B2P_ERR_INVALID_ARG;
+  memset(o, 0, sizeof(*o));
+  int p = t - sc->num_train_timesteps / n_inf;
+  float a_t = ac[t];
+  float a_p = p >= 0 ? ac[p] : 1.0f;
+  float b_t = 1.0f - a_t, b_p = 1.0f - a_p;
+  o->t = t; o->t_prev = p; o->alpha_prod_t = a_t; o->alpha_prod_t_prev = a_p;
+  o->sqrt_alpha_prod_t = sqrtf(a_t); o->sqrt_beta_prod_t = sqrtf(b_t);
+  o->sqrt_alpha_prod_t_prev = sqrtf(a_p);
+  o->sqrt_one_minus_alpha_prod_t_prev = sqrtf(1.0f - a_p);
+  float cur_a = a_t / a_p;
+  float variance = (b_p / b_t) * (1.0f - cur_a);
+  bool ddpm = (sc->kind == B2P_SCHED_GUIDANCE_DDPM || sc->kind == B2P_SCHED_INPAINT_DDPM);
+  if (ddpm) {
+    if (variance < 1e-20f) variance = 1e-20f;
+    o->variance = variance;
+    o->std_dev_t = sqrtf(variance);
+    float cur_b = 1.0f - cur_a;
+    o->x0_coeff = (sqrtf(a_p) * cur_b) / b_t;
+    o->sample_coeff = sqrtf(cur_a) * b_p / b_t;
+  } else {
+    o->variance = variance;
+    o->std_dev_t = eta * sqrtf(variance);
+    o->dir_coeff = sqrtf(1.0f - a_p - o->std_dev_t * o->std_dev_t);
+  }
+  o->guidance_grad_scale = expf(0.5f * o->variance);
+  return B2P_OK;
+}
+
+extern "C" int b2p_sched_step(const b2p_sched_config* sc, const b2p_step_coeffs* k, const float* model_output,
+                              const float* model_output_uncond, float cfg_scale, const float* sample, const float* noise,
+                              const float* target_traj, const float* target_mask, float* prev_out, float* x0_out,
+                              int32_t B, int32_t H, int32_t D, float eta, float magic_num, int32_t flags, void* stream) {
+  if (!sc || !k) return B2P_ERR_INVALID_ARG;
+  b2p::SchedLaunch L{*sc, *k, model_output, model_output_uncond, cfg_scale, sample, noise, target_traj, target_mask,
+                     prev_out, x0_out, B, H, D, eta, magic_num, flags};
+  return b2p::launch_sched_step(L, (cudaStream_t)stream);
+}
