@@ -183,9 +183,10 @@ def test_image_encoder_vs_reference_golden_and_hoisting(golden_dir):
     g = np.load(os.path.join(golden_dir, "encoder_feature.npz"))
     model, sd = get_model("NO_GUIDANCE")
     img = W.synth_image(1, seed=2).to(DEV)
-    feat = model.perception(img)
+    with torch.no_grad():
+        feat = model.perception(img)
     ref = torch.from_numpy(g["feat"])
-    assert float((feat.cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+    assert float((feat.detach().cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
     inp = W.synth_inputs(1, 0, 3)
     t = torch.tensor([10], device=DEV)
     y_img = model(inp["x"].to(DEV), img, t)            # image in: encoder runs once, feature cached
@@ -235,7 +236,8 @@ def test_classifier_guidance_kernel_vs_oracle(case):
     ref = OG.guidance_update(mo, a, target, torch.tensor(1.0003), 15.0)
     x = mo.detach().clone().to(DEV)
     h = model._handle_for(torch.device(DEV))
-    rc = _lib.load().b2p_classifier_guidance(h, _lib.ptr(x), _lib.ptr(te.to(DEV)), _lib.ptr(target.to(DEV)), 1.0003, 15.0, B, model._stream())
+    te_d, tg_d = te.to(DEV), target.to(DEV)   # keep the device tensors alive across the asynchronous launch
+    rc = _lib.load().b2p_classifier_guidance(h, _lib.ptr(x), _lib.ptr(te_d), _lib.ptr(tg_d), 1.0003, 15.0, B, model._stream())
     _lib.check(rc, h)
     assert float((x.cpu() - ref).abs().max()) <= 1e-4
 
