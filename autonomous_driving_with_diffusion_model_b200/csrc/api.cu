@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace b2p {
 int upload_freq_table(const float* f, int n);
@@ -35,6 +36,8 @@ struct LayerOp {
   size_t headW = NPOS, headB = NPOS;
   int head_dim = 0;
   int out = BUF_NONE;
+  // tensor-core copies (bf16 elements into the 16-bit pack): [taps][Cout][Cin] hi / lo, residual [Cout][RCin] hi / lo
+  size_t tcW_hi = NPOS, tcW_lo = NPOS, tcRW_hi = NPOS, tcRW_lo = NPOS;
 };
 
 struct Buf { int L, C; size_t off; };  // per-sample floats = L*C; off = prefix sum of per-sample floats
@@ -72,6 +75,9 @@ struct b2p_handle_s {
   // packed weights
   std::vector<float> pack_host;
   float* d_pack = nullptr;
+  std::vector<uint16_t> pack16_host;   // bf16 hi/lo weight copies for the tcgen05 path
+  uint16_t* d_pack16 = nullptr;
+  float* d_res0 = nullptr;             // fp32 residual projection of the first block (C_in = transition_dim)
   size_t o_w1t, o_b1, o_w3t, o_b3, o_wc0t, o_bc0, o_wc2t, o_bc2, o_tembW, o_tembB;
   TrajPredWeights tp{};
   bool has_tp = false;
@@ -159,6 +165,37 @@ void pack_linear_T(const float* w, int out, int in, float* dst, int ld, int col0
 }
 size_t pack_vec(b2p_handle_s* h, Packer& pk, const std::string& key, size_t n) { return pk.push(W(h, key), n); }
 
+// ---- bf16 hi/lo split (round-to-nearest-even), host side ----
+inline uint16_t f2bf(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf2f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+size_t alloc16(std::vector<uint16_t>& v, size_t n) {
+  size_t off = (v.size() + 127) & ~(size_t)127;   // 256-byte aligned (TMA global address alignment)
+  v.resize(off + n);
+  return off;
+}
+// Conv1d weight [Cout][Cin][k] (or ConvTranspose1d [Cin][Cout][k]) -> K-major [k][Cout][Cin] bf16 hi and lo
+void pack_conv_tc(b2p_handle_s* h, const std::string& key, int cout, int cin, int k, bool transposed, size_t* hi, size_t* lo) {
+  const float* w = W(h, key);
+  size_t n = (size_t)k * cout * cin;
+  *hi = alloc16(h->pack16_host, n);
+  *lo = alloc16(h->pack16_host, n);
+  uint16_t* ph = h->pack16_host.data() + *hi;
+  uint16_t* pl = h->pack16_host.data() + *lo;
+  for (int j = 0; j < k; ++j)
+    for (int co = 0; co < cout; ++co)
+      for (int c = 0; c < cin; ++c) {
+        float v = transposed ? w[((size_t)c * cout + co) * k + j] : w[((size_t)co * cin + c) * k + j];
+        size_t o = ((size_t)j * cout + co) * cin + c;
+        ph[o] = f2bf(v);
+        pl[o] = f2bf(v - bf2f(ph[o]));
+      }
+}
+
 int new_buf(b2p_handle_s* h, int L, int C) {
   Buf b{L, C, h->buf_floats_per_sample};
   h->buf_floats_per_sample += (size_t)L * C;
@@ -226,6 +263,7 @@ int add_res_block(b2p_handle_s* h, Packer& pk, const std::string& p, int in0, in
   LayerOp a;
   a.in0 = in0; a.in1 = in1; a.C0 = C0; a.C1 = C1; a.Lin = a.Lout = L; a.Cout = cout; a.taps = 5; a.stride = 1; a.pad = 2;
   a.W = pack_conv(h, pk, p + ".blocks.0.block.0.weight", cout, cin, 5);
+  if (cin % 64 == 0) pack_conv_tc(h, p + ".blocks.0.block.0.weight", cout, cin, 5, false, &a.tcW_hi, &a.tcW_lo);
   a.bias = pack_vec(h, pk, p + ".blocks.0.block.0.bias", cout);
   a.gamma = pack_vec(h, pk, p + ".blocks.0.block.2.weight", cout);
   a.beta = pack_vec(h, pk, p + ".blocks.0.block.2.bias", cout);
@@ -240,12 +278,14 @@ int add_res_block(b2p_handle_s* h, Packer& pk, const std::string& p, int in0, in
   LayerOp b;
   b.in0 = a.out; b.C0 = cout; b.Lin = b.Lout = L; b.Cout = cout; b.taps = 5; b.stride = 1; b.pad = 2;
   b.W = pack_conv(h, pk, p + ".blocks.1.block.0.weight", cout, cout, 5);
+  pack_conv_tc(h, p + ".blocks.1.block.0.weight", cout, cout, 5, false, &b.tcW_hi, &b.tcW_lo);
   b.bias = pack_vec(h, pk, p + ".blocks.1.block.0.bias", cout);
   b.gamma = pack_vec(h, pk, p + ".blocks.1.block.2.weight", cout);
   b.beta = pack_vec(h, pk, p + ".blocks.1.block.2.bias", cout);
   if (cin != cout) {
     b.rin0 = in0; b.rin1 = in1; b.RC0 = C0; b.RC1 = C1;
     b.resW = pack_conv(h, pk, p + ".residual_conv.weight", cout, cin, 1);
+    if (cin % 64 == 0) pack_conv_tc(h, p + ".residual_conv.weight", cout, cin, 1, false, &b.tcRW_hi, &b.tcRW_lo);
     b.resB = pack_vec(h, pk, p + ".residual_conv.bias", cout);
   } else {
     b.res_id = in0;
@@ -260,7 +300,7 @@ int add_res_block(b2p_handle_s* h, Packer& pk, const std::string& p, int in0, in
 
 int build_program(b2p_handle_s* h) {
   h->ops.clear(); h->bufs.clear(); h->buf_floats_per_sample = 0; h->flops_per_sample = 0;
-  h->pack_host.clear();
+  h->pack_host.clear(); h->pack16_host.clear();
   Packer pk{h->pack_host};
   const int dim = h->dim, n = h->nlev;
   // embedding MLPs, transposed for coalesced reads
@@ -300,6 +340,7 @@ int build_program(b2p_handle_s* h) {
       LayerOp d;
       d.in0 = x; d.C0 = co; d.Lin = L; d.Lout = L / 2; d.Cout = co; d.taps = 3; d.stride = 2; d.pad = 1;
       d.W = pack_conv(h, pk, p + ".3.conv.weight", co, co, 3);
+      pack_conv_tc(h, p + ".3.conv.weight", co, co, 3, false, &d.tcW_hi, &d.tcW_lo);
       d.bias = pack_vec(h, pk, p + ".3.conv.bias", co);
       d.out = new_buf(h, L / 2, co);
       h->ops.push_back(d);
@@ -320,6 +361,7 @@ int build_program(b2p_handle_s* h) {
     LayerOp t;
     t.in0 = x; t.C0 = ci; t.Lin = L; t.Lout = 2 * L; t.Cout = ci; t.taps = 4; t.stride = 2; t.pad = 1; t.transposed = 1;
     t.W = pack_convT(h, pk, p + ".3.conv.weight", ci, ci, 4);
+    pack_conv_tc(h, p + ".3.conv.weight", ci, ci, 4, true, &t.tcW_hi, &t.tcW_lo);
     t.bias = pack_vec(h, pk, p + ".3.conv.bias", ci);
     t.out = new_buf(h, 2 * L, ci);
     h->ops.push_back(t);
@@ -335,6 +377,7 @@ int build_program(b2p_handle_s* h) {
     LayerOp f;
     f.in0 = x; f.C0 = fin; f.Lin = f.Lout = L; f.Cout = fin; f.taps = 5; f.stride = 1; f.pad = 2;
     f.W = pack_conv(h, pk, p + ".0.block.0.weight", fin, fin, 5);
+    pack_conv_tc(h, p + ".0.block.0.weight", fin, fin, 5, false, &f.tcW_hi, &f.tcW_lo);
     f.bias = pack_vec(h, pk, p + ".0.block.0.bias", fin);
     f.gamma = pack_vec(h, pk, p + ".0.block.2.weight", fin);
     f.beta = pack_vec(h, pk, p + ".0.block.2.bias", fin);
@@ -430,8 +473,8 @@ int ensure_workspace(b2p_handle_s* h, int rows) {
   drop_graphs(h);
   if (h->d_ws) { B2P_CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; }
   int cap = rows;
-  size_t per = (size_t)h->dim + 2 * h->dim + h->temb_total + h->buf_floats_per_sample;
-  size_t floats = per * cap + 64 * 8;
+  size_t per = (size_t)h->dim + 2 * h->dim + h->temb_total + h->buf_floats_per_sample + (size_t)h->H * h->chans[1];
+  size_t floats = per * cap + 64 * 16;
   B2P_CUDA_TRY(cudaMalloc((void**)&h->d_ws, floats * sizeof(float) + sizeof(int64_t) * (cap + 8)));
   float* p = h->d_ws;
   auto take = [&](size_t n) { float* r = p; p += (n + 63) & ~(size_t)63; return r; };
@@ -439,6 +482,7 @@ int ensure_workspace(b2p_handle_s* h, int rows) {
   h->d_mish_cond = take((size_t)cap * 2 * h->dim);
   h->d_temb = take((size_t)cap * h->temb_total);
   h->d_act = take((size_t)cap * h->buf_floats_per_sample);
+  h->d_res0 = take((size_t)cap * h->H * h->chans[1]);
   h->d_t = reinterpret_cast<int64_t*>(h->d_ws + floats);
   h->cap = cap;
   return B2P_OK;
@@ -473,7 +517,86 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
     if ((rc = launch_conv_ffma(a, s))) return rc;
     ++*launches;
   }
+  const int prec = h->cfg.precision;
+  const bool tc = prec != B2P_PREC_FP32;
+  const int nsplit = prec == B2P_PREC_BF16X3 ? 2 : 1;
+  auto hi_ptr = [&](int id) -> __nv_bfloat16* {
+    return id < 0 ? nullptr : reinterpret_cast<__nv_bfloat16*>(h->d_act + h->bufs[id].off * (size_t)h->cap);
+  };
+  auto lo_ptr = [&](int id) -> __nv_bfloat16* {
+    return (id < 0 || nsplit != 2) ? nullptr : hi_ptr(id) + (size_t)h->bufs[id].L * h->bufs[id].C * h->cap;
+  };
   for (const LayerOp& op : h->ops) {
+    if (tc && op.tcW_hi != NPOS) {
+      // ------------------------------ tcgen05 path ------------------------------
+      TcArgs t;
+      TcMaps m;
+      memset(&t, 0, sizeof(t));
+      memset(&m, 0, sizeof(m));
+      t.C[0] = op.C0; t.C[1] = op.C1; t.Cout = op.Cout;
+      int Lrows, nparity = 1, lstride = 1;
+      if (!op.transposed) {
+        Lrows = op.Lout; lstride = op.stride;
+        int jmin = 0, jmax = op.taps - 1;
+        if (op.stride == 1) {
+          jmin = op.pad - (op.Lout - 1) > 0 ? op.pad - (op.Lout - 1) : 0;
+          jmax = op.pad + op.Lin - 1 < op.taps - 1 ? op.pad + op.Lin - 1 : op.taps - 1;
+        }
+        t.ntaps = jmax - jmin + 1;
+        for (int i = 0; i < t.ntaps; ++i) { t.tap_l0[0][i] = jmin + i - op.pad; t.tap_w[0][i] = jmin + i; }
+        t.out_L = op.Lout; t.out_lstride = 1;
+      } else {
+        // ConvTranspose1d(k4, s2, p1) as two 2-tap convs: out[2m] = W1 x[m] + W3 x[m-1];  out[2m+1] = W0 x[m+1] + W2 x[m]
+        Lrows = op.Lin; nparity = 2; t.ntaps = 2;
+        t.tap_l0[0][0] = 0; t.tap_w[0][0] = 1; t.tap_l0[0][1] = -1; t.tap_w[0][1] = 3;
+        t.tap_l0[1][0] = 1; t.tap_w[1][0] = 0; t.tap_l0[1][1] = 0; t.tap_w[1][1] = 2;
+        t.out_L = op.Lout; t.out_lstride = 2; t.out_loff0 = 0; t.out_loff1 = 1;
+      }
+      t.Lrows = Lrows; t.log2L = ilog2(Lrows); t.samples_per_tile = 128 / Lrows; t.nrows = rows * Lrows;
+      const int ins[2] = {op.in0, op.in1};
+      const int cs[2] = {op.C0, op.C1};
+      for (int sidx = 0; sidx < 2; ++sidx) {
+        if (cs[sidx] == 0) continue;
+        if ((rc = tc_make_act_map(&m.a[sidx][0], hi_ptr(ins[sidx]), rows, op.Lin, cs[sidx], op.Lin, lstride, t.samples_per_tile))) return h->fail(rc, "tensor map (A)");
+        if (nsplit == 2 && (rc = tc_make_act_map(&m.a[sidx][1], lo_ptr(ins[sidx]), rows, op.Lin, cs[sidx], op.Lin, lstride, t.samples_per_tile))) return h->fail(rc, "tensor map (A lo)");
+      }
+      const __nv_bfloat16* P16 = reinterpret_cast<const __nv_bfloat16*>(h->d_pack16);
+      if ((rc = tc_make_weight_map(&m.w[0], P16 + op.tcW_hi, op.taps * op.Cout, op.C0 + op.C1))) return h->fail(rc, "tensor map (W)");
+      if (nsplit == 2 && (rc = tc_make_weight_map(&m.w[1], P16 + op.tcW_lo, op.taps * op.Cout, op.C0 + op.C1))) return h->fail(rc, "tensor map (W lo)");
+      if (op.resW != NPOS) {
+        if (op.tcRW_hi != NPOS) {
+          t.RC[0] = op.RC0; t.RC[1] = op.RC1; t.resB = P + op.resB;
+          const int rins[2] = {op.rin0, op.rin1};
+          const int rcs[2] = {op.RC0, op.RC1};
+          for (int sidx = 0; sidx < 2; ++sidx) {
+            if (rcs[sidx] == 0) continue;
+            if ((rc = tc_make_act_map(&m.r[sidx][0], hi_ptr(rins[sidx]), rows, op.Lout, rcs[sidx], op.Lout, 1, t.samples_per_tile))) return h->fail(rc, "tensor map (R)");
+            if (nsplit == 2 && (rc = tc_make_act_map(&m.r[sidx][1], lo_ptr(rins[sidx]), rows, op.Lout, rcs[sidx], op.Lout, 1, t.samples_per_tile))) return h->fail(rc, "tensor map (R lo)");
+          }
+          if ((rc = tc_make_weight_map(&m.rw[0], P16 + op.tcRW_hi, op.Cout, op.RC0 + op.RC1))) return h->fail(rc, "tensor map (RW)");
+          if (nsplit == 2 && (rc = tc_make_weight_map(&m.rw[1], P16 + op.tcRW_lo, op.Cout, op.RC0 + op.RC1))) return h->fail(rc, "tensor map (RW lo)");
+        } else {
+          // residual projection of the raw trajectory (C_in = transition_dim): tiny fp32 1x1 conv on CUDA cores
+          ConvArgs pr{};
+          pr.x0 = buf_ptr(h, op.rin0, x); pr.C0 = op.RC0; pr.x0_period = (op.rin0 == BUF_X) ? x_period : 0;
+          pr.Lin = pr.Lout = op.Lout; pr.log2Lout = ilog2(op.Lout); pr.nrows = rows * op.Lout; pr.Cout = op.Cout;
+          pr.taps = 1; pr.jmin = pr.jmax = 0; pr.stride = 1; pr.W = P + op.resW; pr.bias = P + op.resB; pr.out = h->d_res0;
+          if ((rc = launch_conv_ffma(pr, s))) return h->fail(rc, "residual projection launch failed");
+          ++*launches;
+          t.res_f32 = h->d_res0;
+        }
+      } else if (op.res_id != BUF_NONE) {
+        t.res_hi = hi_ptr(op.res_id); t.res_lo = lo_ptr(op.res_id);
+      }
+      t.bias = P + op.bias;
+      if (op.gamma != NPOS) { t.gn_gamma = P + op.gamma; t.gn_beta = P + op.beta; t.cg = op.Cout / 8; }
+      if (op.temb_off >= 0) { t.temb = h->d_temb + op.temb_off; t.temb_stride = h->temb_total; }
+      if (op.headW != NPOS) { t.headW = P + op.headW; t.headB = P + op.headB; t.head_dim = op.head_dim; t.head_out = head_out; }
+      t.out_hi = hi_ptr(op.out); t.out_lo = lo_ptr(op.out);
+      if ((rc = launch_conv_tc(m, t, nsplit, nparity, s))) return h->fail(rc, "tcgen05 conv launch failed");
+      ++*launches;
+      continue;
+    }
     ConvArgs a{};
     a.x0 = buf_ptr(h, op.in0, x); a.x1 = buf_ptr(h, op.in1, x); a.C0 = op.C0; a.C1 = op.C1;
     a.x0_period = (op.in0 == BUF_X) ? x_period : 0;
@@ -496,6 +619,9 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
     }
     if (op.headW != NPOS) { a.headW = P + op.headW; a.headB = P + op.headB; a.head_dim = op.head_dim; a.head_out = head_out; }
     a.out = op.out == BUF_NONE ? nullptr : const_cast<float*>(buf_ptr(h, op.out, x));
+    if (tc) {   // CUDA-core layer feeding tensor-core layers: emit bf16 hi/lo instead of fp32
+      a.out = nullptr; a.out_hi = hi_ptr(op.out); a.out_lo = lo_ptr(op.out);
+    }
     if ((rc = launch_conv_ffma(a, s))) return h->fail(rc, "conv launch failed");
     ++*launches;
   }
@@ -570,6 +696,7 @@ int b2p_destroy(b2p_handle h) {
   cudaSetDevice(h->device);
   drop_graphs(h);
   if (h->d_pack) cudaFree(h->d_pack);
+  if (h->d_pack16) cudaFree(h->d_pack16);
   if (h->d_ws) cudaFree(h->d_ws);
   if (h->p_x) cudaFree(h->p_x);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -614,6 +741,9 @@ int b2p_finalize_weights(b2p_handle h) {
   if (h->d_pack) { B2P_CUDA_TRY(cudaFree(h->d_pack)); h->d_pack = nullptr; }
   B2P_CUDA_TRY(cudaMalloc((void**)&h->d_pack, h->pack_host.size() * sizeof(float)));
   B2P_CUDA_TRY(cudaMemcpy(h->d_pack, h->pack_host.data(), h->pack_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (h->d_pack16) { B2P_CUDA_TRY(cudaFree(h->d_pack16)); h->d_pack16 = nullptr; }
+  B2P_CUDA_TRY(cudaMalloc((void**)&h->d_pack16, h->pack16_host.size() * sizeof(uint16_t) + 256));
+  B2P_CUDA_TRY(cudaMemcpy(h->d_pack16, h->pack16_host.data(), h->pack16_host.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   if (!tp_offs.empty()) resolve_trajpred(h, tp_offs);
   // workspace offsets depend on the buffer table: force re-allocation
   if (h->d_ws) { B2P_CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; h->cap = 0; }
@@ -623,7 +753,6 @@ int b2p_finalize_weights(b2p_handle h) {
 
 int b2p_set_precision(b2p_handle h, int precision) {
   if (!h || precision < 0 || precision > 2) return B2P_ERR_INVALID_ARG;
-  if (precision != B2P_PREC_FP32) return h->fail(B2P_ERR_INVALID_ARG, "tensor-core precisions are not built in this version");
   h->cfg.precision = precision;
   drop_graphs(h);
   return B2P_OK;

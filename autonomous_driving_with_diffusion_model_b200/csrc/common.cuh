@@ -1,5 +1,6 @@
 // Internal declarations shared by the .cu files of libb200plan.  Not part of the public ABI (include/b200plan.h).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -43,6 +44,8 @@ struct ConvArgs {
   const float* resW; const float* resB;              // [RC0+RC1][Cout], [Cout]
   const float* headW; const float* headB; int head_dim; float* head_out;  // [64][head_dim]
   float* out;                         // [nrows, Cout] (may be null when only the head is wanted)
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;  // optional bf16 hi/lo copy of the output (tensor-core precisions)
+  float* res_out;                     // if set, the residual 1x1 result is written here instead of being added
 };
 
 int launch_conv_ffma(const ConvArgs& a, cudaStream_t s);

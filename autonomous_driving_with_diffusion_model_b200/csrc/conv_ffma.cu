@@ -6,6 +6,8 @@
 //   + final 1x1 head and the [B,C,L] -> [B,L,C] rearrange                (modeling/temporal.py:233-245)
 // Layout: channels-last rows (sample, position) x channels, so the trajectory tensor [B,H,D] is consumed and
 // produced as is.  Tile: TM rows (whole samples) x 64 output channels (whole GroupNorm groups) per CTA.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace b2p {
@@ -220,11 +222,23 @@ __global__ void __launch_bounds__(NT) conv_ffma_kernel(ConvArgs a) {
       acc[r][0] += q.x; acc[r][1] += q.y; acc[r][2] += q.z; acc[r][3] += q.w;
     }
     if (a.resW) {
-      acc[r][0] += racc[r][0] + rb4.x; acc[r][1] += racc[r][1] + rb4.y;
-      acc[r][2] += racc[r][2] + rb4.z; acc[r][3] += racc[r][3] + rb4.w;
+      if (a.res_out) {   // emit the 1x1 projection on its own (consumed as a residual by a later tensor-core launch)
+        if (ok) *reinterpret_cast<float4*>(a.res_out + (size_t)grow * a.Cout + gc) =
+            make_float4(racc[r][0] + rb4.x, racc[r][1] + rb4.y, racc[r][2] + rb4.z, racc[r][3] + rb4.w);
+      } else {
+        acc[r][0] += racc[r][0] + rb4.x; acc[r][1] += racc[r][1] + rb4.y;
+        acc[r][2] += racc[r][2] + rb4.z; acc[r][3] += racc[r][3] + rb4.w;
+      }
     }
     if (a.out && ok)
       *reinterpret_cast<float4*>(a.out + (size_t)grow * a.Cout + gc) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    if (a.out_hi && ok) {   // bf16 hi (+lo) copy for the tensor-core layers that follow
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { h[c] = __float2bfloat16_rn(acc[r][c]); l[c] = __float2bfloat16_rn(acc[r][c] - __bfloat162float(h[c])); }
+      *reinterpret_cast<uint2*>(a.out_hi + (size_t)grow * a.Cout + gc) = *reinterpret_cast<uint2*>(h);
+      if (a.out_lo) *reinterpret_cast<uint2*>(a.out_lo + (size_t)grow * a.Cout + gc) = *reinterpret_cast<uint2*>(l);
+    }
   }
 
   if (a.headW) {  // fused 1x1 head over the 64 channels of each row (Cout == 64, gridDim.y == 1)
