@@ -534,24 +534,24 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
       memset(&t, 0, sizeof(t));
       memset(&m, 0, sizeof(m));
       t.C[0] = op.C0; t.C[1] = op.C1; t.Cout = op.Cout;
-      int Lrows, nparity = 1, lstride = 1;
+      const int Lrows = op.Lin;   // GEMM rows are INPUT positions; taps are combined as row shifts in the epilogue
+      t.n_out = 1; t.out_ldiv = 1; t.out_lmul = 1; t.out_L = op.Lout;
       if (!op.transposed) {
-        Lrows = op.Lout; lstride = op.stride;
         int jmin = 0, jmax = op.taps - 1;
-        if (op.stride == 1) {
+        if (op.stride == 1) {   // taps that can reach a valid input position (k=5 on L=2 only touches taps 1..3)
           jmin = op.pad - (op.Lout - 1) > 0 ? op.pad - (op.Lout - 1) : 0;
           jmax = op.pad + op.Lin - 1 < op.taps - 1 ? op.pad + op.Lin - 1 : op.taps - 1;
         }
-        t.ntaps = jmax - jmin + 1;
-        for (int i = 0; i < t.ntaps; ++i) { t.tap_l0[0][i] = jmin + i - op.pad; t.tap_w[0][i] = jmin + i; }
-        t.out_L = op.Lout; t.out_lstride = 1;
+        t.T = jmax - jmin + 1; t.tap0 = jmin; t.nt[0] = t.T;
+        for (int i = 0; i < t.T; ++i) { t.tap_blk[0][i] = i; t.tap_shift[0][i] = jmin + i - op.pad; }
+        t.out_ldiv = op.stride;   // stride-2 conv: out[lo] = sum_j Y_j[2*lo + j - pad], emitted by the even rows
       } else {
-        // ConvTranspose1d(k4, s2, p1) as two 2-tap convs: out[2m] = W1 x[m] + W3 x[m-1];  out[2m+1] = W0 x[m+1] + W2 x[m]
-        Lrows = op.Lin; nparity = 2; t.ntaps = 2;
-        t.tap_l0[0][0] = 0; t.tap_w[0][0] = 1; t.tap_l0[0][1] = -1; t.tap_w[0][1] = 3;
-        t.tap_l0[1][0] = 1; t.tap_w[1][0] = 0; t.tap_l0[1][1] = 0; t.tap_w[1][1] = 2;
-        t.out_L = op.Lout; t.out_lstride = 2; t.out_loff0 = 0; t.out_loff1 = 1;
+        // ConvTranspose1d(k4, s2, p1): out[2m] = Y1[m] + Y3[m-1];  out[2m+1] = Y0[m+1] + Y2[m]
+        t.T = 4; t.tap0 = 0; t.n_out = 2; t.out_lmul = 2;
+        t.nt[0] = 2; t.tap_blk[0][0] = 1; t.tap_shift[0][0] = 0; t.tap_blk[0][1] = 3; t.tap_shift[0][1] = -1;
+        t.nt[1] = 2; t.tap_blk[1][0] = 0; t.tap_shift[1][0] = 1; t.tap_blk[1][1] = 2; t.tap_shift[1][1] = 0;
       }
+      const int lstride = 1;
       t.Lrows = Lrows; t.log2L = ilog2(Lrows); t.samples_per_tile = 128 / Lrows; t.nrows = rows * Lrows;
       const int ins[2] = {op.in0, op.in1};
       const int cs[2] = {op.C0, op.C1};
@@ -561,8 +561,8 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
         if (nsplit == 2 && (rc = tc_make_act_map(&m.a[sidx][1], lo_ptr(ins[sidx]), rows, op.Lin, cs[sidx], op.Lin, lstride, t.samples_per_tile))) return h->fail(rc, "tensor map (A lo)");
       }
       const __nv_bfloat16* P16 = reinterpret_cast<const __nv_bfloat16*>(h->d_pack16);
-      if ((rc = tc_make_weight_map(&m.w[0], P16 + op.tcW_hi, op.taps * op.Cout, op.C0 + op.C1))) return h->fail(rc, "tensor map (W)");
-      if (nsplit == 2 && (rc = tc_make_weight_map(&m.w[1], P16 + op.tcW_lo, op.taps * op.Cout, op.C0 + op.C1))) return h->fail(rc, "tensor map (W lo)");
+      if ((rc = tc_make_weight_map(&m.w[0], P16 + op.tcW_hi, op.taps, op.Cout, op.C0 + op.C1, t.T))) return h->fail(rc, "tensor map (W)");
+      if (nsplit == 2 && (rc = tc_make_weight_map(&m.w[1], P16 + op.tcW_lo, op.taps, op.Cout, op.C0 + op.C1, t.T))) return h->fail(rc, "tensor map (W lo)");
       if (op.resW != NPOS) {
         if (op.tcRW_hi != NPOS) {
           t.RC[0] = op.RC0; t.RC[1] = op.RC1; t.resB = P + op.resB;
@@ -573,8 +573,8 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
             if ((rc = tc_make_act_map(&m.r[sidx][0], hi_ptr(rins[sidx]), rows, op.Lout, rcs[sidx], op.Lout, 1, t.samples_per_tile))) return h->fail(rc, "tensor map (R)");
             if (nsplit == 2 && (rc = tc_make_act_map(&m.r[sidx][1], lo_ptr(rins[sidx]), rows, op.Lout, rcs[sidx], op.Lout, 1, t.samples_per_tile))) return h->fail(rc, "tensor map (R lo)");
           }
-          if ((rc = tc_make_weight_map(&m.rw[0], P16 + op.tcRW_hi, op.Cout, op.RC0 + op.RC1))) return h->fail(rc, "tensor map (RW)");
-          if (nsplit == 2 && (rc = tc_make_weight_map(&m.rw[1], P16 + op.tcRW_lo, op.Cout, op.RC0 + op.RC1))) return h->fail(rc, "tensor map (RW lo)");
+          if ((rc = tc_make_weight_map(&m.rw[0], P16 + op.tcRW_hi, 1, op.Cout, op.RC0 + op.RC1, 0))) return h->fail(rc, "tensor map (RW)");
+          if (nsplit == 2 && (rc = tc_make_weight_map(&m.rw[1], P16 + op.tcRW_lo, 1, op.Cout, op.RC0 + op.RC1, 0))) return h->fail(rc, "tensor map (RW lo)");
         } else {
           // residual projection of the raw trajectory (C_in = transition_dim): tiny fp32 1x1 conv on CUDA cores
           ConvArgs pr{};
@@ -593,7 +593,7 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
       if (op.temb_off >= 0) { t.temb = h->d_temb + op.temb_off; t.temb_stride = h->temb_total; }
       if (op.headW != NPOS) { t.headW = P + op.headW; t.headB = P + op.headB; t.head_dim = op.head_dim; t.head_out = head_out; }
       t.out_hi = hi_ptr(op.out); t.out_lo = lo_ptr(op.out);
-      if ((rc = launch_conv_tc(m, t, nsplit, nparity, s))) return h->fail(rc, "tcgen05 conv launch failed");
+      if ((rc = launch_conv_tc(m, t, nsplit, s))) return h->fail(rc, "tcgen05 conv launch failed");
       ++*launches;
       continue;
     }

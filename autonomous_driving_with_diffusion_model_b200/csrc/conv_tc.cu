@@ -11,10 +11,11 @@
 //   pairs and three MMAs (hi*hi + lo*hi + hi*lo) accumulate in fp32 in TMEM ("bf16x3", fp32-class parity).
 // * one elected thread issues tcgen05.mma (cta_group::1, M=128, N=64, K=16); accumulators live in TMEM
 //   (columns [0,64) main GEMM, [64,128) the residual 1x1 conv of the block input when present).
-// * epilogue: thread t owns TMEM lane t == tile row t: bias, GroupNorm(8) statistics by warp shuffles over the L rows
-//   of a sample, Mish, + time embedding, + residual, optional fused 1x1 head, bf16 hi/lo store.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (TMEM lane quadrants
-// 2,3,0,1).
+// * epilogue on all 16 warps: warp w owns TMEM lane quadrant (w & 3) and the 16-column slice (w >> 2) of the 64-column
+//   tile, so a thread holds 16 channels of one tile row: tap combine (row-shift shuffles), bias, GroupNorm(8) statistics
+//   by warp shuffles over the L rows of a sample (+ a shared-memory exchange between column slices when a group is wider
+//   than 16 channels), Mish, + time embedding, + residual, optional fused 1x1 head, bf16 hi/lo store.
+// Thread 0 is the TMA producer and thread 32 the MMA issuer before they join the epilogue; warp 1 owns the TMEM allocation.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -27,13 +28,11 @@ constexpr int TC_M = 128;           // rows per tile
 constexpr int TC_N = 64;            // output channels per tile
 constexpr int TC_K = 64;            // channels per pipeline stage (128 bytes of bf16: one swizzle atom row)
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_THREADS = 192;
-constexpr int TC_TMEM_COLS = 128;
+constexpr int TC_THREADS = 512;
+constexpr int EPI_COLS = 16;          // columns per epilogue thread
 constexpr int A_BYTES = TC_M * TC_K * 2;   // 16 KB
 constexpr int B_BYTES = TC_N * TC_K * 2;   //  8 KB
 
-template <int NSPLIT> struct StageBytes { static constexpr int value = NSPLIT * (A_BYTES + B_BYTES); };
-template <int NSPLIT> struct NumStages { static constexpr int value = NSPLIT == 2 ? 4 : 6; };
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,41 +90,81 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// GroupNorm(8) + Mish on one tile row held in registers: a group is CG consecutive channels x the L rows (lanes) of a
-// sample; per-thread partial sums are combined across the L lanes with xor shuffles (two-pass: mean, then variance).
+// Mish with the SFU approximations (ex2.approx / rcp.approx): relative error ~1e-6, far below the bf16-split noise.
+__device__ __forceinline__ float mish_fast(float x) {
+  float e = __expf(x);
+  float n = e * (e + 2.f);
+  float m = x * __fdividef(n, n + 2.f);
+  return x > 20.f ? x : m;
+}
+
+// GroupNorm(8) + Mish for the 16 channels a thread holds.  A group is CG consecutive channels x the L rows (adjacent
+// lanes) of a sample.  CG <= 16: the group is local to the thread's slice; CG = 32 / 64: partial sums of the 2 / 4
+// column-slice warps covering the group are exchanged through shared memory (xchg[row][slice]).  Two passes (mean, then
+// centred variance) like the reference's GroupNorm.  Called by ALL threads of the CTA (contains __syncthreads).
 template <int CG>
-__device__ __forceinline__ void group_norm_mish(float (&v)[TC_N], int L, const float* __restrict__ gamma, const float* __restrict__ beta) {
+__device__ __forceinline__ void group_norm_mish16(float (&v)[EPI_COLS], int L, int row, int slice, float (*xchg)[4],
+                                                  const float* gamma, const float* beta) {
+  constexpr int W = CG < EPI_COLS ? CG : EPI_COLS;      // channels of one group inside this thread
+  constexpr int NG = EPI_COLS / W;                      // groups per thread
+  constexpr int SL = CG / W;                            // slices sharing one group
   const float inv_n = 1.0f / (float)(CG * L);
+  float mean[NG], rstd[NG];
 #pragma unroll
-  for (int g0 = 0; g0 < TC_N; g0 += CG) {
+  for (int g = 0; g < NG; ++g) {
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < CG; ++c) s += v[g0 + c];
+    for (int c = 0; c < W; ++c) s += v[g * W + c];
     for (int o = 1; o < L; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * inv_n;
+    mean[g] = s;
+  }
+  if (SL > 1) {
+    xchg[row][slice] = mean[0];
+    __syncthreads();
+    const int base = slice & ~(SL - 1);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < SL; ++j) s += xchg[row][base + j];
+    mean[0] = s;
+    __syncthreads();
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    mean[g] *= inv_n;
     float q = 0.f;
 #pragma unroll
-    for (int c = 0; c < CG; ++c) { float d = v[g0 + c] - mean; q = fmaf(d, d, q); }
+    for (int c = 0; c < W; ++c) { float d = v[g * W + c] - mean[g]; q = fmaf(d, d, q); }
     for (int o = 1; o < L; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = 1.0f / sqrtf(q * inv_n + 1e-5f);
+    rstd[g] = q;
+  }
+  if (SL > 1) {
+    xchg[row][slice] = rstd[0];
+    __syncthreads();
+    const int base = slice & ~(SL - 1);
+    float q = 0.f;
 #pragma unroll
-    for (int c = 0; c < CG; ++c) v[g0 + c] = mish_f((v[g0 + c] - mean) * rstd * __ldg(gamma + g0 + c) + __ldg(beta + g0 + c));
+    for (int j = 0; j < SL; ++j) q += xchg[row][base + j];
+    rstd[0] = q;
+    __syncthreads();
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const float r = rsqrtf(rstd[g] * inv_n + 1e-5f);
+#pragma unroll
+    for (int c = 0; c < W; ++c) v[g * W + c] = mish_fast((v[g * W + c] - mean[g]) * r * gamma[g * W + c] + beta[g * W + c]);
   }
 }
 
@@ -135,194 +174,242 @@ struct __align__(16) TcBarriers {
   uint64_t tmem_full;
   uint32_t tmem_base;
   uint32_t pad;
+  float bias[TC_N], gamma[TC_N], beta[TC_N], resb[TC_N];   // per-tile epilogue vectors
 };
+// epilogue scratch aliases the (by then idle) TMA ring: xchg[128][4] GroupNorm partial sums, head[128][4][8] partial dots
+constexpr int EPI_XCHG_BYTES = TC_M * 4 * 4;
 
+constexpr int TC_SMEM_STAGE_REGION = 224 * 1024;   // bytes available to the TMA ring
+constexpr int TC_SMEM_TOTAL = TC_SMEM_STAGE_REGION + 1024 /*alignment slack*/ + (int)sizeof(TcBarriers);
+
+// "taps in N": one pass over the activations computes Y_t = A * W_t^T for every tap t into its own 64-column TMEM
+// block; the conv sum  out[l] = sum_t Y_t[l + shift_t]  is a ROW shift of the accumulator, done in the epilogue with warp
+// shuffles (the L rows of a sample are adjacent lanes).  The activation tile is therefore loaded once per 64-channel
+// chunk instead of once per tap, and zero padding is just "source lane outside the sample".
 template <int NSPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs a) {
-  constexpr int STAGES = NumStages<NSPLIT>::value;
-  constexpr int STAGE_BYTES = StageBytes<NSPLIT>::value;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + STAGES * STAGE_BYTES);
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + TC_SMEM_STAGE_REGION);
+
+  const int T = a.T;
+  const int stage_bytes = NSPLIT * (A_BYTES + T * B_BYTES);
+  int stages = TC_SMEM_STAGE_REGION / stage_bytes;
+  if (stages > 8) stages = 8;
+  const uint32_t tmem_cols = (T + 1) * TC_N <= 128 ? 128u : ((T + 1) * TC_N <= 256 ? 256u : 512u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, n0 = blockIdx.y * TC_N, par = blockIdx.z;
+  const int tile_m = blockIdx.x, n0 = blockIdx.y * TC_N;
   const int b0 = tile_m * a.samples_per_tile;
 
-  // iteration space of the K loop: main phase (taps x sources x 64-channel chunks), then the residual 1x1 phase
   const int chunks0 = a.C[0] / TC_K, chunks1 = a.C[1] / TC_K;
-  const int main_iters = a.ntaps * (chunks0 + chunks1);
+  const int main_iters = chunks0 + chunks1;
   const int rchunks0 = a.RC[0] / TC_K, rchunks1 = a.RC[1] / TC_K;
   const int res_iters = rchunks0 + rchunks1;
   const int total_iters = main_iters + res_iters;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
     mbar_init(&bars->tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM allocation (one warp), address lands in shared memory
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TC_TMEM_COLS) : "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + TC_N) {   // stage the tile's epilogue vectors
+    const int c = threadIdx.x - 64;
+    bars->bias[c] = __ldg(a.bias + n0 + c);
+    bars->gamma[c] = a.gn_gamma ? __ldg(a.gn_gamma + n0 + c) : 1.f;
+    bars->beta[c] = a.gn_gamma ? __ldg(a.gn_beta + n0 + c) : 0.f;
+    bars->resb[c] = a.resB ? __ldg(a.resB + n0 + c) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      prefetch_tmap(&maps.a[0][0]);
-      prefetch_tmap(&maps.w[0]);
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&bars->empty[s], ph ^ 1);
-        uint8_t* st = smem + s * STAGE_BYTES;
-        mbar_expect_tx(&bars->full[s], STAGE_BYTES);
-        if (it < main_iters) {
-          const int per_tap = chunks0 + chunks1;
-          const int tap = it / per_tap, ch = it % per_tap;
-          const int src = ch < chunks0 ? 0 : 1;
-          const int c0 = (src == 0 ? ch : ch - chunks0) * TC_K;
-          const int kglob = (src == 0 ? 0 : a.C[0]) + c0;                     // column in the packed weight matrix
-          const int l0 = a.tap_l0[par][tap];
-          const int wrow = a.tap_w[par][tap] * a.Cout + n0;
+  if (threadIdx.x == 0) {
+    // =============================== TMA producer (one thread) ===============================
+    prefetch_tmap(&maps.a[0][0]);
+    prefetch_tmap(&maps.w[0]);
+    if (NSPLIT == 2) { prefetch_tmap(&maps.a[0][1]); prefetch_tmap(&maps.w[1]); }
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % stages;
+      const uint32_t ph = (it / stages) & 1;
+      mbar_wait(&bars->empty[s], ph ^ 1);
+      uint8_t* st = smem + s * stage_bytes;
+      uint8_t* sb = st + NSPLIT * A_BYTES;
+      if (it < main_iters) {
+        mbar_expect_tx(&bars->full[s], stage_bytes);
+        const int src = it < chunks0 ? 0 : 1;
+        const int c0 = (src == 0 ? it : it - chunks0) * TC_K;
+        const int kglob = (src == 0 ? 0 : a.C[0]) + c0;
 #pragma unroll
-          for (int h = 0; h < NSPLIT; ++h) {
-            tma_load_3d(st + h * A_BYTES, &maps.a[src][h], &bars->full[s], c0, l0, b0);
-            tma_load_2d(st + NSPLIT * A_BYTES + h * B_BYTES, &maps.w[h], &bars->full[s], kglob, wrow);
-          }
-        } else {
-          const int ch = it - main_iters;
-          const int src = ch < rchunks0 ? 0 : 1;
-          const int c0 = (src == 0 ? ch : ch - rchunks0) * TC_K;
-          const int kglob = (src == 0 ? 0 : a.RC[0]) + c0;
+        for (int h = 0; h < NSPLIT; ++h) {
+          tma_load_3d(st + h * A_BYTES, &maps.a[src][h], &bars->full[s], c0, 0, b0);
+          tma_load_3d(sb + h * T * B_BYTES, &maps.w[h], &bars->full[s], kglob, n0, a.tap0);
+        }
+      } else {
+        mbar_expect_tx(&bars->full[s], NSPLIT * (A_BYTES + B_BYTES));
+        const int ch = it - main_iters;
+        const int src = ch < rchunks0 ? 0 : 1;
+        const int c0 = (src == 0 ? ch : ch - rchunks0) * TC_K;
+        const int kglob = (src == 0 ? 0 : a.RC[0]) + c0;
 #pragma unroll
-          for (int h = 0; h < NSPLIT; ++h) {
-            tma_load_3d(st + h * A_BYTES, &maps.r[src][h], &bars->full[s], c0, 0, b0);
-            tma_load_2d(st + NSPLIT * A_BYTES + h * B_BYTES, &maps.rw[h], &bars->full[s], kglob, n0);
-          }
+        for (int h = 0; h < NSPLIT; ++h) {
+          tma_load_3d(st + h * A_BYTES, &maps.r[src][h], &bars->full[s], c0, 0, b0);
+          tma_load_2d(sb + h * T * B_BYTES, &maps.rw[h], &bars->full[s], kglob, n0);
         }
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc();
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&bars->full[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + NSPLIT * A_BYTES;
-        const bool res_phase = it >= main_iters;
-        const uint32_t d = tmem_base + (res_phase ? TC_N : 0);
-        const bool first = res_phase ? (it == main_iters) : (it == 0);
+  } else if (threadIdx.x == 32) {
+    // =============================== MMA issuer (one thread) ===============================
+    const uint32_t idesc = umma_idesc();
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % stages;
+      const uint32_t ph = (it / stages) & 1;
+      mbar_wait(&bars->full[s], ph);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + s * stage_bytes);
+      const uint32_t sb = sa + NSPLIT * A_BYTES;
+      const bool res_phase = it >= main_iters;
+      const int nblk = res_phase ? 1 : T;
+      const uint32_t dbase = tmem_base + (res_phase ? T * TC_N : 0);
+      const bool first = res_phase ? (it == main_iters) : (it == 0);
 #pragma unroll
-        for (int k = 0; k < TC_K / TC_UMMA_K; ++k) {
-          const uint32_t koff = k * TC_UMMA_K * 2;   // bytes inside the 128B swizzle row
-          const uint64_t a_hi = umma_desc(sa + koff), b_hi = umma_desc(sb + koff);
+      for (int k = 0; k < TC_K / TC_UMMA_K; ++k) {
+        const uint32_t koff = k * TC_UMMA_K * 2;   // bytes inside the 128B swizzle row
+        const uint64_t a_hi = umma_desc(sa + koff);
+        const uint64_t a_lo = umma_desc(sa + A_BYTES + koff);
+        for (int t = 0; t < nblk; ++t) {
+          const uint32_t d = dbase + t * TC_N;
+          const uint64_t b_hi = umma_desc(sb + t * B_BYTES + koff);
           umma(d, a_hi, b_hi, idesc, (first && k == 0) ? 0u : 1u);
           if (NSPLIT == 2) {
-            const uint64_t a_lo = umma_desc(sa + A_BYTES + koff), b_lo = umma_desc(sb + B_BYTES + koff);
+            const uint64_t b_lo = umma_desc(sb + (T + t) * B_BYTES + koff);
             umma(d, a_lo, b_hi, idesc, 1u);
             umma(d, a_hi, b_lo, idesc, 1u);
           }
         }
-        umma_commit(&bars->empty[s]);          // frees the smem stage when these MMAs retire
       }
-      umma_commit(&bars->tmem_full);           // accumulators complete
+      umma_commit(&bars->empty[s]);
     }
-  } else {
-    // =============================== epilogue (warps 2..5) ===============================
+    umma_commit(&bars->tmem_full);
+  }
+  __syncwarp();
+
+  // =============================== epilogue (all 16 warps) ===============================
+  {
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int slice = warp >> 2;                    // 16-column slice of the 64-column tile
+    const int col0 = slice * EPI_COLS;
     const int r = quad * 32 + lane;                 // tile row == TMEM lane
     const int L = a.Lrows;
     const long grow = (long)tile_m * TC_M + r;
-    const bool ok = grow < a.nrows;
+    const bool row_ok = grow < a.nrows;
     const int b = (int)(grow >> a.log2L), l = (int)(grow & (L - 1));
+    float (*xchg)[4] = reinterpret_cast<float (*)[4]>(smem);
+    float (*headp)[4][8] = reinterpret_cast<float (*)[4][8]>(smem + EPI_XCHG_BYTES);
     mbar_wait(&bars->tmem_full, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    float v[TC_N];
-    tmem_ld32(taddr, v);
-    tmem_ld32(taddr + 32, v + 32);
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + col0;
+    const int gcol = n0 + col0;
+
+    for (int o = 0; o < a.n_out; ++o) {
+      float v[EPI_COLS];
 #pragma unroll
-    for (int c = 0; c < TC_N; ++c) v[c] += __ldg(a.bias + n0 + c);
-    if (a.gn_gamma) {
-      switch (a.cg) {    // compile-time group width keeps v[] in registers
-        case 8: group_norm_mish<8>(v, L, a.gn_gamma + n0, a.gn_beta + n0); break;
-        case 16: group_norm_mish<16>(v, L, a.gn_gamma + n0, a.gn_beta + n0); break;
-        case 32: group_norm_mish<32>(v, L, a.gn_gamma + n0, a.gn_beta + n0); break;
-        default: group_norm_mish<64>(v, L, a.gn_gamma + n0, a.gn_beta + n0); break;
+      for (int c = 0; c < EPI_COLS; ++c) v[c] = bars->bias[col0 + c];
+      // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the sample) ----
+      for (int i = 0; i < a.nt[o]; ++i) {
+        const int t = a.tap_blk[o][i], d = a.tap_shift[o][i];
+        const bool valid = (l + d >= 0) && (l + d < L);
+        const int src = (lane + d) & 31;
+        float y[EPI_COLS];
+        tmem_ld16(taddr + t * TC_N, y);
+        if (d == 0) {
+#pragma unroll
+          for (int c = 0; c < EPI_COLS; ++c) v[c] += y[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < EPI_COLS; ++c) { float g = __shfl_sync(0xffffffffu, y[c], src); v[c] += valid ? g : 0.f; }
+        }
       }
-    }
-    if (a.temb && ok) {
-      const float* t = a.temb + (size_t)b * a.temb_stride + n0;
-#pragma unroll
-      for (int c = 0; c < TC_N; c += 4) { float4 t4 = __ldg(reinterpret_cast<const float4*>(t + c)); v[c] += t4.x; v[c + 1] += t4.y; v[c + 2] += t4.z; v[c + 3] += t4.w; }
-    }
-    if (res_iters > 0) {                             // residual 1x1 conv accumulated in TMEM columns [64,128)
-      float rv[32];
-#pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        tmem_ld32(taddr + TC_N + 32 * hlf, rv);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) v[32 * hlf + c] += rv[c] + __ldg(a.resB + n0 + 32 * hlf + c);
+      if (a.gn_gamma) {
+        switch (a.cg) {
+          case 8: group_norm_mish16<8>(v, L, r, slice, xchg, bars->gamma + col0, bars->beta + col0); break;
+          case 16: group_norm_mish16<16>(v, L, r, slice, xchg, bars->gamma + col0, bars->beta + col0); break;
+          case 32: group_norm_mish16<32>(v, L, r, slice, xchg, bars->gamma + col0, bars->beta + col0); break;
+          default: group_norm_mish16<64>(v, L, r, slice, xchg, bars->gamma + col0, bars->beta + col0); break;
+        }
       }
-    }
-    if (ok) {
-      if (a.res_f32) {
-        const float* q = a.res_f32 + (size_t)grow * a.Cout + n0;
+      const bool ok = row_ok && (a.out_ldiv == 1 || (l % a.out_ldiv) == 0);
+      if (a.temb && ok) {
+        const float* tp = a.temb + (size_t)b * a.temb_stride + gcol;
 #pragma unroll
-        for (int c = 0; c < TC_N; c += 4) { float4 t4 = __ldg(reinterpret_cast<const float4*>(q + c)); v[c] += t4.x; v[c + 1] += t4.y; v[c + 2] += t4.z; v[c + 3] += t4.w; }
+        for (int c = 0; c < EPI_COLS; c += 4) { float4 t4 = __ldg(reinterpret_cast<const float4*>(tp + c)); v[c] += t4.x; v[c + 1] += t4.y; v[c + 2] += t4.z; v[c + 3] += t4.w; }
       }
-      if (a.res_hi) {
-        const uint4* qh = reinterpret_cast<const uint4*>(a.res_hi + (size_t)grow * a.Cout + n0);
-        const uint4* ql = a.res_lo ? reinterpret_cast<const uint4*>(a.res_lo + (size_t)grow * a.Cout + n0) : nullptr;
+      if (res_iters > 0) {   // residual 1x1 conv accumulated in the TMEM block after the tap blocks
+        float rv[EPI_COLS];
+        tmem_ld16(taddr + T * TC_N, rv);
 #pragma unroll
-        for (int c8 = 0; c8 < TC_N / 8; ++c8) {
-          uint4 hh = __ldg(qh + c8);
-          const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hh);
+        for (int c = 0; c < EPI_COLS; ++c) v[c] += rv[c] + bars->resb[col0 + c];
+      }
+      if (ok) {
+        if (a.res_f32) {
+          const float* q = a.res_f32 + (size_t)grow * a.Cout + gcol;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[c8 * 8 + i] += __bfloat162float(hp[i]);
-          if (ql) {
-            uint4 ll = __ldg(ql + c8);
-            const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&ll);
+          for (int c = 0; c < EPI_COLS; c += 4) { float4 t4 = __ldg(reinterpret_cast<const float4*>(q + c)); v[c] += t4.x; v[c + 1] += t4.y; v[c + 2] += t4.z; v[c + 3] += t4.w; }
+        }
+        if (a.res_hi) {
+          const uint4* qh = reinterpret_cast<const uint4*>(a.res_hi + (size_t)grow * a.Cout + gcol);
+          const uint4* ql = a.res_lo ? reinterpret_cast<const uint4*>(a.res_lo + (size_t)grow * a.Cout + gcol) : nullptr;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[c8 * 8 + i] += __bfloat162float(lp[i]);
+          for (int c8 = 0; c8 < EPI_COLS / 8; ++c8) {
+            uint4 hh = __ldg(qh + c8);
+            const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[c8 * 8 + i] += __bfloat162float(hp[i]);
+            if (ql) {
+              uint4 ll = __ldg(ql + c8);
+              const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&ll);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[c8 * 8 + i] += __bfloat162float(lp[i]);
+            }
+          }
+        }
+        const size_t orow = (size_t)b * a.out_L + (size_t)(l / a.out_ldiv) * a.out_lmul + o;
+        if (a.out_hi) {
+          uint4* oh = reinterpret_cast<uint4*>(a.out_hi + orow * a.Cout + gcol);
+          uint4* ol = a.out_lo ? reinterpret_cast<uint4*>(a.out_lo + orow * a.Cout + gcol) : nullptr;
+#pragma unroll
+          for (int c8 = 0; c8 < EPI_COLS / 8; ++c8) {
+            uint4 hh, ll;
+            __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(&hh);
+            __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(&ll);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float x = v[c8 * 8 + i];
+              hp[i] = __float2bfloat16_rn(x);
+              lp[i] = __float2bfloat16_rn(x - __bfloat162float(hp[i]));
+            }
+            oh[c8] = hh;
+            if (ol) ol[c8] = ll;
           }
         }
       }
-      const size_t orow = (size_t)b * a.out_L + (size_t)l * a.out_lstride + (par ? a.out_loff1 : a.out_loff0);
-      if (a.out_hi) {
-        uint4* oh = reinterpret_cast<uint4*>(a.out_hi + orow * a.Cout + n0);
-        uint4* ol = a.out_lo ? reinterpret_cast<uint4*>(a.out_lo + orow * a.Cout + n0) : nullptr;
-#pragma unroll
-        for (int c8 = 0; c8 < TC_N / 8; ++c8) {
-          uint4 hh, ll;
-          __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(&hh);
-          __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(&ll);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float x = v[c8 * 8 + i];
-            hp[i] = __float2bfloat16_rn(x);
-            lp[i] = __float2bfloat16_rn(x - __bfloat162float(hp[i]));
-          }
-          oh[c8] = hh;
-          if (ol) ol[c8] = ll;
-        }
-      }
-      if (a.headW) {   // fused 1x1 head: this thread holds all 64 channels of its row
+      if (a.headW) {   // fused 1x1 head (Cout == 64): partial dot products per column slice, summed by slice 0
         for (int d = 0; d < a.head_dim; ++d) {
-          float s = __ldg(a.headB + d);
+          float s = 0.f;
 #pragma unroll
-          for (int c = 0; c < TC_N; ++c) s = fmaf(v[c], __ldg(a.headW + c * a.head_dim + d), s);
-          a.head_out[(size_t)grow * a.head_dim + d] = s;
+          for (int c = 0; c < EPI_COLS; ++c) s = fmaf(v[c], __ldg(a.headW + (col0 + c) * a.head_dim + d), s);
+          headp[r][slice][d] = s;
+        }
+        __syncthreads();
+        if (slice == 0 && ok) {
+          for (int d = 0; d < a.head_dim; ++d)
+            a.head_out[(size_t)grow * a.head_dim + d] = __ldg(a.headB + d) + headp[r][0][d] + headp[r][1][d] + headp[r][2][d] + headp[r][3][d];
         }
       }
     }
@@ -331,7 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -362,33 +449,45 @@ int tc_make_act_map(CUtensorMap* m, const void* base, int B, int L, int C, int b
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? B2P_OK : B2P_ERR_INVALID_ARG;
 }
-// weights [rows = taps*Cout, K = Cin] bf16 -> box {64 (K), 64 rows}
-int tc_make_weight_map(CUtensorMap* m, const void* base, int rows, int K) {
+// conv weights [taps][Cout][Cin] bf16 -> box {64 (K), 64 output channels, ntaps}; ntaps == 0 -> plain 2-D [Cout][Cin] map
+int tc_make_weight_map(CUtensorMap* m, const void* base, int taps, int Cout, int K, int box_taps) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return B2P_ERR_NO_DEVICE;
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_K, (cuuint32_t)TC_N};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r;
+  if (box_taps == 0) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_K, (cuuint32_t)TC_N};
+    cuuint32_t estr[2] = {1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Cout * K * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_K, (cuuint32_t)TC_N, (cuuint32_t)box_taps};
+    cuuint32_t estr[3] = {1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   return r == CUDA_SUCCESS ? B2P_OK : B2P_ERR_INVALID_ARG;
 }
 
 template <int NSPLIT>
 static int launch_t(const TcMaps& maps, const TcArgs& a, dim3 grid, cudaStream_t s) {
-  constexpr int smem = NumStages<NSPLIT>::value * StageBytes<NSPLIT>::value + (int)sizeof(TcBarriers) + 1024;
+  constexpr int smem = TC_SMEM_TOTAL;
   B2P_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   conv_tc_kernel<NSPLIT><<<grid, TC_THREADS, smem, s>>>(maps, a);
   return (int)cudaGetLastError();
 }
 
-int launch_conv_tc(const TcMaps& maps, const TcArgs& a, int nsplit, int nparity, cudaStream_t s) {
+int launch_conv_tc(const TcMaps& maps, const TcArgs& a, int nsplit, cudaStream_t s) {
+  if (a.T < 1 || a.T > 5 || a.n_out < 1 || a.n_out > 2 || a.out_ldiv < 1) return B2P_ERR_INVALID_ARG;
+  if (nsplit * (A_BYTES + a.T * B_BYTES) * 2 > TC_SMEM_STAGE_REGION) return B2P_ERR_INVALID_ARG;
   if (a.Cout % TC_N || a.C[0] % TC_K || a.C[1] % TC_K || a.RC[0] % TC_K || a.RC[1] % TC_K || a.nrows <= 0) return B2P_ERR_INVALID_ARG;
   if (a.Lrows > 32 || (a.Lrows & (a.Lrows - 1)) || TC_M % a.Lrows) return B2P_ERR_INVALID_ARG;
   if (a.gn_gamma && (TC_N % a.cg != 0)) return B2P_ERR_INVALID_ARG;
-  if (a.headW && a.Cout != TC_N) return B2P_ERR_INVALID_ARG;
-  dim3 grid((a.nrows + TC_M - 1) / TC_M, a.Cout / TC_N, nparity);
+  if (a.headW && (a.Cout != TC_N || a.head_dim > 8)) return B2P_ERR_INVALID_ARG;
+  dim3 grid((a.nrows + TC_M - 1) / TC_M, a.Cout / TC_N, 1);
   return nsplit == 2 ? launch_t<2>(maps, a, grid, s) : launch_t<1>(maps, a, grid, s);
 }
 

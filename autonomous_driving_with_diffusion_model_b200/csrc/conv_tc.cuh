@@ -16,12 +16,17 @@ struct TcMaps {
 struct TcArgs {
   int C[2];               // channels of the (up to two, concatenated) main-phase sources; C[1] may be 0
   int RC[2];              // residual-phase sources (both 0 => no residual conv)
-  int ntaps;
-  int tap_l0[2][5];       // [parity][tap] first input position of the row-shifted box
-  int tap_w[2][5];        // [parity][tap] tap index into the packed weights
+  int T;                  // tap blocks computed by the main phase (packed-weight taps tap0 .. tap0+T-1)
+  int tap0;
+  int n_out;              // outputs per GEMM row: 1 (conv, downsample) or 2 (transposed conv: rows 2m and 2m+1)
+  int nt[2];              // taps contributing to output o
+  int tap_blk[2][5];      // [o][i] tap block
+  int tap_shift[2][5];    // [o][i] row shift: out_o[l] += Y_blk[l + shift]
+  int out_ldiv;           // 2 for the stride-2 conv: only rows l % 2 == 0 emit output row l/2
+  int out_L, out_lmul;    // output row = b*out_L + (l / out_ldiv)*out_lmul + o
   int Cout;
-  int nrows;              // B * Lrows
-  int Lrows, log2L;       // rows per sample in this GEMM
+  int nrows;              // B * Lrows (GEMM rows)
+  int Lrows, log2L;       // GEMM rows per sample (= input positions)
   int samples_per_tile;   // 128 / Lrows
   // epilogue
   const float* bias;
@@ -32,11 +37,10 @@ struct TcArgs {
   const __nv_bfloat16* res_hi; const __nv_bfloat16* res_lo;   // identity residual, bf16 hi/lo
   const float* headW; const float* headB; int head_dim; float* head_out;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
-  int out_L, out_lstride, out_loff0, out_loff1;      // output row = b*out_L + l*out_lstride + out_loff[parity]
 };
 
 int tc_make_act_map(CUtensorMap* m, const void* base, int B, int L, int C, int box_l, int lstride, int box_b);
-int tc_make_weight_map(CUtensorMap* m, const void* base, int rows, int K);
-int launch_conv_tc(const TcMaps& maps, const TcArgs& a, int nsplit, int nparity, cudaStream_t s);
+int tc_make_weight_map(CUtensorMap* m, const void* base, int taps, int Cout, int K, int box_taps);
+int launch_conv_tc(const TcMaps& maps, const TcArgs& a, int nsplit, cudaStream_t s);
 
 }  // namespace b2p
