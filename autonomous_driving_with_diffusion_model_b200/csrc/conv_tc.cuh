@@ -37,6 +37,7 @@ struct TcArgs {
   const __nv_bfloat16* res_hi; const __nv_bfloat16* res_lo;   // identity residual, bf16 hi/lo
   const float* headW; const float* headB; int head_dim; float* head_out;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  int dbg;                // developer bisect switch (B2P_TC_DBG): 1 = skip the TMA/MMA main loop, 2 = skip the epilogue math
 };
 
 int tc_make_act_map(CUtensorMap* m, const void* base, int B, int L, int C, int box_l, int lstride, int box_b);
