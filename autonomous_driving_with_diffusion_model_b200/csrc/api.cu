@@ -85,13 +85,13 @@ struct b2p_handle_s {
   // workspace (activation buffers) for `cap` denoiser rows
   int cap = 0;
   float* d_ws = nullptr;
-  float *d_time_embed = nullptr, *d_mish_cond = nullptr, *d_temb = nullptr, *d_act = nullptr;
+  float *d_time_embed = nullptr, *d_mish_te = nullptr, *d_mish_feat = nullptr, *d_temb = nullptr, *d_act = nullptr;
   int64_t* d_t = nullptr;
 
   // static plan buffers
   int plan_capB = 0, plan_capT = 0;
   float *p_x = nullptr, *p_feat = nullptr, *p_target = nullptr, *p_cond = nullptr, *p_noise = nullptr, *p_traj = nullptr,
-        *p_mask = nullptr, *p_mo = nullptr, *p_action = nullptr, *p_out = nullptr;
+        *p_mask = nullptr, *p_mo = nullptr, *p_action = nullptr, *p_out = nullptr, *p_ttab = nullptr, *p_itab = nullptr, *p_tetab = nullptr;
   int64_t* p_tsteps = nullptr;
   std::vector<GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
@@ -479,7 +479,8 @@ int ensure_workspace(b2p_handle_s* h, int rows) {
   float* p = h->d_ws;
   auto take = [&](size_t n) { float* r = p; p += (n + 63) & ~(size_t)63; return r; };
   h->d_time_embed = take((size_t)cap * h->dim);
-  h->d_mish_cond = take((size_t)cap * 2 * h->dim);
+  h->d_mish_te = take((size_t)cap * h->dim);
+  h->d_mish_feat = take((size_t)cap * h->dim);
   h->d_temb = take((size_t)cap * h->temb_total);
   h->d_act = take((size_t)cap * h->buf_floats_per_sample);
   h->d_res0 = take((size_t)cap * h->H * h->chans[1]);
@@ -494,28 +495,36 @@ inline const float* buf_ptr(b2p_handle_s* h, int id, const float* x) {
   return h->d_act + h->bufs[id].off * (size_t)h->cap;
 }
 
-// the denoiser on `rows` batch rows; x rows may repeat with period x_period (CFG feeds [x; x])
+// the denoiser on `rows` batch rows; x rows may repeat with period x_period (CFG feeds [x; x]).
+// itab/ttab_row != null: "table mode" (inside a plan, no CFG): the per-block time-MLP outputs were precomputed as an
+// image term itab[rows, temb_total] (step-invariant) and a time vector ttab_row[temb_total] for this step, so the
+// embedding kernels are skipped.
 int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, int feat_rows, const int64_t* t, int t_count,
-             const float* cond, float* head_out, float* time_embed_out, int rows, cudaStream_t s, int64_t* launches) {
+             const float* cond, float* head_out, float* time_embed_out, int rows, cudaStream_t s, int64_t* launches,
+             const float* itab = nullptr, const float* ttab_row = nullptr) {
   if (!h->finalized) return h->fail(B2P_ERR_NOT_FINALIZED, "weights not finalized");
   int rc = ensure_workspace(h, rows);
   if (rc) return rc;
   const float* P = h->d_pack;
-  EmbedArgs e{};
-  e.t = t; e.t_count = t_count; e.feat = feat; e.feat_rows = feat_rows; e.cond = cond;
-  e.use_cond = h->cfg.guidance == B2P_FREE_GUIDANCE;
-  e.w1t = P + h->o_w1t; e.b1 = P + h->o_b1; e.w3t = P + h->o_w3t; e.b3 = P + h->o_b3;
-  if (e.use_cond) { e.wc0t = P + h->o_wc0t; e.bc0 = P + h->o_bc0; e.wc2t = P + h->o_wc2t; e.bc2 = P + h->o_bc2; }
-  e.time_embed = time_embed_out ? time_embed_out : h->d_time_embed;
-  e.mish_cond = h->d_mish_cond; e.B = rows; e.dim = h->dim;
-  if ((rc = launch_embed(e, s))) return rc;
-  ++*launches;
-  {  // all 16 block time-MLPs as one GEMM [rows,128] x [128, temb_total]
+  const float* temb_rows = itab;          // per-sample term [rows, temb_total]
+  if (!itab) {
+    EmbedArgs e{};
+    e.t = t; e.t_count = t_count; e.feat = feat; e.feat_rows = feat_rows; e.cond = cond;
+    e.use_cond = h->cfg.guidance == B2P_FREE_GUIDANCE;
+    e.w1t = P + h->o_w1t; e.b1 = P + h->o_b1; e.w3t = P + h->o_w3t; e.b3 = P + h->o_b3;
+    if (e.use_cond) { e.wc0t = P + h->o_wc0t; e.bc0 = P + h->o_bc0; e.wc2t = P + h->o_wc2t; e.bc2 = P + h->o_bc2; }
+    e.time_embed = time_embed_out ? time_embed_out : h->d_time_embed;
+    e.mish_te = h->d_mish_te; e.mish_feat = h->d_mish_feat; e.te_rows = rows; e.feat_out_rows = rows; e.B = rows; e.dim = h->dim;
+    if ((rc = launch_embed(e, s))) return rc;
+    ++*launches;
+    // all 16 block time-MLPs as one GEMM [rows, 2*dim] x [2*dim, temb_total] (the two halves are two K-slabs)
     ConvArgs a{};
-    a.x0 = h->d_mish_cond; a.C0 = 2 * h->dim; a.Lin = a.Lout = 1; a.log2Lout = 0; a.nrows = rows; a.Cout = h->temb_total;
+    a.x0 = h->d_mish_te; a.C0 = h->dim; a.x1 = h->d_mish_feat; a.C1 = h->dim;
+    a.Lin = a.Lout = 1; a.log2Lout = 0; a.nrows = rows; a.Cout = h->temb_total;
     a.taps = 1; a.jmin = a.jmax = 0; a.stride = 1; a.W = P + h->o_tembW; a.bias = P + h->o_tembB; a.out = h->d_temb;
     if ((rc = launch_conv_ffma(a, s))) return rc;
     ++*launches;
+    temb_rows = h->d_temb;
   }
   const int prec = h->cfg.precision;
   const bool tc = prec != B2P_PREC_FP32;
@@ -526,7 +535,9 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
   auto lo_ptr = [&](int id) -> __nv_bfloat16* {
     return (id < 0 || nsplit != 2) ? nullptr : hi_ptr(id) + (size_t)h->bufs[id].L * h->bufs[id].C * h->cap;
   };
-  for (const LayerOp& op : h->ops) {
+  bool proj_done = false;   // residual projection of the raw trajectory already produced by the first conv launch
+  for (size_t oi = 0; oi < h->ops.size(); ++oi) {
+    const LayerOp& op = h->ops[oi];
     if (tc && op.tcW_hi != NPOS) {
       // ------------------------------ tcgen05 path ------------------------------
       TcArgs t;
@@ -575,6 +586,8 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
           }
           if ((rc = tc_make_weight_map(&m.rw[0], P16 + op.tcRW_hi, 1, op.Cout, op.RC0 + op.RC1, 0))) return h->fail(rc, "tensor map (RW)");
           if (nsplit == 2 && (rc = tc_make_weight_map(&m.rw[1], P16 + op.tcRW_lo, 1, op.Cout, op.RC0 + op.RC1, 0))) return h->fail(rc, "tensor map (RW lo)");
+        } else if (proj_done) {
+          t.res_f32 = h->d_res0;
         } else {
           // residual projection of the raw trajectory (C_in = transition_dim): tiny fp32 1x1 conv on CUDA cores
           ConvArgs pr{};
@@ -590,7 +603,7 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
       }
       t.bias = P + op.bias;
       if (op.gamma != NPOS) { t.gn_gamma = P + op.gamma; t.gn_beta = P + op.beta; t.cg = op.Cout / 8; }
-      if (op.temb_off >= 0) { t.temb = h->d_temb + op.temb_off; t.temb_stride = h->temb_total; }
+      if (op.temb_off >= 0) { t.temb = temb_rows + op.temb_off; t.temb_stride = h->temb_total; t.temb2 = ttab_row ? ttab_row + op.temb_off : nullptr; }
       if (op.headW != NPOS) { t.headW = P + op.headW; t.headB = P + op.headB; t.head_dim = op.head_dim; t.head_out = head_out; }
       t.out_hi = hi_ptr(op.out); t.out_lo = lo_ptr(op.out);
       if ((rc = launch_conv_tc(m, t, nsplit, s))) return h->fail(rc, "tcgen05 conv launch failed");
@@ -610,7 +623,7 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
     }
     a.W = P + op.W; a.bias = P + op.bias;
     if (op.gamma != NPOS) { a.gn_gamma = P + op.gamma; a.gn_beta = P + op.beta; a.cg = op.Cout / 8; }
-    if (op.temb_off >= 0) { a.temb = h->d_temb + op.temb_off; a.temb_stride = h->temb_total; }
+    if (op.temb_off >= 0) { a.temb = temb_rows + op.temb_off; a.temb_stride = h->temb_total; a.temb2 = ttab_row ? ttab_row + op.temb_off : nullptr; }
     a.res_id = buf_ptr(h, op.res_id, x);
     if (op.resW != NPOS) {
       a.rx0 = buf_ptr(h, op.rin0, x); a.rx1 = buf_ptr(h, op.rin1, x); a.RC0 = op.RC0; a.RC1 = op.RC1;
@@ -621,6 +634,14 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
     a.out = op.out == BUF_NONE ? nullptr : const_cast<float*>(buf_ptr(h, op.out, x));
     if (tc) {   // CUDA-core layer feeding tensor-core layers: emit bf16 hi/lo instead of fp32
       a.out = nullptr; a.out_hi = hi_ptr(op.out); a.out_lo = lo_ptr(op.out);
+      if (oi + 1 < h->ops.size()) {   // also emit the next launch's 1x1 residual projection of the same input (fp32)
+        const LayerOp& nx = h->ops[oi + 1];
+        if (nx.resW != NPOS && nx.tcRW_hi == NPOS && nx.rin0 == op.in0 && nx.rin1 == BUF_NONE && nx.Lout == op.Lout && nx.Cout == op.Cout) {
+          a.rx0 = buf_ptr(h, nx.rin0, x); a.RC0 = nx.RC0; a.rx0_period = (nx.rin0 == BUF_X) ? x_period : 0;
+          a.resW = P + nx.resW; a.resB = P + nx.resB; a.res_out = h->d_res0;
+          proj_done = true;
+        }
+      }
     }
     if ((rc = launch_conv_ffma(a, s))) return h->fail(rc, "conv launch failed");
     ++*launches;
@@ -784,7 +805,7 @@ int b2p_unet_forward(b2p_handle h, const float* x, const float* feat, int32_t fe
     rc = run_unet(h, x, 0, feat, feat_rows, t, t_count, cond, act, te, B, s, &n);
     if (!rc && out) {
       // out = cat[ cat[0, state_pred(action[:, :-1], te)], action ]  (modeling/temporal.py:237-241)
-      rc = launch_state_pred(h->tp, act, te, out, 1, B, h->H, h->D, s);
+      rc = launch_state_pred(h->tp, act, te, h->dim, out, 1, B, h->H, h->D, s);
       ++n;
     }
     if (scratch) B2P_CUDA_TRY(cudaFreeAsync(scratch, s));
@@ -798,7 +819,7 @@ int b2p_state_pred(b2p_handle h, const float* action, const float* time_embed, f
   if (!h->finalized || !h->has_tp) return h->fail(B2P_ERR_STATE, "model has no state predictor");
   B2P_CUDA_TRY(cudaSetDevice(h->device));
   // state [B, H-1, D-3]: dense rows, no zero row, no action columns
-  return launch_state_pred(h->tp, action, time_embed, state, 0, B, h->H, h->D, (cudaStream_t)stream);
+  return launch_state_pred(h->tp, action, time_embed, h->dim, state, 0, B, h->H, h->D, (cudaStream_t)stream);
 }
 
 int b2p_state_pred_vjp(b2p_handle h, const float* action, const float* time_embed, const float* grad_state, float* grad_action,
@@ -806,7 +827,7 @@ int b2p_state_pred_vjp(b2p_handle h, const float* action, const float* time_embe
   if (!h || !action || !time_embed || !grad_state || !grad_action || B <= 0) return B2P_ERR_INVALID_ARG;
   if (!h->finalized || !h->has_tp) return h->fail(B2P_ERR_STATE, "model has no state predictor");
   B2P_CUDA_TRY(cudaSetDevice(h->device));
-  return launch_state_pred_vjp(h->tp, action, time_embed, grad_state, grad_action, B, h->H, h->D, (cudaStream_t)stream);
+  return launch_state_pred_vjp(h->tp, action, time_embed, h->dim, grad_state, grad_action, B, h->H, h->D, (cudaStream_t)stream);
 }
 
 int b2p_classifier_guidance(b2p_handle h, float* model_output, const float* time_embed, const float* target, float grad_scale,
@@ -814,7 +835,7 @@ int b2p_classifier_guidance(b2p_handle h, float* model_output, const float* time
   if (!h || !model_output || !time_embed || !target || B <= 0) return B2P_ERR_INVALID_ARG;
   if (!h->finalized || !h->has_tp) return h->fail(B2P_ERR_STATE, "model has no state predictor");
   B2P_CUDA_TRY(cudaSetDevice(h->device));
-  return launch_classifier_guidance(h->tp, model_output, time_embed, target, grad_scale, classifier_scale, B, h->H, h->D,
+  return launch_classifier_guidance(h->tp, model_output, time_embed, h->dim, target, grad_scale, classifier_scale, B, h->H, h->D,
                                     (cudaStream_t)stream);
 }
 
@@ -825,7 +846,7 @@ static int ensure_plan_buffers(b2p_handle h, int B, int T) {
   if (h->p_x) { B2P_CUDA_TRY(cudaFree(h->p_x)); h->p_x = nullptr; }
   int cb = B > h->plan_capB ? B : h->plan_capB, ct = T > h->plan_capT ? T : h->plan_capT;
   size_t hd = (size_t)h->H * h->D;
-  size_t floats = (size_t)cb * (hd * 6 + h->dim + 2 + 4 + (size_t)h->H * 3) + (size_t)ct * cb * hd + 64 * 16;
+  size_t floats = (size_t)cb * (hd * 6 + h->dim + 2 + 4 + (size_t)h->H * 3 + h->temb_total) + (size_t)ct * (cb * hd + h->temb_total + h->dim) + 64 * 20;
   B2P_CUDA_TRY(cudaMalloc((void**)&h->p_x, floats * sizeof(float) + sizeof(int64_t) * (ct + 8)));
   float* p = h->p_x;
   auto take = [&](size_t n) { float* r = p; p += (n + 63) & ~(size_t)63; return r; };
@@ -838,6 +859,9 @@ static int ensure_plan_buffers(b2p_handle h, int B, int T) {
   h->p_mo = take(2 * cb * hd);
   h->p_action = take((size_t)cb * h->H * 3);
   h->p_out = take(cb * hd);
+  h->p_itab = take((size_t)cb * h->temb_total);
+  h->p_ttab = take((size_t)ct * h->temb_total);
+  h->p_tetab = take((size_t)ct * h->dim);
   h->p_noise = take((size_t)ct * cb * hd);
   h->p_tsteps = reinterpret_cast<int64_t*>(h->p_x + floats);
   h->plan_capB = cb; h->plan_capT = ct;
@@ -856,6 +880,27 @@ static int enqueue_plan(b2p_handle h, const b2p_plan_config& pc, const GraphKey&
   if (rc) return rc;
   const int g = h->cfg.guidance;
   const bool inpaint = pc.sched.kind == B2P_SCHED_INPAINT_DDIM || pc.sched.kind == B2P_SCHED_INPAINT_DDPM;
+  const bool tables = g != B2P_FREE_GUIDANCE;   // CFG adds cond_mlp(cond) to the time embedding per sample: no shared time vector
+  if (tables) {
+    // once per plan: time table [T, temb_total] (+ bias), image term [B, temb_total], time embeddings [T, dim]
+    const float* P = h->d_pack;
+    const int rows_e = T > B ? T : B;
+    EmbedArgs e{};
+    e.t = h->p_tsteps; e.t_count = T; e.feat = h->p_feat; e.feat_rows = B; e.use_cond = 0;
+    e.w1t = P + h->o_w1t; e.b1 = P + h->o_b1; e.w3t = P + h->o_w3t; e.b3 = P + h->o_b3;
+    e.time_embed = h->p_tetab; e.mish_te = h->d_mish_te; e.mish_feat = h->d_mish_feat; e.te_rows = T; e.feat_out_rows = B;
+    e.B = rows_e; e.dim = h->dim;
+    if ((rc = launch_embed(e, s))) return rc;
+    ConvArgs a{};
+    a.x0 = h->d_mish_te; a.C0 = h->dim; a.Lin = a.Lout = 1; a.nrows = T; a.Cout = h->temb_total; a.taps = 1; a.stride = 1;
+    a.W = P + h->o_tembW; a.bias = P + h->o_tembB; a.out = h->p_ttab;
+    if ((rc = launch_conv_ffma(a, s))) return rc;
+    ConvArgs b{};
+    b.x0 = h->d_mish_feat; b.C0 = h->dim; b.Lin = b.Lout = 1; b.nrows = B; b.Cout = h->temb_total; b.taps = 1; b.stride = 1;
+    b.W = P + h->o_tembW + (size_t)h->dim * h->temb_total; b.out = h->p_itab;
+    if ((rc = launch_conv_ffma(b, s))) return rc;
+    *launches += 3;
+  }
   for (int i = 0; i < T; ++i) {
     int t = (T - 1 - i) * (pc.sched.num_train_timesteps / T);
     b2p_step_coeffs kc;
@@ -868,16 +913,19 @@ static int enqueue_plan(b2p_handle h, const b2p_plan_config& pc, const GraphKey&
       if ((rc = run_unet(h, h->p_x, B, h->p_feat, B, tp, 1, h->p_cond, h->p_mo, nullptr, 2 * B, s, launches))) return rc;
       mo_u = h->p_mo + (size_t)B * hd;
     } else if (g == B2P_CLASSIFIER_GUIDANCE) {
-      if ((rc = run_unet(h, h->p_x, 0, h->p_feat, B, tp, 1, nullptr, h->p_action, h->d_time_embed, B, s, launches))) return rc;
-      if ((rc = launch_state_pred(h->tp, h->p_action, h->d_time_embed, h->p_mo, 1, B, h->H, h->D, s))) return rc;
+      const float* te_row = h->p_tetab + (size_t)i * h->dim;   // one time embedding shared by the batch (stride 0)
+      if ((rc = run_unet(h, h->p_x, 0, h->p_feat, B, tp, 1, nullptr, h->p_action, nullptr, B, s, launches, h->p_itab,
+                         h->p_ttab + (size_t)i * h->temb_total))) return rc;
+      if ((rc = launch_state_pred(h->tp, h->p_action, te_row, 0, h->p_mo, 1, B, h->H, h->D, s))) return rc;
       ++*launches;
       if (!inpaint && k.has_target) {
-        if ((rc = launch_classifier_guidance(h->tp, h->p_mo, h->d_time_embed, h->p_target, kc.guidance_grad_scale,
+        if ((rc = launch_classifier_guidance(h->tp, h->p_mo, te_row, 0, h->p_target, kc.guidance_grad_scale,
                                              pc.classifier_scale, B, h->H, h->D, s))) return rc;
         ++*launches;
       }
     } else {
-      if ((rc = run_unet(h, h->p_x, 0, h->p_feat, B, tp, 1, nullptr, h->p_mo, nullptr, B, s, launches))) return rc;
+      if ((rc = run_unet(h, h->p_x, 0, h->p_feat, B, tp, 1, nullptr, h->p_mo, nullptr, B, s, launches, h->p_itab,
+                         h->p_ttab + (size_t)i * h->temb_total))) return rc;
     }
     int flags = B2P_STEP_ZERO_FIRST_WAYPOINT;
     bool last = (i == T - 1);
@@ -911,7 +959,7 @@ static int plan_impl(b2p_handle h, const b2p_plan_config* pc, const float* x_ini
   B2P_CUDA_TRY(cudaSetDevice(h->device));
   int rc;
   if ((rc = ensure_plan_buffers(h, B, T))) return rc;
-  if ((rc = ensure_workspace(h, g == B2P_FREE_GUIDANCE ? 2 * B : B))) return rc;
+  if ((rc = ensure_workspace(h, g == B2P_FREE_GUIDANCE ? 2 * B : (B > T ? B : T)))) return rc;
   const size_t hd = (size_t)h->H * h->D;
   const cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   B2P_CUDA_TRY(cudaMemcpyAsync(h->p_x, x_init, sizeof(float) * B * hd, kind, s));

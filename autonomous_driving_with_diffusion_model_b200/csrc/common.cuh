@@ -39,6 +39,7 @@ struct ConvArgs {
   const float* gn_gamma; const float* gn_beta;  // null => no GroupNorm/Mish
   int cg;                             // channels per group (Cout/8)
   const float* temb; int temb_stride; // + temb[b*temb_stride + co]
+  const float* temb2;                 // + temb2[co] (per-step time term shared by the whole batch), may be null
   const float* res_id;                // identity residual [nrows, Cout]
   const float* rx0; const float* rx1; int RC0, RC1;  // residual 1x1 conv inputs (same Lout rows)
   const float* resW; const float* resB;              // [RC0+RC1][Cout], [Cout]
@@ -59,8 +60,10 @@ struct EmbedArgs {
   const float* w1t; const float* b1;  // time_mlp.1 transposed [dim][4dim]
   const float* w3t; const float* b3;  // time_mlp.3 transposed [4dim][dim]
   const float* wc0t; const float* bc0; const float* wc2t; const float* bc2;  // cond_mlp transposed
-  float* time_embed;                  // [B, dim]
-  float* mish_cond;                   // [B, 2*dim] = Mish(cat[time_embed, feat])
+  float* time_embed;                  // [te_rows, dim] (may be null)
+  float* mish_te;                     // [te_rows, dim]   = Mish(time_embed)         } the two halves of
+  float* mish_feat;                   // [feat_out_rows, dim] = Mish(feat)           } Mish(cat[time_embed, feat])
+  int te_rows, feat_out_rows;         // rows written to each output (<= B)
   int B, dim;
 };
 int launch_embed(const EmbedArgs& a, cudaStream_t s);
@@ -94,11 +97,12 @@ struct TrajPredWeights {
   const float* in_w_raw;                         // [64][3]
 };
 // full_output == 0: out = state [B, H-1, D-3];  == 1: out = cat[cat[0, state], action] [B, H, D] (temporal.py:237-241)
-int launch_state_pred(const TrajPredWeights& w, const float* action, const float* time_embed, float* out, int full_output,
+// te_stride: row stride of time_embed in floats (dim, or 0 when one row is shared by the whole batch)
+int launch_state_pred(const TrajPredWeights& w, const float* action, const float* time_embed, int te_stride, float* out, int full_output,
                       int B, int H, int D, cudaStream_t s);
-int launch_state_pred_vjp(const TrajPredWeights& w, const float* action, const float* time_embed, const float* grad_state,
+int launch_state_pred_vjp(const TrajPredWeights& w, const float* action, const float* time_embed, int te_stride, const float* grad_state,
                           float* grad_action, int B, int H, int D, cudaStream_t s);
-int launch_classifier_guidance(const TrajPredWeights& w, float* model_output, const float* time_embed, const float* target,
+int launch_classifier_guidance(const TrajPredWeights& w, float* model_output, const float* time_embed, int te_stride, const float* target,
                                float grad_scale, float scale, int B, int H, int D, cudaStream_t s);
 
 __device__ __forceinline__ float mish_f(float x) {

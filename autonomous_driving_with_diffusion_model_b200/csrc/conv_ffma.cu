@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(NT) conv_ffma_kernel(ConvArgs a) {
   }
 
   const int gc = col0 + tx * 4;  // global column of this thread's 4 outputs
-  float4 bias4 = __ldg(reinterpret_cast<const float4*>(a.bias + gc));
+  float4 bias4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + gc)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int r = 0; r < RM; ++r) { acc[r][0] += bias4.x; acc[r][1] += bias4.y; acc[r][2] += bias4.z; acc[r][3] += bias4.w; }
 
@@ -215,6 +215,10 @@ __global__ void __launch_bounds__(NT) conv_ffma_kernel(ConvArgs a) {
     bool ok = grow < a.nrows;
     if (a.temb && ok) {
       float4 t4 = __ldg(reinterpret_cast<const float4*>(a.temb + (size_t)(grow >> a.log2Lout) * a.temb_stride + gc));
+      acc[r][0] += t4.x; acc[r][1] += t4.y; acc[r][2] += t4.z; acc[r][3] += t4.w;
+    }
+    if (a.temb2) {
+      float4 t4 = __ldg(reinterpret_cast<const float4*>(a.temb2 + gc));
       acc[r][0] += t4.x; acc[r][1] += t4.y; acc[r][2] += t4.z; acc[r][3] += t4.w;
     }
     if (a.res_id && ok) {

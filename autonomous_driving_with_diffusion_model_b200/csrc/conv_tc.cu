@@ -313,10 +313,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int b = (int)(grow >> a.log2L), l = (int)(grow & (L - 1));
     float (*xchg)[4] = reinterpret_cast<float (*)[4]>(smem);
     float (*headp)[4][8] = reinterpret_cast<float (*)[4][8]>(smem + EPI_XCHG_BYTES);
+    const int gcol = n0 + col0;
+    // everything that is added AFTER GroupNorm/Mish (time embedding terms, identity residual, residual-conv bias) is
+    // fetched from global memory now, while the tensor core is still busy
+    float addv[EPI_COLS];
+#pragma unroll
+    for (int c = 0; c < EPI_COLS; ++c) addv[c] = res_iters > 0 ? bars->resb[col0 + c] : 0.f;
+    if (row_ok) {
+      if (a.temb) {
+        const float* tp = a.temb + (size_t)b * a.temb_stride + gcol;
+#pragma unroll
+        for (int c = 0; c < EPI_COLS; c += 4) { float4 t4 = __ldg(reinterpret_cast<const float4*>(tp + c)); addv[c] += t4.x; addv[c + 1] += t4.y; addv[c + 2] += t4.z; addv[c + 3] += t4.w; }
+      }
+      if (a.temb2) {
+#pragma unroll
+        for (int c = 0; c < EPI_COLS; c += 4) { float4 t4 = __ldg(reinterpret_cast<const float4*>(a.temb2 + gcol + c)); addv[c] += t4.x; addv[c + 1] += t4.y; addv[c + 2] += t4.z; addv[c + 3] += t4.w; }
+      }
+      if (a.res_f32) {
+        const float* q = a.res_f32 + (size_t)grow * a.Cout + gcol;
+#pragma unroll
+        for (int c = 0; c < EPI_COLS; c += 4) { float4 t4 = __ldg(reinterpret_cast<const float4*>(q + c)); addv[c] += t4.x; addv[c + 1] += t4.y; addv[c + 2] += t4.z; addv[c + 3] += t4.w; }
+      }
+      if (a.res_hi) {
+        const uint4* qh = reinterpret_cast<const uint4*>(a.res_hi + (size_t)grow * a.Cout + gcol);
+        const uint4* ql = a.res_lo ? reinterpret_cast<const uint4*>(a.res_lo + (size_t)grow * a.Cout + gcol) : nullptr;
+#pragma unroll
+        for (int c8 = 0; c8 < EPI_COLS / 8; ++c8) {
+          uint4 hh = __ldg(qh + c8);
+          const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hh);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) addv[c8 * 8 + i] += __bfloat162float(hp[i]);
+          if (ql) {
+            uint4 ll = __ldg(ql + c8);
+            const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&ll);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) addv[c8 * 8 + i] += __bfloat162float(lp[i]);
+          }
+        }
+      }
+    }
     mbar_wait(&bars->tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + col0;
-    const int gcol = n0 + col0;
     const int n_out = (a.dbg & 2) ? 0 : a.n_out;
 
     for (int o = 0; o < n_out; ++o) {
@@ -347,40 +385,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
       const bool ok = row_ok && (a.out_ldiv == 1 || (l % a.out_ldiv) == 0);
-      if (a.temb && ok) {
-        const float* tp = a.temb + (size_t)b * a.temb_stride + gcol;
 #pragma unroll
-        for (int c = 0; c < EPI_COLS; c += 4) { float4 t4 = __ldg(reinterpret_cast<const float4*>(tp + c)); v[c] += t4.x; v[c + 1] += t4.y; v[c + 2] += t4.z; v[c + 3] += t4.w; }
-      }
+      for (int c = 0; c < EPI_COLS; ++c) v[c] += addv[c];
       if (res_iters > 0) {   // residual 1x1 conv accumulated in the TMEM block after the tap blocks
         float rv[EPI_COLS];
         tmem_ld16(taddr + T * TC_N, rv);
 #pragma unroll
-        for (int c = 0; c < EPI_COLS; ++c) v[c] += rv[c] + bars->resb[col0 + c];
+        for (int c = 0; c < EPI_COLS; ++c) v[c] += rv[c];
       }
       if (ok) {
-        if (a.res_f32) {
-          const float* q = a.res_f32 + (size_t)grow * a.Cout + gcol;
-#pragma unroll
-          for (int c = 0; c < EPI_COLS; c += 4) { float4 t4 = __ldg(reinterpret_cast<const float4*>(q + c)); v[c] += t4.x; v[c + 1] += t4.y; v[c + 2] += t4.z; v[c + 3] += t4.w; }
-        }
-        if (a.res_hi) {
-          const uint4* qh = reinterpret_cast<const uint4*>(a.res_hi + (size_t)grow * a.Cout + gcol);
-          const uint4* ql = a.res_lo ? reinterpret_cast<const uint4*>(a.res_lo + (size_t)grow * a.Cout + gcol) : nullptr;
-#pragma unroll
-          for (int c8 = 0; c8 < EPI_COLS / 8; ++c8) {
-            uint4 hh = __ldg(qh + c8);
-            const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hh);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[c8 * 8 + i] += __bfloat162float(hp[i]);
-            if (ql) {
-              uint4 ll = __ldg(ql + c8);
-              const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&ll);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[c8 * 8 + i] += __bfloat162float(lp[i]);
-            }
-          }
-        }
         const size_t orow = (size_t)b * a.out_L + (size_t)(l / a.out_ldiv) * a.out_lmul + o;
         if (a.out_hi) {
           uint4* oh = reinterpret_cast<uint4*>(a.out_hi + orow * a.Cout + gcol);

@@ -32,6 +32,7 @@ struct TcArgs {
   const float* bias;
   const float* gn_gamma; const float* gn_beta; int cg;
   const float* temb; int temb_stride;
+  const float* temb2;     // per-step time term shared by the batch (may be null)
   const float* resB;
   const float* res_f32;                              // identity residual, fp32 [nrows, Cout]
   const __nv_bfloat16* res_hi; const __nv_bfloat16* res_lo;   // identity residual, bf16 hi/lo

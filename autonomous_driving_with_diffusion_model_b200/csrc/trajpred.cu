@@ -216,14 +216,14 @@ __device__ void encoder_layer_bwd(TpSmem& sm, int l, const TrajPredWeights::Laye
 // MODE 0: forward only; 1: guidance update; 2: VJP with an arbitrary cotangent `target` = grad_state [B,S,SD] -> out = grad_action [B,H,3]
 template <int MODE>
 __global__ void __launch_bounds__(TP_NT) trajpred_kernel(TrajPredWeights w, const float* __restrict__ action, int action_stride,
-                                                         int action_col0, const float* __restrict__ time_embed, float* out, int full,
+                                                         int action_col0, const float* __restrict__ time_embed, int te_stride, float* out, int full,
                                                          int state_given, const float* __restrict__ target, float grad_scale,
                                                          float scale_state, float scale_action, int H, int D) {
   extern __shared__ __align__(16) unsigned char raw[];
   TpSmem& sm = *reinterpret_cast<TpSmem*>(raw);
   const int b = blockIdx.x, tid = threadIdx.x, S = H - 1, SD = D - 3;
   for (int i = tid; i < S * 3; i += TP_NT) sm.act[(i / 3) * 4 + i % 3] = action[((size_t)b * H + i / 3) * action_stride + action_col0 + i % 3];
-  if (tid < TP_D) sm.te[tid] = time_embed[(size_t)b * TP_D + tid];
+  if (tid < TP_D) sm.te[tid] = time_embed[(size_t)b * te_stride + tid];
   __syncthreads();
   for (int i = tid; i < S * TP_D; i += TP_NT) {   // x0 = input_proj(action) + pos + time_embed
     int s = i / TP_D, n = i % TP_D;
@@ -345,29 +345,29 @@ __global__ void __launch_bounds__(TP_NT) trajpred_kernel(TrajPredWeights w, cons
 
 static int tp_check(int H, int D) { return (H - 1 > TP_MAXS || H < 2 || D - 3 > 4 || D - 3 < 2) ? B2P_ERR_INVALID_ARG : B2P_OK; }
 
-int launch_state_pred(const TrajPredWeights& w, const float* action, const float* time_embed, float* out, int full_output, int B,
+int launch_state_pred(const TrajPredWeights& w, const float* action, const float* time_embed, int te_stride, float* out, int full_output, int B,
                       int H, int D, cudaStream_t s) {
   if (tp_check(H, D)) return B2P_ERR_INVALID_ARG;
   B2P_CUDA_TRY(cudaFuncSetAttribute(trajpred_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TpSmem)));
-  trajpred_kernel<0><<<B, TP_NT, sizeof(TpSmem), s>>>(w, action, 3, 0, time_embed, out, full_output, 0, nullptr, 0.f, 0.f, 0.f, H, D);
+  trajpred_kernel<0><<<B, TP_NT, sizeof(TpSmem), s>>>(w, action, 3, 0, time_embed, te_stride, out, full_output, 0, nullptr, 0.f, 0.f, 0.f, H, D);
   return (int)cudaGetLastError();
 }
 
-int launch_classifier_guidance(const TrajPredWeights& w, float* model_output, const float* time_embed, const float* target,
+int launch_classifier_guidance(const TrajPredWeights& w, float* model_output, const float* time_embed, int te_stride, const float* target,
                                float grad_scale, float scale, int B, int H, int D, cudaStream_t s) {
   if (tp_check(H, D)) return B2P_ERR_INVALID_ARG;
   B2P_CUDA_TRY(cudaFuncSetAttribute(trajpred_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TpSmem)));
   float scale_state = (float)((double)scale / 15.0);   // quirk 5 (control/guidance.py:56)
-  trajpred_kernel<1><<<B, TP_NT, sizeof(TpSmem), s>>>(w, model_output, D, D - 3, time_embed, model_output, 1, 1, target, grad_scale,
+  trajpred_kernel<1><<<B, TP_NT, sizeof(TpSmem), s>>>(w, model_output, D, D - 3, time_embed, te_stride, model_output, 1, 1, target, grad_scale,
                                                          scale_state, scale, H, D);
   return (int)cudaGetLastError();
 }
 
-int launch_state_pred_vjp(const TrajPredWeights& w, const float* action, const float* time_embed, const float* grad_state,
+int launch_state_pred_vjp(const TrajPredWeights& w, const float* action, const float* time_embed, int te_stride, const float* grad_state,
                           float* grad_action, int B, int H, int D, cudaStream_t s) {
   if (tp_check(H, D)) return B2P_ERR_INVALID_ARG;
   B2P_CUDA_TRY(cudaFuncSetAttribute(trajpred_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TpSmem)));
-  trajpred_kernel<2><<<B, TP_NT, sizeof(TpSmem), s>>>(w, action, 3, 0, time_embed, grad_action, 0, 0, grad_state, 0.f, 0.f, 0.f, H, D);
+  trajpred_kernel<2><<<B, TP_NT, sizeof(TpSmem), s>>>(w, action, 3, 0, time_embed, te_stride, grad_action, 0, 0, grad_state, 0.f, 0.f, 0.f, H, D);
   return (int)cudaGetLastError();
 }
 
