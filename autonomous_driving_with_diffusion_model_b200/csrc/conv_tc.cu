@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "conv_tc.cuh"
@@ -33,6 +34,7 @@ constexpr int TC_THREADS = 512;
 constexpr int EPI_COLS = 16;          // columns per epilogue thread
 constexpr int A_BYTES = TC_M * TC_K * 2;   // 16 KB
 constexpr int B_BYTES = TC_N * TC_K * 2;   //  8 KB
+constexpr int SLOT_BYTES = 16 * 1024;      // TMA ring slot
 
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -77,9 +79,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
   return d;
 }
-// kind::f16: D fp32, A/B bf16, both K-major, M=128, N=64
-__device__ __forceinline__ constexpr uint32_t umma_idesc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// kind::f16: D fp32, A/B bf16, both K-major, M=128, N=n (multiple of 16, <= 256)
+__device__ __forceinline__ constexpr uint32_t umma_idesc_n(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -170,23 +172,43 @@ __device__ __forceinline__ void group_norm_mish16(float (&v)[EPI_COLS], int L, i
 }
 
 struct __align__(16) TcBarriers {
-  uint64_t full[8];
-  uint64_t empty[8];
+  uint64_t full[16];
+  uint64_t empty[16];
   uint64_t tmem_full;
   uint32_t tmem_base;
   uint32_t pad;
   float bias[TC_N], gamma[TC_N], beta[TC_N], resb[TC_N];   // per-tile epilogue vectors
 };
-// epilogue scratch aliases the (by then idle) TMA ring: xchg[128][4] GroupNorm partial sums, head[128][4][8] partial dots
+// epilogue scratch aliases the (by then idle) TMA ring:
+//   red[2][KS][128/KS][64] fp32   split-K partial tiles received from the cluster peers        (64 KB)
+//   xchg[128][4]                  GroupNorm partial sums between column slices                  ( 2 KB)
+//   head[128][4][8]               fused-head partial dot products                               (16 KB)
+constexpr int EPI_RED_BYTES = 2 * TC_M * TC_N * 4;
 constexpr int EPI_XCHG_BYTES = TC_M * 4 * 4;
 
 constexpr int TC_SMEM_STAGE_REGION = 224 * 1024;   // bytes available to the TMA ring
 constexpr int TC_SMEM_TOTAL = TC_SMEM_STAGE_REGION + 1024 /*alignment slack*/ + (int)sizeof(TcBarriers);
 
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t local_saddr, uint32_t cta, float x, float y, float z, float w) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(cta));
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
 // "taps in N": one pass over the activations computes Y_t = A * W_t^T for every tap t into its own 64-column TMEM
 // block; the conv sum  out[l] = sum_t Y_t[l + shift_t]  is a ROW shift of the accumulator, done in the epilogue with warp
 // shuffles (the L rows of a sample are adjacent lanes).  The activation tile is therefore loaded once per 64-channel
 // chunk instead of once per tap, and zero padding is just "source lane outside the sample".
+//
+// Split-K over a thread-block cluster (gridDim.z == cluster size KS): the 64-channel K chunks of a layer are dealt
+// round-robin to the KS CTAs of a cluster, so KS times more SMs stream the layer's weights/activations.  Each CTA
+// combines its taps, then the partial [128 x 64] tiles are reduce-scattered BY ROWS through distributed shared memory:
+// CTA j receives rows [j*128/KS, (j+1)*128/KS) from every peer, sums them in a fixed order (deterministic) and runs
+// the GroupNorm/Mish/residual epilogue for those rows only (whole samples, so GroupNorm stays CTA-local).
 template <int NSPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -194,13 +216,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + TC_SMEM_STAGE_REGION);
 
   const int T = a.T;
-  const int stage_bytes = NSPLIT * (A_BYTES + T * B_BYTES);
+  const int stage_bytes = NSPLIT * (A_BYTES + T * B_BYTES);   // [A hi | A lo | W hi (T taps) | W lo (T taps)]
   int stages = TC_SMEM_STAGE_REGION / stage_bytes;
   if (stages > 8) stages = 8;
   const uint32_t tmem_cols = (T + 1) * TC_N <= 128 ? 128u : ((T + 1) * TC_N <= 256 ? 256u : 512u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x, n0 = blockIdx.y * TC_N;
+  const int KS = gridDim.z, rank = blockIdx.z;      // cluster = (1, 1, KS): rank == %cluster_ctarank
   const int b0 = tile_m * a.samples_per_tile;
 
   const int chunks0 = a.C[0] / TC_K, chunks1 = a.C[1] / TC_K;
@@ -208,6 +231,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int rchunks0 = a.RC[0] / TC_K, rchunks1 = a.RC[1] / TC_K;
   const int res_iters = rchunks0 + rchunks1;
   const int total_iters = (a.dbg & 1) ? 0 : main_iters + res_iters;
+  // this CTA's share: global iterations rank, rank + KS, ...
+  const int n_local = total_iters > rank ? (total_iters - rank + KS - 1) / KS : 0;
+  const int n_main_local = (a.dbg & 1) ? 0 : (main_iters > rank ? (main_iters - rank + KS - 1) / KS : 0);
+  const int n_res_local = n_local - n_main_local;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
@@ -221,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + TC_N) {   // stage the tile's epilogue vectors
     const int c = threadIdx.x - 64;
-    bars->bias[c] = __ldg(a.bias + n0 + c);
+    bars->bias[c] = a.bias ? __ldg(a.bias + n0 + c) : 0.f;
     bars->gamma[c] = a.gn_gamma ? __ldg(a.gn_gamma + n0 + c) : 1.f;
     bars->beta[c] = a.gn_gamma ? __ldg(a.gn_beta + n0 + c) : 0.f;
     bars->resb[c] = a.resB ? __ldg(a.resB + n0 + c) : 0.f;
@@ -236,9 +263,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     prefetch_tmap(&maps.a[0][0]);
     prefetch_tmap(&maps.w[0]);
     if (NSPLIT == 2) { prefetch_tmap(&maps.a[0][1]); prefetch_tmap(&maps.w[1]); }
-    for (int it = 0; it < total_iters; ++it) {
-      const int s = it % stages;
-      const uint32_t ph = (it / stages) & 1;
+    for (int j = 0; j < n_local; ++j) {
+      const int it = rank + j * KS;
+      const int s = j % stages;
+      const uint32_t ph = (j / stages) & 1;
       mbar_wait(&bars->empty[s], ph ^ 1);
       uint8_t* st = smem + s * stage_bytes;
       uint8_t* sb = st + NSPLIT * A_BYTES;
@@ -267,31 +295,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else if (threadIdx.x == 32) {
     // =============================== MMA issuer (one thread) ===============================
-    const uint32_t idesc = umma_idesc();
-    for (int it = 0; it < total_iters; ++it) {
-      const int s = it % stages;
-      const uint32_t ph = (it / stages) & 1;
+    // All taps of a chunk are adjacent in shared memory ([T*64 rows] x 128 B, K-major), so ONE tcgen05.mma with
+    // N = T*64 (<= 256; a fifth tap takes a second N = 64 instruction) covers them: the issuing thread stays far ahead
+    // of the tensor pipe.  Descriptors are built once per stage and advanced by adding to the address field.
+    const int nA = T < 4 ? T : 4;                                       // taps covered by the first instruction
+    const uint32_t idescA = umma_idesc_n(nA * TC_N), idescB = umma_idesc_n(TC_N);
+    bool main_first = true, res_first = true;
+    for (int j = 0; j < n_local; ++j) {
+      const int it = rank + j * KS;
+      const int s = j % stages;
+      const uint32_t ph = (j / stages) & 1;
       mbar_wait(&bars->full[s], ph);
       tc_fence_after();
       const uint32_t sa = smem_u32(smem + s * stage_bytes);
       const uint32_t sb = sa + NSPLIT * A_BYTES;
       const bool res_phase = it >= main_iters;
-      const int nblk = res_phase ? 1 : T;
-      const uint32_t dbase = tmem_base + (res_phase ? T * TC_N : 0);
-      const bool first = res_phase ? (it == main_iters) : (it == 0);
+      const bool first = res_phase ? res_first : main_first;
+      if (res_phase) res_first = false; else main_first = false;
+      const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + A_BYTES);
+      const uint64_t b_hi = umma_desc(sb), b_lo = umma_desc(sb + T * B_BYTES);
+      if (!res_phase) {
 #pragma unroll
-      for (int k = 0; k < TC_K / TC_UMMA_K; ++k) {
-        const uint32_t koff = k * TC_UMMA_K * 2;   // bytes inside the 128B swizzle row
-        const uint64_t a_hi = umma_desc(sa + koff);
-        const uint64_t a_lo = umma_desc(sa + A_BYTES + koff);
-        for (int t = 0; t < nblk; ++t) {
-          const uint32_t d = dbase + t * TC_N;
-          const uint64_t b_hi = umma_desc(sb + t * B_BYTES + koff);
-          umma(d, a_hi, b_hi, idesc, (first && k == 0) ? 0u : 1u);
+        for (int k = 0; k < TC_K / TC_UMMA_K; ++k) {
+          const uint64_t ko = (uint64_t)(k * TC_UMMA_K * 2 / 16);       // +32 B per K step, in 16-byte units
+          const uint32_t acc = (first && k == 0) ? 0u : 1u;
+          umma(tmem_base, a_hi + ko, b_hi + ko, idescA, acc);
           if (NSPLIT == 2) {
-            const uint64_t b_lo = umma_desc(sb + (T + t) * B_BYTES + koff);
-            umma(d, a_lo, b_hi, idesc, 1u);
-            umma(d, a_hi, b_lo, idesc, 1u);
+            umma(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);
+            umma(tmem_base, a_hi + ko, b_lo + ko, idescA, 1u);
+          }
+          if (T > 4) {
+            const uint64_t t4 = (uint64_t)(4 * B_BYTES / 16);
+            umma(tmem_base + 4 * TC_N, a_hi + ko, b_hi + t4 + ko, idescB, acc);
+            if (NSPLIT == 2) {
+              umma(tmem_base + 4 * TC_N, a_lo + ko, b_hi + t4 + ko, idescB, 1u);
+              umma(tmem_base + 4 * TC_N, a_hi + ko, b_lo + t4 + ko, idescB, 1u);
+            }
+          }
+        }
+      } else {
+        const uint32_t d = tmem_base + T * TC_N;
+#pragma unroll
+        for (int k = 0; k < TC_K / TC_UMMA_K; ++k) {
+          const uint64_t ko = (uint64_t)(k * TC_UMMA_K * 2 / 16);
+          umma(d, a_hi + ko, b_hi + ko, idescB, (first && k == 0) ? 0u : 1u);
+          if (NSPLIT == 2) {
+            umma(d, a_lo + ko, b_hi + ko, idescB, 1u);
+            umma(d, a_hi + ko, b_lo + ko, idescB, 1u);
           }
         }
       }
@@ -308,12 +358,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int col0 = slice * EPI_COLS;
     const int r = quad * 32 + lane;                 // tile row == TMEM lane
     const int L = a.Lrows;
+    const int rows_per_owner = TC_M / KS;
+    const int r_local = r % rows_per_owner;
+    const bool own = (r / rows_per_owner) == rank;  // this CTA finishes row r
     const long grow = (long)tile_m * TC_M + r;
-    const bool row_ok = grow < a.nrows;
+    const bool row_ok = own && grow < a.nrows;
     const int b = (int)(grow >> a.log2L), l = (int)(grow & (L - 1));
-    float (*xchg)[4] = reinterpret_cast<float (*)[4]>(smem);
-    float (*headp)[4][8] = reinterpret_cast<float (*)[4][8]>(smem + EPI_XCHG_BYTES);
+    float* red = reinterpret_cast<float*>(smem);                                                  // [2][KS][rows_per_owner][64]
+    float (*xchg)[4] = reinterpret_cast<float (*)[4]>(smem + EPI_RED_BYTES);
+    float (*headp)[4][8] = reinterpret_cast<float (*)[4][8]>(smem + EPI_RED_BYTES + EPI_XCHG_BYTES);
     const int gcol = n0 + col0;
+    const int n_out = (a.dbg & 2) ? 0 : a.n_out;
     // everything that is added AFTER GroupNorm/Mish (time embedding terms, identity residual, residual-conv bias) is
     // fetched from global memory now, while the tensor core is still busy
     float addv[EPI_COLS];
@@ -355,27 +410,67 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     mbar_wait(&bars->tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + col0;
-    const int n_out = (a.dbg & 2) ? 0 : a.n_out;
 
-    for (int o = 0; o < n_out; ++o) {
-      float v[EPI_COLS];
+    // ---- this CTA's partial results: slot o = output o (tap-combined), slot 1 = residual 1x1 block when n_out == 1 ----
+    float part[2][EPI_COLS];
 #pragma unroll
-      for (int c = 0; c < EPI_COLS; ++c) v[c] = bars->bias[col0 + c];
-      // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the sample) ----
-      for (int i = 0; i < a.nt[o]; ++i) {
-        const int t = a.tap_blk[o][i], d = a.tap_shift[o][i];
-        const bool valid = (l + d >= 0) && (l + d < L);
-        const int src = (lane + d) & 31;
-        float y[EPI_COLS];
-        tmem_ld16(taddr + t * TC_N, y);
-        if (d == 0) {
+    for (int c = 0; c < EPI_COLS; ++c) { part[0][c] = 0.f; part[1][c] = 0.f; }
+    if (n_main_local > 0) {
 #pragma unroll
-          for (int c = 0; c < EPI_COLS; ++c) v[c] += y[c];
-        } else {
+      for (int o = 0; o < 2; ++o) {
+        if (o >= n_out) break;
+        for (int i = 0; i < a.nt[o]; ++i) {
+          const int t = a.tap_blk[o][i], d = a.tap_shift[o][i];
+          const bool valid = (l + d >= 0) && (l + d < L);
+          const int src = (lane + d) & 31;
+          float y[EPI_COLS];
+          tmem_ld16(taddr + t * TC_N, y);
+          if (d == 0) {
 #pragma unroll
-          for (int c = 0; c < EPI_COLS; ++c) { float g = __shfl_sync(0xffffffffu, y[c], src); v[c] += valid ? g : 0.f; }
+            for (int c = 0; c < EPI_COLS; ++c) part[o][c] += y[c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < EPI_COLS; ++c) { float g = __shfl_sync(0xffffffffu, y[c], src); part[o][c] += valid ? g : 0.f; }
+          }
         }
       }
+    }
+    const bool has_res = res_iters > 0;
+    if (has_res && n_res_local > 0) tmem_ld16(taddr + T * TC_N, part[1]);
+    const int nslots = (n_out == 2 || has_res) ? 2 : 1;
+
+    if (KS > 1 && !(a.dbg & 4)) {
+      // ---- reduce-scatter by rows through distributed shared memory ----
+      cluster_sync_all();                            // every peer's TMA ring is idle: its memory may be overwritten
+      const uint32_t owner = (uint32_t)(r / rows_per_owner);
+      for (int sl = 0; sl < nslots; ++sl) {
+        const uint32_t dst = smem_u32(red + (((size_t)sl * KS + rank) * rows_per_owner + r_local) * TC_N + col0);
+#pragma unroll
+        for (int c = 0; c < EPI_COLS; c += 4)
+          st_cluster_f4(dst + c * 4, owner, sl == 0 ? part[0][c] : part[1][c], sl == 0 ? part[0][c + 1] : part[1][c + 1],
+                        sl == 0 ? part[0][c + 2] : part[1][c + 2], sl == 0 ? part[0][c + 3] : part[1][c + 3]);
+      }
+      cluster_sync_all();                            // all partial tiles have landed
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        if (sl >= nslots) break;
+#pragma unroll
+        for (int c = 0; c < EPI_COLS; ++c) part[sl][c] = 0.f;
+        for (int srcc = 0; srcc < KS; ++srcc) {      // fixed summation order => deterministic
+          const float4* q = reinterpret_cast<const float4*>(red + (((size_t)sl * KS + srcc) * rows_per_owner + r_local) * TC_N + col0);
+#pragma unroll
+          for (int c4 = 0; c4 < EPI_COLS / 4; ++c4) { float4 t4 = q[c4]; part[sl][c4 * 4] += t4.x; part[sl][c4 * 4 + 1] += t4.y; part[sl][c4 * 4 + 2] += t4.z; part[sl][c4 * 4 + 3] += t4.w; }
+        }
+      }
+      __syncthreads();                               // red[] fully consumed before xchg/head scratch (disjoint) — keeps phases tidy
+    }
+
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      if (o >= n_out) break;
+      float v[EPI_COLS];
+#pragma unroll
+      for (int c = 0; c < EPI_COLS; ++c) v[c] = part[o][c] + bars->bias[col0 + c];
       if (a.gn_gamma) {
         switch (a.cg) {
           case 8: group_norm_mish16<8>(v, L, r, slice, xchg, bars->gamma + col0, bars->beta + col0); break;
@@ -387,11 +482,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const bool ok = row_ok && (a.out_ldiv == 1 || (l % a.out_ldiv) == 0);
 #pragma unroll
       for (int c = 0; c < EPI_COLS; ++c) v[c] += addv[c];
-      if (res_iters > 0) {   // residual 1x1 conv accumulated in the TMEM block after the tap blocks
-        float rv[EPI_COLS];
-        tmem_ld16(taddr + T * TC_N, rv);
+      if (has_res) {
 #pragma unroll
-        for (int c = 0; c < EPI_COLS; ++c) v[c] += rv[c];
+        for (int c = 0; c < EPI_COLS; ++c) v[c] += part[1][c];
       }
       if (ok) {
         const size_t orow = (size_t)b * a.out_L + (size_t)(l / a.out_ldiv) * a.out_lmul + o;
@@ -491,20 +584,39 @@ template <int NSPLIT>
 static int launch_t(const TcMaps& maps, const TcArgs& a, dim3 grid, cudaStream_t s) {
   constexpr int smem = TC_SMEM_TOTAL;
   B2P_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  conv_tc_kernel<NSPLIT><<<grid, TC_THREADS, smem, s>>>(maps, a);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = grid.z;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<NSPLIT>, maps, a);
+}
+
+// split-K factor: as many cluster CTAs as (a) there are K chunks, (b) keeps whole samples per owner (128/KS >= L),
+// (c) fits the launch in roughly one wave of the 148 SMs
+static int pick_ksplit(const TcArgs& a, int tiles) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("B2P_TC_KSPLIT"); forced = e ? atoi(e) : 0; }
+  const int iters = (a.C[0] + a.C[1] + a.RC[0] + a.RC[1]) / TC_K;
+  int ks = 1;   // split-K is opt-in (B2P_TC_KSPLIT): the DSMEM reduce-scatter costs more than it saves at these sizes
+  (void)tiles;
+  if (forced > 0) { ks = 1; while (ks < forced && ks * 2 <= iters && TC_M / (ks * 2) >= a.Lrows) ks *= 2; }
+  return ks;
 }
 
 int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStream_t s) {
   TcArgs a = a_in;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("B2P_TC_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   if (a.T < 1 || a.T > 5 || a.n_out < 1 || a.n_out > 2 || a.out_ldiv < 1) return B2P_ERR_INVALID_ARG;
-  if (nsplit * (A_BYTES + a.T * B_BYTES) * 2 > TC_SMEM_STAGE_REGION) return B2P_ERR_INVALID_ARG;
   if (a.Cout % TC_N || a.C[0] % TC_K || a.C[1] % TC_K || a.RC[0] % TC_K || a.RC[1] % TC_K || a.nrows <= 0) return B2P_ERR_INVALID_ARG;
   if (a.Lrows > 32 || (a.Lrows & (a.Lrows - 1)) || TC_M % a.Lrows) return B2P_ERR_INVALID_ARG;
   if (a.gn_gamma && (TC_N % a.cg != 0)) return B2P_ERR_INVALID_ARG;
   if (a.headW && (a.Cout != TC_N || a.head_dim > 8)) return B2P_ERR_INVALID_ARG;
-  dim3 grid((a.nrows + TC_M - 1) / TC_M, a.Cout / TC_N, 1);
+  if (a.n_out == 2 && (a.RC[0] || a.RC[1])) return B2P_ERR_INVALID_ARG;
+  const int mt = (a.nrows + TC_M - 1) / TC_M, nt = a.Cout / TC_N;
+  dim3 grid(mt, nt, pick_ksplit(a, mt * nt));
   return nsplit == 2 ? launch_t<2>(maps, a, grid, s) : launch_t<1>(maps, a, grid, s);
 }
 

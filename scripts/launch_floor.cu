@@ -19,6 +19,23 @@ __global__ void k_tmem(int* p, uint32_t cols) {
   if (threadIdx.x / 32 == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
   if (p && threadIdx.x == 9999) *p = dyn[0];
 }
+__global__ void k_cluster(int* p, int nsync) {
+  for (int i = 0; i < nsync; ++i) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  if (p && threadIdx.x == 9999) *p = 1;
+}
+static void launch_cluster(int gx, int gz, int threads, int smem, int nsync, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, 1, gz); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = gz;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int* p = nullptr;
+  cudaLaunchKernelEx(&cfg, k_cluster, p, nsync);
+}
 template <typename F> float time_graph(F launch, int n, cudaStream_t s) {
   cudaGraph_t g; cudaGraphExec_t e;
   cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
@@ -39,6 +56,14 @@ int main() {
   cudaFuncSetAttribute(k_empty, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   cudaFuncSetAttribute(k_params, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   cudaFuncSetAttribute(k_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  for (int gz : {1, 2, 4, 8}) {
+    printf("cluster z=%d\n", gz);
+    printf("  16 clusters, 512thr 226KB, 0 syncs : %.2f us/launch\n", time_graph([&] { launch_cluster(16, gz, 512, 226 * 1024, 0, s); }, n, s));
+    printf("  16 clusters, 512thr 226KB, 2 syncs : %.2f us/launch\n", time_graph([&] { launch_cluster(16, gz, 512, 226 * 1024, 2, s); }, n, s));
+    printf("  16 clusters, 512thr 0KB,   2 syncs : %.2f us/launch\n", time_graph([&] { launch_cluster(16, gz, 512, 0, 2, s); }, n, s));
+    printf("  1 cluster,   512thr 226KB, 2 syncs : %.2f us/launch\n", time_graph([&] { launch_cluster(1, gz, 512, 226 * 1024, 2, s); }, n, s));
+  }
   for (int grid : {1, 32, 148}) {
     printf("grid %d\n", grid);
     printf("  empty 128thr 0smem         : %.2f us/launch\n", time_graph([&] { k_empty<<<grid, 128, 0, s>>>(nullptr); }, n, s));
