@@ -189,6 +189,11 @@ constexpr int EPI_XCHG_BYTES = TC_M * 4 * 4;
 constexpr int TC_SMEM_STAGE_REGION = 224 * 1024;   // bytes available to the TMA ring
 constexpr int TC_SMEM_TOTAL = TC_SMEM_STAGE_REGION + 1024 /*alignment slack*/ + (int)sizeof(TcBarriers);
 
+// programmatic dependent launch: block until the preceding kernel in the stream has completed and flushed its writes /
+// allow the next kernel in the stream to be scheduled (its pre-wait prologue then overlaps the rest of this kernel)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -263,35 +268,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     prefetch_tmap(&maps.a[0][0]);
     prefetch_tmap(&maps.w[0]);
     if (NSPLIT == 2) { prefetch_tmap(&maps.a[0][1]); prefetch_tmap(&maps.w[1]); }
-    for (int j = 0; j < n_local; ++j) {
+    // The weights do not depend on the previous layer: their TMA loads for the first ring pass are issued BEFORE the
+    // grid-dependency wait and overlap the tail of the preceding kernel; only the activation loads wait for it.
+    auto issue = [&](int j, bool do_w, bool do_a) {
       const int it = rank + j * KS;
       const int s = j % stages;
-      const uint32_t ph = (j / stages) & 1;
-      mbar_wait(&bars->empty[s], ph ^ 1);
       uint8_t* st = smem + s * stage_bytes;
       uint8_t* sb = st + NSPLIT * A_BYTES;
-      if (it < main_iters) {
-        mbar_expect_tx(&bars->full[s], stage_bytes);
-        const int src = it < chunks0 ? 0 : 1;
-        const int c0 = (src == 0 ? it : it - chunks0) * TC_K;
-        const int kglob = (src == 0 ? 0 : a.C[0]) + c0;
+      const bool res_phase = it >= main_iters;
+      const int ch = res_phase ? it - main_iters : it;
+      const int nch0 = res_phase ? rchunks0 : chunks0;
+      const int src = ch < nch0 ? 0 : 1;
+      const int c0 = (src == 0 ? ch : ch - nch0) * TC_K;
+      const int kglob = (src == 0 ? 0 : (res_phase ? a.RC[0] : a.C[0])) + c0;
+      if (do_w) {
+        mbar_expect_tx(&bars->full[s], res_phase ? NSPLIT * (A_BYTES + B_BYTES) : stage_bytes);
 #pragma unroll
         for (int h = 0; h < NSPLIT; ++h) {
-          tma_load_3d(st + h * A_BYTES, &maps.a[src][h], &bars->full[s], c0, 0, b0);
-          tma_load_3d(sb + h * T * B_BYTES, &maps.w[h], &bars->full[s], kglob, n0, a.tap0);
-        }
-      } else {
-        mbar_expect_tx(&bars->full[s], NSPLIT * (A_BYTES + B_BYTES));
-        const int ch = it - main_iters;
-        const int src = ch < rchunks0 ? 0 : 1;
-        const int c0 = (src == 0 ? ch : ch - rchunks0) * TC_K;
-        const int kglob = (src == 0 ? 0 : a.RC[0]) + c0;
-#pragma unroll
-        for (int h = 0; h < NSPLIT; ++h) {
-          tma_load_3d(st + h * A_BYTES, &maps.r[src][h], &bars->full[s], c0, 0, b0);
-          tma_load_2d(sb + h * T * B_BYTES, &maps.rw[h], &bars->full[s], kglob, n0);
+          if (res_phase) tma_load_2d(sb + h * T * B_BYTES, &maps.rw[h], &bars->full[s], kglob, n0);
+          else tma_load_3d(sb + h * T * B_BYTES, &maps.w[h], &bars->full[s], kglob, n0, a.tap0);
         }
       }
+      if (do_a) {
+#pragma unroll
+        for (int h = 0; h < NSPLIT; ++h)
+          tma_load_3d(st + h * A_BYTES, res_phase ? &maps.r[src][h] : &maps.a[src][h], &bars->full[s], c0, 0, b0);
+      }
+    };
+    const int npre = n_local < stages ? n_local : stages;
+    for (int j = 0; j < npre; ++j) issue(j, true, false);
+    griddep_wait();
+    for (int j = 0; j < npre; ++j) issue(j, false, true);
+    for (int j = npre; j < n_local; ++j) {
+      mbar_wait(&bars->empty[j % stages], ((j / stages) & 1) ^ 1);
+      issue(j, true, true);
     }
   } else if (threadIdx.x == 32) {
     // =============================== MMA issuer (one thread) ===============================
@@ -350,6 +360,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     umma_commit(&bars->tmem_full);
   }
   __syncwarp();
+  griddep_wait();                 // everything below may read the previous kernels' outputs (residuals)
+  griddep_launch_dependents();    // the next layer may start its prologue / weight prefetch on the idle SMs
 
   // =============================== epilogue (all 16 warps) ===============================
   {
@@ -587,10 +599,14 @@ static int launch_t(const TcMaps& maps, const TcArgs& a, dim3 grid, cudaStream_t
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = grid.z;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("B2P_TC_PDL"); pdl = e ? atoi(e) : 1; }
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
   return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<NSPLIT>, maps, a);
 }
 
