@@ -271,6 +271,16 @@ class TemporalMapUnet(nn.Module):
             self._packed[idx] = key
         return h
 
+    def set_precision(self, precision: str) -> "TemporalMapUnet":
+        """'fp32' (CUDA-core FFMA, exact fp32), 'bf16x3' (tcgen05, bf16 hi/lo split, fp32-class parity) or 'bf16' (tcgen05 single pass)."""
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {list(_lib.PRECISIONS)}")
+        self.precision = precision
+        lib = _lib.load()
+        for h in self._handles.values():
+            _lib.check(lib.b2p_set_precision(h, _lib.PRECISIONS[precision]), h, "b2p_set_precision")
+        return self
+
     def __del__(self):
         try:
             lib = _lib.load()
