@@ -56,5 +56,5 @@ def test_two_rank_sharded_plan_equals_unsharded():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert err <= 1e-4     # no cross-sample operation anywhere (CPU BLAS blocking varies with batch; the CUDA path is bitwise, see GPU tests)
+    assert err <= 1e-3     # metres on x,y (x23.315); no cross-sample operation anywhere (CPU BLAS blocking varies with batch; the CUDA path is bitwise, see GPU tests)
     assert tmax == 2.0     # max over ranks
