@@ -564,6 +564,7 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
       }
       const int lstride = 1;
       t.Lrows = Lrows; t.log2L = ilog2(Lrows); t.samples_per_tile = 128 / Lrows; t.nrows = rows * Lrows;
+      t.tile_n = tc_pick_tile_n(t.nrows, op.Cout, op.headW != NPOS);
       const int ins[2] = {op.in0, op.in1};
       const int cs[2] = {op.C0, op.C1};
       for (int sidx = 0; sidx < 2; ++sidx) {
@@ -572,8 +573,8 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
         if (nsplit == 2 && (rc = tc_make_act_map(&m.a[sidx][1], lo_ptr(ins[sidx]), rows, op.Lin, cs[sidx], op.Lin, lstride, t.samples_per_tile))) return h->fail(rc, "tensor map (A lo)");
       }
       const __nv_bfloat16* P16 = reinterpret_cast<const __nv_bfloat16*>(h->d_pack16);
-      if ((rc = tc_make_weight_map(&m.w[0], P16 + op.tcW_hi, op.taps, op.Cout, op.C0 + op.C1, t.T))) return h->fail(rc, "tensor map (W)");
-      if (nsplit == 2 && (rc = tc_make_weight_map(&m.w[1], P16 + op.tcW_lo, op.taps, op.Cout, op.C0 + op.C1, t.T))) return h->fail(rc, "tensor map (W lo)");
+      if ((rc = tc_make_weight_map(&m.w[0], P16 + op.tcW_hi, op.taps, op.Cout, op.C0 + op.C1, t.T, t.tile_n))) return h->fail(rc, "tensor map (W)");
+      if (nsplit == 2 && (rc = tc_make_weight_map(&m.w[1], P16 + op.tcW_lo, op.taps, op.Cout, op.C0 + op.C1, t.T, t.tile_n))) return h->fail(rc, "tensor map (W lo)");
       if (op.resW != NPOS) {
         if (op.tcRW_hi != NPOS) {
           t.RC[0] = op.RC0; t.RC[1] = op.RC1; t.resB = P + op.resB;
@@ -584,8 +585,8 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
             if ((rc = tc_make_act_map(&m.r[sidx][0], hi_ptr(rins[sidx]), rows, op.Lout, rcs[sidx], op.Lout, 1, t.samples_per_tile))) return h->fail(rc, "tensor map (R)");
             if (nsplit == 2 && (rc = tc_make_act_map(&m.r[sidx][1], lo_ptr(rins[sidx]), rows, op.Lout, rcs[sidx], op.Lout, 1, t.samples_per_tile))) return h->fail(rc, "tensor map (R lo)");
           }
-          if ((rc = tc_make_weight_map(&m.rw[0], P16 + op.tcRW_hi, 1, op.Cout, op.RC0 + op.RC1, 0))) return h->fail(rc, "tensor map (RW)");
-          if (nsplit == 2 && (rc = tc_make_weight_map(&m.rw[1], P16 + op.tcRW_lo, 1, op.Cout, op.RC0 + op.RC1, 0))) return h->fail(rc, "tensor map (RW lo)");
+          if ((rc = tc_make_weight_map(&m.rw[0], P16 + op.tcRW_hi, 1, op.Cout, op.RC0 + op.RC1, 0, t.tile_n))) return h->fail(rc, "tensor map (RW)");
+          if (nsplit == 2 && (rc = tc_make_weight_map(&m.rw[1], P16 + op.tcRW_lo, 1, op.Cout, op.RC0 + op.RC1, 0, t.tile_n))) return h->fail(rc, "tensor map (RW lo)");
         } else if (proj_done) {
           t.res_f32 = h->d_res0;
         } else {
