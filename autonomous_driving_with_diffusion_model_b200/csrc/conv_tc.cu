@@ -174,10 +174,16 @@ struct __align__(16) TcShared {
 //                          cx[2][4][128] (GroupNorm partials written by PEER CTAs, so it may never alias live stages) at 208 KB
 //   ring start, reused after the main loop:  xchg[2][128][4] (partials between the column slices of this CTA), head[128][4][8]
 //   [224 KB, ...)          TcShared (barriers, TMEM base, epilogue vectors)
-constexpr int TC_SMEM_STAGE_REGION = 224 * 1024;
-constexpr int TC_RING_BYTES_NARROW = 208 * 1024;
+//   TN == 16 uses a 106 KB ring (+ cx) so that TWO CTAs fit on an SM: a 128-CTA layer then leaves room for the next layer's
+//   CTAs to become resident early (programmatic dependent launch) instead of waiting for SMs to drain.
+template <int TN> struct SmemPlan {
+  static constexpr int ring = TN == 64 ? 224 * 1024 : (TN == 32 ? 208 * 1024 : 106 * 1024);
+  static constexpr int cx_off = ring;                                      // cluster exchange buffer (TN < 64), 4 KB
+  static constexpr int shared_off = TN == 64 ? ring : ring + 4 * 1024;     // TcShared
+  static constexpr int total = shared_off + 1024 /*alignment slack*/ + (int)sizeof(TcShared);
+  static constexpr int min_ctas = TN == 16 ? 2 : 1;
+};
 constexpr int EPI_XCHG_BYTES = 2 * TC_M * 4 * 4;
-constexpr int TC_SMEM_TOTAL = TC_SMEM_STAGE_REGION + 1024 /*alignment slack*/ + (int)sizeof(TcShared);
 struct EpiScratch {
   float (*xchg)[TC_M][4];   // [pass][row][slice]
   float (*cx)[4][TC_M];     // [pass][source CTA][row]
@@ -254,16 +260,16 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
 }
 
 template <int NSPLIT, int TN>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs a) {
   constexpr int EC = TN / 4;                        // columns per epilogue thread
   constexpr int BT_BYTES = TN * TC_K * 2;           // one tap's weight tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_SMEM_STAGE_REGION);
+  TcShared* sh = reinterpret_cast<TcShared*>(smem + SmemPlan<TN>::shared_off);
 
   const int T = a.T;
   const int stage_bytes = NSPLIT * (A_BYTES + T * BT_BYTES);   // [A hi | A lo | W hi (T taps) | W lo (T taps)]
-  int stages = (TN == 64 ? TC_SMEM_STAGE_REGION : TC_RING_BYTES_NARROW) / stage_bytes;
+  int stages = SmemPlan<TN>::ring / stage_bytes;
   if (stages > 8) stages = 8;
   const int need_cols = (T + 1) * TN;
   const uint32_t tmem_cols = need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u)));
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int b = (int)(grow >> a.log2L), l = (int)(grow & (L - 1));
     EpiScratch es;
     es.xchg = reinterpret_cast<float (*)[TC_M][4]>(smem);
-    es.cx = reinterpret_cast<float (*)[4][TC_M]>(smem + TC_RING_BYTES_NARROW);
+    es.cx = reinterpret_cast<float (*)[4][TC_M]>(smem + SmemPlan<TN>::cx_off);
     float (*headp)[4][8] = reinterpret_cast<float (*)[4][8]>(smem + EPI_XCHG_BYTES);
     const int gcol = n0 + col0;
     const int n_out = (a.dbg & 2) ? 0 : a.n_out;
@@ -589,7 +595,7 @@ int tc_make_weight_map(CUtensorMap* m, const void* base, int taps, int Cout, int
 
 template <int NSPLIT, int TN>
 static int launch_t(const TcMaps& maps, const TcArgs& a, dim3 grid, cudaStream_t s) {
-  constexpr int smem = TC_SMEM_TOTAL;
+  constexpr int smem = SmemPlan<TN>::total;
   B2P_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<NSPLIT, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -624,7 +630,7 @@ int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStrea
   const int TN = a.tile_n;
   if (TN != 64 && TN != 32 && TN != 16) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.T < 1 || a.T > 5 || a.n_out < 1 || a.n_out > 2 || a.out_ldiv < 1) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  if (nsplit * (A_BYTES + a.T * TN * TC_K * 2) * 2 > (TN == 64 ? TC_SMEM_STAGE_REGION : TC_RING_BYTES_NARROW)) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
+  if (nsplit * (A_BYTES + a.T * TN * TC_K * 2) * 2 > (TN == 64 ? SmemPlan<64>::ring : (TN == 32 ? SmemPlan<32>::ring : SmemPlan<16>::ring))) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.Cout % TN || a.C[0] % TC_K || a.C[1] % TC_K || a.RC[0] % TC_K || a.RC[1] % TC_K || a.nrows <= 0) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.Lrows > 32 || (a.Lrows & (a.Lrows - 1)) || TC_M % a.Lrows) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.headW && (a.Cout != 64 || TN != 64 || a.head_dim > 8)) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
