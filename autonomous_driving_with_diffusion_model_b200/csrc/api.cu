@@ -564,13 +564,17 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
       }
       const int lstride = 1;
       t.Lrows = Lrows; t.log2L = ilog2(Lrows); t.samples_per_tile = 128 / Lrows; t.nrows = rows * Lrows;
-      t.tile_n = tc_pick_tile_n(t.nrows, op.Cout, op.headW != NPOS);
+      if (op.gamma != NPOS) { t.gn_gamma = P + op.gamma; t.gn_beta = P + op.beta; t.cg = op.Cout / 8; }
+      if (op.headW != NPOS) { t.headW = P + op.headW; t.headB = P + op.headB; t.head_dim = op.head_dim; t.head_out = head_out; }
+      if ((rc = tc_configure(t))) return h->fail(rc, "unsupported layer tiling");
+      // with activation multicast (cluster_l > cluster_n) each CTA of the cluster loads 1/cluster_l of the row tile's samples
+      const int box_b = t.cluster_l > t.cluster_n ? t.samples_per_tile / t.cluster_l : t.samples_per_tile;
       const int ins[2] = {op.in0, op.in1};
       const int cs[2] = {op.C0, op.C1};
       for (int sidx = 0; sidx < 2; ++sidx) {
         if (cs[sidx] == 0) continue;
-        if ((rc = tc_make_act_map(&m.a[sidx][0], hi_ptr(ins[sidx]), rows, op.Lin, cs[sidx], op.Lin, lstride, t.samples_per_tile))) return h->fail(rc, "tensor map (A)");
-        if (nsplit == 2 && (rc = tc_make_act_map(&m.a[sidx][1], lo_ptr(ins[sidx]), rows, op.Lin, cs[sidx], op.Lin, lstride, t.samples_per_tile))) return h->fail(rc, "tensor map (A lo)");
+        if ((rc = tc_make_act_map(&m.a[sidx][0], hi_ptr(ins[sidx]), rows, op.Lin, cs[sidx], op.Lin, lstride, box_b))) return h->fail(rc, "tensor map (A)");
+        if (nsplit == 2 && (rc = tc_make_act_map(&m.a[sidx][1], lo_ptr(ins[sidx]), rows, op.Lin, cs[sidx], op.Lin, lstride, box_b))) return h->fail(rc, "tensor map (A lo)");
       }
       const __nv_bfloat16* P16 = reinterpret_cast<const __nv_bfloat16*>(h->d_pack16);
       if ((rc = tc_make_weight_map(&m.w[0], P16 + op.tcW_hi, op.taps, op.Cout, op.C0 + op.C1, t.T, t.tile_n))) return h->fail(rc, "tensor map (W)");
@@ -582,8 +586,8 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
           const int rcs[2] = {op.RC0, op.RC1};
           for (int sidx = 0; sidx < 2; ++sidx) {
             if (rcs[sidx] == 0) continue;
-            if ((rc = tc_make_act_map(&m.r[sidx][0], hi_ptr(rins[sidx]), rows, op.Lout, rcs[sidx], op.Lout, 1, t.samples_per_tile))) return h->fail(rc, "tensor map (R)");
-            if (nsplit == 2 && (rc = tc_make_act_map(&m.r[sidx][1], lo_ptr(rins[sidx]), rows, op.Lout, rcs[sidx], op.Lout, 1, t.samples_per_tile))) return h->fail(rc, "tensor map (R lo)");
+            if ((rc = tc_make_act_map(&m.r[sidx][0], hi_ptr(rins[sidx]), rows, op.Lout, rcs[sidx], op.Lout, 1, box_b))) return h->fail(rc, "tensor map (R)");
+            if (nsplit == 2 && (rc = tc_make_act_map(&m.r[sidx][1], lo_ptr(rins[sidx]), rows, op.Lout, rcs[sidx], op.Lout, 1, box_b))) return h->fail(rc, "tensor map (R lo)");
           }
           if ((rc = tc_make_weight_map(&m.rw[0], P16 + op.tcRW_hi, 1, op.Cout, op.RC0 + op.RC1, 0, t.tile_n))) return h->fail(rc, "tensor map (RW)");
           if (nsplit == 2 && (rc = tc_make_weight_map(&m.rw[1], P16 + op.tcRW_lo, 1, op.Cout, op.RC0 + op.RC1, 0, t.tile_n))) return h->fail(rc, "tensor map (RW lo)");

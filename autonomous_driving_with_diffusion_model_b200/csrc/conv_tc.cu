@@ -78,6 +78,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset in every CTA of `mask`, and each of their mbarriers
+// (same offset) receives the complete_tx for the bytes written into that CTA
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -104,6 +110,10 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -192,7 +202,7 @@ struct EpiScratch {
 // Sum `x` (already reduced over the L lanes of the sample) over the column slices / cluster CTAs that share the group.
 //   SL  = slices of this CTA inside one group (1, 2 or 4), CN = CTAs of the cluster sharing the group (1, 2 or 4)
 template <int SL, int CN>
-__device__ __forceinline__ float group_allreduce(float x, int pass, int row, int slice, int crank, const EpiScratch& sh) {
+__device__ __forceinline__ float group_allreduce(float x, int pass, int row, int slice, int crank, int cbase, const EpiScratch& sh) {
   if (SL > 1) {
     sh.xchg[pass][row][slice] = x;
     __syncthreads();
@@ -206,7 +216,7 @@ __device__ __forceinline__ float group_allreduce(float x, int pass, int row, int
     if ((slice & (SL - 1)) == 0) {                 // one thread per (row, group part) publishes to every CTA of the cluster
       const uint32_t la = smem_u32(&sh.cx[pass][crank][row]);
 #pragma unroll
-      for (int c = 0; c < CN; ++c) st_cluster_f32(la, (uint32_t)c, x);
+      for (int c = 0; c < CN; ++c) st_cluster_f32(la, (uint32_t)(cbase + c), x);
     }
     cluster_sync_all();
     float s = 0.f;
@@ -221,7 +231,7 @@ __device__ __forceinline__ float group_allreduce(float x, int pass, int row, int
 // lanes) of a sample; TN is the CTA's column-tile width.  Two passes (mean, then centred variance) like the reference.
 // Called by ALL threads of the CTA (contains __syncthreads / cluster barriers).
 template <int CG, int TN>
-__device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int row, int slice, int crank, const EpiScratch& es,
+__device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int row, int slice, int crank, int cbase, const EpiScratch& es,
                                                 const float* gamma, const float* beta) {
   constexpr int EC = TN / 4;
   constexpr int W = CG < EC ? CG : EC;              // channels of one group inside this thread
@@ -239,7 +249,7 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
     for (int o = 1; o < L; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     mean[g] = s;
   }
-  if (SL > 1 || CN > 1) mean[0] = group_allreduce<SL, CN>(mean[0], 0, row, slice, crank, es);
+  if (SL > 1 || CN > 1) mean[0] = group_allreduce<SL, CN>(mean[0], 0, row, slice, crank, cbase, es);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     mean[g] *= inv_n;
@@ -249,7 +259,7 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
     for (int o = 1; o < L; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     rstd[g] = q;
   }
-  if (SL > 1 || CN > 1) rstd[0] = group_allreduce<SL, CN>(rstd[0], 1, row, slice, crank, es);
+  if (SL > 1 || CN > 1) rstd[0] = group_allreduce<SL, CN>(rstd[0], 1, row, slice, crank, cbase, es);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     const float r = rsqrtf(rstd[g] * inv_n + 1e-5f);
@@ -276,7 +286,13 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x, n0 = blockIdx.y * TN;
-  const int crank = blockIdx.y % a.cluster_n;      // rank inside the (1, cluster_n, 1) cluster
+  // cluster = (1, CL, 1) consecutive column tiles of the same row tile: they share the activation tile (TMA multicast: every
+  // CTA loads 1/CL of it and broadcasts) and, in sub-groups of cluster_n, a GroupNorm group (statistics exchange)
+  const int CL = a.cluster_l;
+  const int lrank = blockIdx.y % CL;               // rank inside the cluster (== %cluster_ctarank)
+  const int crank = lrank % a.cluster_n;           // rank inside the GroupNorm sub-group
+  const int cbase = lrank - crank;                 // first cluster rank of the sub-group
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   const int b0 = tile_m * a.samples_per_tile;
 
   const int chunks0 = a.C[0] / TC_K, chunks1 = a.C[1] / TC_K;
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   const int n_local = (a.dbg & 1) ? 0 : main_iters + res_iters;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], (CL > a.cluster_n) ? CL : 1); }
     mbar_init(&sh->tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -305,6 +321,8 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const bool mcast = CL > a.cluster_n;             // activation multicast active (off by default: measured slower)
+  if (mcast) cluster_sync_all();                   // peers' barriers are initialised before anyone multicasts / commits into them
   const uint32_t tmem_base = sh->tmem_base;
 
   if (threadIdx.x == 0) {
@@ -333,9 +351,14 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
         }
       }
       if (do_a) {
+        // this CTA fetches samples [lrank*spt/CL, (lrank+1)*spt/CL) of the tile and broadcasts them to the whole cluster
+        const int sub = a.samples_per_tile / CL;
 #pragma unroll
-        for (int h = 0; h < NSPLIT; ++h)
-          tma_load_3d(st + h * A_BYTES, res_phase ? &maps.r[src][h] : &maps.a[src][h], &sh->full[s], c0, 0, b0);
+        for (int h = 0; h < NSPLIT; ++h) {
+          const CUtensorMap* mp = res_phase ? &maps.r[src][h] : &maps.a[src][h];
+          if (mcast) tma_load_3d_mc(st + h * A_BYTES + lrank * (A_BYTES / CL), mp, &sh->full[s], c0, 0, b0 + lrank * sub, cmask);
+          else tma_load_3d(st + h * A_BYTES, mp, &sh->full[s], c0, 0, b0);
+        }
       }
     };
     const int npre = n_local < stages ? n_local : stages;
@@ -394,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
           }
         }
       }
-      umma_commit(&sh->empty[s]);
+      if (CL > a.cluster_n) umma_commit_mc(&sh->empty[s], cmask); else umma_commit(&sh->empty[s]);   // the stage is free in a CTA once ALL cluster consumers released it
     }
     umma_commit(&sh->tmem_full);
   }
@@ -484,10 +507,10 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       }
       if (a.gn_gamma) {
         switch (a.cg) {
-          case 8: group_norm_mish<8, TN>(v, L, r, slice, crank, es, sh->gamma + col0, sh->beta + col0); break;
-          case 16: group_norm_mish<16, TN>(v, L, r, slice, crank, es, sh->gamma + col0, sh->beta + col0); break;
-          case 32: group_norm_mish<32, TN>(v, L, r, slice, crank, es, sh->gamma + col0, sh->beta + col0); break;
-          default: group_norm_mish<64, TN>(v, L, r, slice, crank, es, sh->gamma + col0, sh->beta + col0); break;
+          case 8: group_norm_mish<8, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0); break;
+          case 16: group_norm_mish<16, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0); break;
+          case 32: group_norm_mish<32, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0); break;
+          default: group_norm_mish<64, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0); break;
         }
       }
       const bool ok = row_ok && (a.out_ldiv == 1 || (l % a.out_ldiv) == 0);
@@ -536,6 +559,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     }
     tc_fence_before();
   }
+  if (mcast) cluster_sync_all();                   // no CTA may exit while peers can still signal its barriers / write its smem
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -602,7 +626,7 @@ static int launch_t(const TcMaps& maps, const TcArgs& a, dim3 grid, cudaStream_t
   cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = a.cluster_n; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = a.cluster_l; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   static int pdl = -1;
@@ -624,6 +648,29 @@ int tc_pick_tile_n(int nrows, int Cout, bool has_head) {
   return tn;
 }
 
+// Decide the tiling of one layer launch: column-tile width, GroupNorm sub-group size and multicast cluster size.
+// Must be called after the layer fields (nrows, Cout, gn_gamma/cg, headW, samples_per_tile) are set and BEFORE the
+// activation tensor maps are encoded (their box covers samples_per_tile / cluster_l samples).
+int tc_configure(TcArgs& a) {
+  a.tile_n = tc_pick_tile_n(a.nrows, a.Cout, a.headW != nullptr);
+  const int TN = a.tile_n;
+  if (a.Cout % TN) return B2P_ERR_INVALID_ARG;
+  a.cluster_n = 1;
+  if (a.gn_gamma) {
+    if (a.cg != 8 && a.cg != 16 && a.cg != 32 && a.cg != 64) return B2P_ERR_INVALID_ARG;
+    if (a.cg > TN) a.cluster_n = a.cg / TN;          // CTAs sharing a GroupNorm group exchange statistics over DSMEM
+  }
+  // multicast cluster: as many column tiles as share the row tile, <= 8, a multiple of the GroupNorm sub-group, and no
+  // more than the samples of a row tile (every CTA loads whole samples)
+  static int mc = -1;
+  if (mc < 0) { const char* e = getenv("B2P_TC_MCAST"); mc = e ? atoi(e) : 1; }   // opt-in: the lock-step it imposes costs more than the L2 reads it saves
+  int cl = a.cluster_n;
+  const int ntiles = a.Cout / TN;
+  while (cl * 2 <= mc && cl * 2 <= 8 && ntiles % (cl * 2) == 0 && a.samples_per_tile % (cl * 2) == 0) cl *= 2;
+  a.cluster_l = cl;
+  return (ntiles % a.cluster_l) ? B2P_ERR_INVALID_ARG : B2P_OK;
+}
+
 int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStream_t s) {
   TcArgs a = a_in;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("B2P_TC_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
@@ -635,12 +682,8 @@ int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStrea
   if (a.Lrows > 32 || (a.Lrows & (a.Lrows - 1)) || TC_M % a.Lrows) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.headW && (a.Cout != 64 || TN != 64 || a.head_dim > 8)) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.n_out == 2 && (a.RC[0] || a.RC[1])) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  a.cluster_n = 1;
-  if (a.gn_gamma) {
-    if (a.cg != 8 && a.cg != 16 && a.cg != 32 && a.cg != 64) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-    if (a.cg > TN) a.cluster_n = a.cg / TN;          // CTAs sharing a GroupNorm group exchange statistics over DSMEM
-  }
-  if ((a.Cout / TN) % a.cluster_n) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
+  if (a.cluster_n < 1 || a.cluster_l < a.cluster_n || a.cluster_l % a.cluster_n) { fprintf(stderr, "launch_conv_tc: tc_configure() was not applied\n"); return B2P_ERR_INVALID_ARG; }
+  if ((a.Cout / TN) % a.cluster_l) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   dim3 grid((a.nrows + TC_M - 1) / TC_M, a.Cout / TN, 1);
   if (nsplit == 2) {
     if (TN == 64) return launch_t<2, 64>(maps, a, grid, s);

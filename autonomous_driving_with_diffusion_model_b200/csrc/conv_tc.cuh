@@ -40,12 +40,14 @@ struct TcArgs {
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   int tile_n;             // column-tile width: 64, 32 or 16 (tc_pick_tile_n)
   int cluster_n;          // set by launch_conv_tc: CTAs along N sharing one GroupNorm group
+  int cluster_l;          // set by launch_conv_tc: cluster size along N (activation-tile multicast), multiple of cluster_n
   int dbg;                // developer bisect switch (B2P_TC_DBG): 1 = skip the TMA/MMA main loop, 2 = skip the epilogue math
 };
 
 int tc_make_act_map(CUtensorMap* m, const void* base, int B, int L, int C, int box_l, int lstride, int box_b);
 int tc_make_weight_map(CUtensorMap* m, const void* base, int taps, int Cout, int K, int box_taps, int box_n);
 int tc_pick_tile_n(int nrows, int Cout, bool has_head);
+int tc_configure(TcArgs& a);
 int launch_conv_tc(const TcMaps& maps, const TcArgs& a, int nsplit, cudaStream_t s);
 
 }  // namespace b2p
