@@ -51,6 +51,19 @@ struct ConvArgs {
 
 int launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
 
+// launch `kernel` with the programmatic-stream-serialization attribute (the kernel must call pdl_wait() before it reads
+// anything produced by the preceding kernel)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // time / condition embedding (modeling/temporal.py:205-213 + the Mish in front of every block's time_mlp)
 struct EmbedArgs {
   const int64_t* t; int t_count;      // timesteps, repeated to B
@@ -104,6 +117,10 @@ int launch_state_pred_vjp(const TrajPredWeights& w, const float* action, const f
                           float* grad_action, int B, int H, int D, cudaStream_t s);
 int launch_classifier_guidance(const TrajPredWeights& w, float* model_output, const float* time_embed, int te_stride, const float* target,
                                float grad_scale, float scale, int B, int H, int D, cudaStream_t s);
+
+// programmatic dependent launch (PDL): wait for the preceding kernel's results / let the following kernel start its prologue
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float mish_f(float x) {
   // x * tanh(softplus(x)), softplus threshold 20 (nn.Mish); tanh(log1p(e^x)) == n/(n+2), n = e^x (e^x + 2)

@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(NT) conv_ffma_kernel(ConvArgs a) {
   __shared__ __align__(16) Smem<TM> sm;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int row0 = blockIdx.x * TM, col0 = blockIdx.y * TN;
+  pdl_wait();                 // inputs come from the preceding kernel
+  pdl_launch_dependents();
 
   float acc[RM][4];
 #pragma unroll
@@ -268,6 +270,7 @@ __global__ void __launch_bounds__(NT) conv_ffma_kernel(ConvArgs a) {
 template <int TM>
 static int launch_tm(const ConvArgs& a, bool vec, cudaStream_t s) {
   dim3 grid((a.nrows + TM - 1) / TM, a.Cout / TN);
+  // plain (fully serialised) launches: these grids fill the machine, so early-resident dependents only take SM slots away
   if (vec) conv_ffma_kernel<TM, true><<<grid, NT, 0, s>>>(a);
   else conv_ffma_kernel<TM, false><<<grid, NT, 0, s>>>(a);
   return (int)cudaGetLastError();

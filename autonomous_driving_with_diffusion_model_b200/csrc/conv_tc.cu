@@ -118,8 +118,9 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-template <int EC> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
-template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
+template <int EC, bool WAIT = true> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <bool WAIT> __device__ __forceinline__ void tmem_ld16_impl(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -127,26 +128,33 @@ template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float* v) {
+template <bool WAIT> __device__ __forceinline__ void tmem_ld8_impl(uint32_t taddr, float* v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-template <> __device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float* v) {
+template <bool WAIT> __device__ __forceinline__ void tmem_ld4_impl(uint32_t taddr, float* v) {
   uint32_t r[4];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+template <> __device__ __forceinline__ void tmem_ld<16, true>(uint32_t t, float* v) { tmem_ld16_impl<true>(t, v); }
+template <> __device__ __forceinline__ void tmem_ld<16, false>(uint32_t t, float* v) { tmem_ld16_impl<false>(t, v); }
+template <> __device__ __forceinline__ void tmem_ld<8, true>(uint32_t t, float* v) { tmem_ld8_impl<true>(t, v); }
+template <> __device__ __forceinline__ void tmem_ld<8, false>(uint32_t t, float* v) { tmem_ld8_impl<false>(t, v); }
+template <> __device__ __forceinline__ void tmem_ld<4, true>(uint32_t t, float* v) { tmem_ld4_impl<true>(t, v); }
+template <> __device__ __forceinline__ void tmem_ld<4, false>(uint32_t t, float* v) { tmem_ld4_impl<false>(t, v); }
 
 // Mish with the SFU approximations (ex2.approx / rcp.approx): relative error ~1e-6, far below the bf16-split noise.
 __device__ __forceinline__ float mish_fast(float x) {
@@ -490,18 +498,37 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       for (int c = 0; c < EC; ++c) v[c] = sh->bias[col0 + c];
       // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the sample) ----
       if (n_local > 0) {
-        for (int i = 0; i < a.nt[o]; ++i) {
-          const int t = a.tap_blk[o][i], d = a.tap_shift[o][i];
-          const bool valid = (l + d >= 0) && (l + d < L);
-          const int src = (lane + d) & 31;
-          float y[EC];
-          tmem_ld<EC>(taddr + t * TN, y);
-          if (d == 0) {
+        if (EC <= 8) {
+          // narrow tiles: issue the TMEM loads of all taps back to back and wait once
+          float y[5][EC];
 #pragma unroll
-            for (int c = 0; c < EC; ++c) v[c] += y[c];
-          } else {
+          for (int i = 0; i < 5; ++i)
+            if (i < a.nt[o]) tmem_ld<EC, false>(taddr + a.tap_blk[o][i] * TN, y[i]);
+          tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < EC; ++c) { float g = __shfl_sync(0xffffffffu, y[c], src); v[c] += valid ? g : 0.f; }
+          for (int i = 0; i < 5; ++i) {
+            if (i < a.nt[o]) {
+              const int d = a.tap_shift[o][i];
+              const bool valid = (l + d >= 0) && (l + d < L);
+              const int src = (lane + d) & 31;
+#pragma unroll
+              for (int c = 0; c < EC; ++c) { float g = __shfl_sync(0xffffffffu, y[i][c], src); v[c] += valid ? g : 0.f; }
+            }
+          }
+        } else {
+          for (int i = 0; i < a.nt[o]; ++i) {
+            const int t = a.tap_blk[o][i], d = a.tap_shift[o][i];
+            const bool valid = (l + d >= 0) && (l + d < L);
+            const int src = (lane + d) & 31;
+            float y[EC];
+            tmem_ld<EC>(taddr + t * TN, y);
+            if (d == 0) {
+#pragma unroll
+              for (int c = 0; c < EC; ++c) v[c] += y[c];
+            } else {
+#pragma unroll
+              for (int c = 0; c < EC; ++c) { float g = __shfl_sync(0xffffffffu, y[c], src); v[c] += valid ? g : 0.f; }
+            }
           }
         }
       }

@@ -29,6 +29,8 @@ __global__ void embed_kernel(EmbedArgs a) {
   float* part2 = part + dim4;  // [4][dim]
   const int b = blockIdx.x, tid = threadIdx.x;
   const bool do_te = b < a.te_rows;
+  pdl_wait();
+  pdl_launch_dependents();
   if (do_te) {
     const float t = (float)a.t[b % a.t_count];
     if (tid < dim) {

@@ -78,6 +78,8 @@ __device__ __forceinline__ float step_one(const SchedK& a, int idx, float m, flo
 }
 
 __global__ void __launch_bounds__(256) sched_step_kernel(SchedK a) {
+  pdl_wait();                 // model_output comes from the preceding kernel
+  pdl_launch_dependents();
   int i4 = blockIdx.x * blockDim.x + threadIdx.x;
   int base = i4 * 4;
   if (base >= a.n) return;
@@ -157,7 +159,8 @@ int launch_sched_step(const SchedLaunch& L, cudaStream_t s) {
     a.thr_s = thr;
   }
   int n4 = n / 4;
-  sched_step_kernel<<<(n4 + 255) / 256, 256, 0, s>>>(a);
+  cudaError_t le = launch_pdl(sched_step_kernel, dim3((n4 + 255) / 256), dim3(256), 0, s, a);
+  if (le != cudaSuccess) return (int)le;
   if (thr) B2P_CUDA_TRY(cudaFreeAsync(thr, s));
   return (int)cudaGetLastError();
 }
