@@ -207,37 +207,14 @@ struct EpiScratch {
   float (*cx)[4][TC_M];     // [pass][source CTA][row]
 };
 
-// Sum `x` (already reduced over the L lanes of the sample) over the column slices / cluster CTAs that share the group.
-//   SL  = slices of this CTA inside one group (1, 2 or 4), CN = CTAs of the cluster sharing the group (1, 2 or 4)
-template <int SL, int CN>
-__device__ __forceinline__ float group_allreduce(float x, int pass, int row, int slice, int crank, int cbase, const EpiScratch& sh) {
-  if (SL > 1) {
-    sh.xchg[pass][row][slice] = x;
-    __syncthreads();
-    const int base = slice & ~(SL - 1);
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < SL; ++j) s += sh.xchg[pass][row][base + j];
-    x = s;
-  }
-  if (CN > 1) {
-    if ((slice & (SL - 1)) == 0) {                 // one thread per (row, group part) publishes to every CTA of the cluster
-      const uint32_t la = smem_u32(&sh.cx[pass][crank][row]);
-#pragma unroll
-      for (int c = 0; c < CN; ++c) st_cluster_f32(la, (uint32_t)(cbase + c), x);
-    }
-    cluster_sync_all();
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < CN; ++c) s += sh.cx[pass][c][row];   // fixed order: every CTA gets bit-identical statistics
-    x = s;
-  }
-  return x;
-}
-
 // GroupNorm(8) + Mish for the EC channels a thread holds.  A group is CG consecutive channels x the L rows (adjacent
-// lanes) of a sample; TN is the CTA's column-tile width.  Two passes (mean, then centred variance) like the reference.
-// Called by ALL threads of the CTA (contains __syncthreads / cluster barriers).
+// lanes) of a sample; TN is the CTA's column-tile width.  Every thread first computes the mean and the centred sum of
+// squares (M2) of ITS part of the group (W channels x L rows, two passes over registers + xor shuffles).  When the group
+// spans several column slices of the CTA (SL) and/or several CTAs of the cluster (CN), the (mean, M2) pairs of the equally
+// sized parts are exchanged ONCE — through shared memory between slices, through distributed shared memory between
+// CTAs — and merged with the parallel-variance formula  M2 = sum M2_p + n_p * sum (mean_p - mean)^2, which is as accurate
+// as the reference's two-pass GroupNorm.  Parts are summed in a fixed order so all CTAs get bit-identical statistics.
+// Called by ALL threads of the CTA (contains __syncthreads / a cluster barrier).
 template <int CG, int TN>
 __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int row, int slice, int crank, int cbase, const EpiScratch& es,
                                                 const float* gamma, const float* beta) {
@@ -247,33 +224,55 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
   constexpr int WC = CG < TN ? CG : TN;             // channels of one group inside this CTA
   constexpr int SL = WC / W;                        // slices of this CTA sharing a group
   constexpr int CN = CG / WC;                       // CTAs sharing a group
-  const float inv_n = 1.0f / (float)(CG * L);
-  float mean[NG], rstd[NG];
+  const float inv_np = 1.0f / (float)(W * L);       // elements of one part
+  float mean[NG], m2[NG];
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < W; ++c) s += v[g * W + c];
     for (int o = 1; o < L; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    mean[g] = s;
-  }
-  if (SL > 1 || CN > 1) mean[0] = group_allreduce<SL, CN>(mean[0], 0, row, slice, crank, cbase, es);
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    mean[g] *= inv_n;
+    mean[g] = s * inv_np;
     float q = 0.f;
 #pragma unroll
     for (int c = 0; c < W; ++c) { float d = v[g * W + c] - mean[g]; q = fmaf(d, d, q); }
     for (int o = 1; o < L; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    rstd[g] = q;
+    m2[g] = q;
   }
-  if (SL > 1 || CN > 1) rstd[0] = group_allreduce<SL, CN>(rstd[0], 1, row, slice, crank, cbase, es);
+  if (SL > 1) {                                      // merge the slices of this CTA (NG == 1 here)
+    es.xchg[0][row][slice] = mean[0];
+    es.xchg[1][row][slice] = m2[0];
+    __syncthreads();
+    const int base = slice & ~(SL - 1);
+    float ms = 0.f, qs = 0.f;
+#pragma unroll
+    for (int j = 0; j < SL; ++j) ms += es.xchg[0][row][base + j];
+    const float mu = ms * (1.0f / SL);
+#pragma unroll
+    for (int j = 0; j < SL; ++j) { float d = es.xchg[0][row][base + j] - mu; qs += es.xchg[1][row][base + j] + (float)(W * L) * d * d; }
+    mean[0] = mu; m2[0] = qs;
+  }
+  if (CN > 1) {                                      // merge the CTAs of the cluster sub-group
+    if ((slice & (SL - 1)) == 0) {
+      const uint32_t la0 = smem_u32(&es.cx[0][crank][row]), la1 = smem_u32(&es.cx[1][crank][row]);
+#pragma unroll
+      for (int c = 0; c < CN; ++c) { st_cluster_f32(la0, (uint32_t)(cbase + c), mean[0]); st_cluster_f32(la1, (uint32_t)(cbase + c), m2[0]); }
+    }
+    cluster_sync_all();
+    float ms = 0.f, qs = 0.f;
+#pragma unroll
+    for (int c = 0; c < CN; ++c) ms += es.cx[0][c][row];
+    const float mu = ms * (1.0f / CN);
+#pragma unroll
+    for (int c = 0; c < CN; ++c) { float d = es.cx[0][c][row] - mu; qs += es.cx[1][c][row] + (float)(WC * L) * d * d; }
+    mean[0] = mu; m2[0] = qs;
+  }
+  const float inv_n = 1.0f / (float)(CG * L);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    const float r = rsqrtf(rstd[g] * inv_n + 1e-5f);
+    const float r = rsqrtf(m2[g] * inv_n + 1e-5f);
 #pragma unroll
-    for (int c = 0; c < W; ++c)
-      v[g * W + c] = mish_fast((v[g * W + c] - mean[g]) * r * gamma[g * W + c] + beta[g * W + c]);
+    for (int c = 0; c < W; ++c) v[g * W + c] = mish_fast((v[g * W + c] - mean[g]) * r * gamma[g * W + c] + beta[g * W + c]);
   }
 }
 
