@@ -311,8 +311,13 @@ class TemporalMapUnet(nn.Module):
         lib = _lib.load()
         h = self._handle_for(x.device)
         B = x.shape[0]
-        if tuple(x.shape[1:]) != (self.horizon, self.transition_dim):
+        if x.dim() != 3 or tuple(x.shape[1:]) != (self.horizon, self.transition_dim):
             raise ValueError(f"x must be [B,{self.horizon},{self.transition_dim}], got {tuple(x.shape)}")
+        time = torch.as_tensor(time, device=x.device)
+        if B == 0:   # empty batch: nothing to launch (torch modules return empty tensors too)
+            if self.use_cond == GuidanceType.CLASSIFIER_GUIDANCE and return_action_and_time_only:
+                return x.new_zeros((0, self.horizon, 3)), x.new_zeros((0, self.dim))
+            return x.new_zeros((0, self.horizon, self.transition_dim))
         x = x.detach().contiguous().float()
         feat = self.encode(img).detach().contiguous().float()
         t = time.reshape(-1).to(device=x.device, dtype=torch.int64).contiguous()

@@ -52,6 +52,10 @@ class DiffusionPlanner:
             raise RuntimeError("DiffusionPlanner.plan needs CUDA tensors (no CPU fallback)")
         dev = x_init.device
         B, T = x_init.shape[0], int(self.num_inference_steps)
+        if x_init.dim() != 3 or tuple(x_init.shape[1:]) != (m.horizon, m.transition_dim):
+            raise ValueError(f"x_init must be [B,{m.horizon},{m.transition_dim}], got {tuple(x_init.shape)}")
+        if B == 0:
+            return x_init.new_zeros((0, m.horizon, m.transition_dim), dtype=torch.float32)
         h = m._handle_for(dev)
         f32 = lambda t, shape=None: None if t is None else (t.detach().to(dev, torch.float32).expand(*shape) if shape else t.detach().to(dev, torch.float32)).contiguous()  # noqa: E731
         feat = f32(m.encode(image_or_feature.to(dev)), (B, m.dim))

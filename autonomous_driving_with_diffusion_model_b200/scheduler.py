@@ -160,6 +160,8 @@ class _FusedScheduler:
         if sample.device.type != "cuda":
             raise RuntimeError("scheduler.step runs on CUDA tensors only (no CPU fallback)")
         B, H, D = sample.shape
+        if B == 0:
+            return torch.empty_like(sample, dtype=torch.float32), torch.empty_like(sample, dtype=torch.float32)
         f32 = lambda t: None if t is None else t.detach().to(sample.device, torch.float32).expand(B, H, D).contiguous()  # noqa: E731
         mo, x = f32(model_output), f32(sample)
         mo_u, nz, tj, mk = f32(model_output_uncond), f32(noise), f32(target_traj), f32(target_mask)

@@ -331,6 +331,56 @@ def test_plan_host_entry_matches_device_entry():
     assert torch.equal(a, b)
 
 
+def test_edge_cases_empty_ragged_noncontiguous_and_errors():
+    model, sd = get_model("NO_GUIDANCE")
+    sched = make_sched("guidance_ddim")
+    sched.set_timesteps(10)
+    planner = P.DiffusionPlanner(model, sched, _cfg("NO_GUIDANCE", 10))
+    e = torch.zeros(0, 16, 7, device=DEV)
+    assert model(e, torch.zeros(0, 64, device=DEV), torch.tensor([5], device=DEV)).shape == (0, 16, 7)     # empty batch
+    assert planner.plan(e, torch.zeros(0, 64, device=DEV)).shape == (0, 16, 7)
+    assert sched.step(e, 90, e).prev_sample.shape == (0, 16, 7)
+    inp = W.synth_inputs(5, 0, 55)
+    x = inp["x"].to(DEV)
+    xnc = x.transpose(1, 2).contiguous().transpose(1, 2)            # non-contiguous view of the same values
+    assert not xnc.is_contiguous()
+    t = torch.tensor([7, 7, 7, 7, 7], device=DEV)
+    assert torch.equal(model(xnc, inp["feat"].to(DEV), t), model(x, inp["feat"].to(DEV), t))
+    assert torch.equal(model(x.double(), inp["feat"].to(DEV).double(), t), model(x, inp["feat"].to(DEV), t))   # dtype coercion
+    assert torch.equal(model(x, inp["feat"].to(DEV), 7), model(x, inp["feat"].to(DEV), torch.tensor([7], device=DEV)))  # scalar time
+    with pytest.raises(ValueError):
+        model(torch.zeros(2, 8, 7, device=DEV), inp["feat"][:2].to(DEV), t[:2])                 # wrong horizon
+    with pytest.raises(RuntimeError):
+        model(x, inp["feat"][:3].to(DEV), t)                                                    # feature rows do not match the batch
+    with pytest.raises(ValueError):
+        planner.plan(torch.zeros(2, 16, 5, device=DEV), inp["feat"][:2].to(DEV))
+    m2 = P.build_model(_cfg("FREE_GUIDANCE")).to(DEV).eval()
+    with pytest.raises(ValueError):                                                             # CFG plan without a target
+        P.DiffusionPlanner(m2, make_sched("guidance_ddim", "FREE_GUIDANCE"), _cfg("FREE_GUIDANCE", 10)).plan(x, inp["feat"].to(DEV))
+    m2.load_state_dict(W.make_state_dict("FREE_GUIDANCE"))
+    bad = dict(m2.state_dict()); bad.pop("cond_mlp.0.weight")
+    with pytest.raises(RuntimeError):
+        m2.load_state_dict(bad)                                                                 # missing key: same strictness as nn.Module
+
+
+def test_image_in_generate_traj_matches_oracle_with_encoder():
+    """generate_traj(image, target): encoder (hoisted, torch/cuDNN) + captured loop, vs the oracle fed the same feature."""
+    torch.backends.cudnn.allow_tf32 = False
+    model, sd = get_model("FREE_GUIDANCE")
+    cfg = _cfg("FREE_GUIDANCE", 10)
+    planner = P.DiffusionPlanner(model, make_sched("guidance_ddim", "FREE_GUIDANCE"), cfg)
+    img = W.synth_image(1, seed=8, h=128, w=224).to(DEV)
+    target = torch.tensor([[0.2, -0.1]], device=DEV)
+    planner.init_trajs = W.hash_normal("agent/init", (1, 16, 7)).to(DEV)
+    out = planner.generate_traj(img, target)
+    with torch.no_grad():
+        feat = model.perception(img).cpu()
+    ref = OP.plan(sd, "FREE_GUIDANCE", "guidance_ddim", planner.init_trajs.cpu(), feat, 10, target=target.cpu())
+    d = (out.cpu() - ref).abs()
+    assert float(d[..., :2].max()) <= 1e-3 * MAGIC and float(d[..., 2:].max()) <= 1e-3
+    torch.backends.cudnn.allow_tf32 = True
+
+
 # ------------------------------------------------------------------------------------------------------------
 # tensor-core precisions (tcgen05 path).  Stated bounds, normalised units:
 #   bf16x3 (bf16 hi/lo split, 3 MMAs, fp32 accumulate): forward <= 2e-4, full plan <= 1e-3  (the fp32 north_star bound)
