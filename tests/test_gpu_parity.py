@@ -442,6 +442,23 @@ def test_plan_tensor_core_precisions(golden_dir, name, precision):
         assert float(d.max()) <= 0.3 and float(d.mean()) <= 0.05, (name, float(d.max()), float(d.mean()))
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_tensor_core_all_tile_widths(precision):
+    """The column-tile width (64 / 32 / 16, with cluster GroupNorm exchange for the narrow ones) is picked from the batch
+    size: sweep batches that exercise every variant at every level, including partial last row tiles."""
+    model, sd = get_tc_model("NO_GUIDANCE", precision)
+    for B in (2, 9, 130, 300, 620):
+        inp = W.synth_inputs(B, 0, 300 + B)
+        t = torch.full((B,), 41, dtype=torch.long)
+        ref = U.unet_forward(sd, inp["x"], inp["feat"], t, None, "NO_GUIDANCE")
+        out = model(inp["x"].to(DEV), inp["feat"].to(DEV), t.to(DEV))
+        d = (out.cpu() - ref).abs()
+        if precision == "bf16x3":
+            assert float(d.max()) <= 2e-4, (B, float(d.max()))
+        else:
+            assert float(d.max()) <= 6e-2 and float(d.mean()) <= 1e-2, (B, float(d.max()), float(d.mean()))
+
+
 def test_tensor_core_full_size_determinism_and_sharding():
     model, sd = get_tc_model("NO_GUIDANCE", "bf16x3")
     T, B = 10, 256
