@@ -10,7 +10,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libb200plan.so")
-SOURCES = ["api.cu", "sched.cu", "embed.cu", "conv_ffma.cu", "conv_tc.cu", "trajpred.cu"]
+SOURCES = ["api.cu", "sched.cu", "embed.cu", "conv_ffma.cu", "conv_gemv.cu", "conv_tc.cu", "trajpred.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--expt-relaxed-constexpr",

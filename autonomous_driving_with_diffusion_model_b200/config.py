@@ -16,7 +16,7 @@ _DEFAULTS = {
                   NOISE_SCHEDULER=dict(BETA_START=1e-4, BETA_END=0.02, TYPE="squaredcos_cap_v2", PRED_TYPE="sample")),
     "GUIDANCE": dict(USE_COND="NO_GUIDANCE", LOSS_LIST=None, STEP=1, CLASSIFIER_SCALE=0.1, FREE_SCALE=1.0),
     "EVAL": dict(BATCH_SIZE=4, ETA=0, CHECKPOINT=None, SCHEDULER="ddim", SAMPLE_STEPS=100),
-    "B200": dict(PRECISION="fp32"),
+    "B200": dict(PRECISION="fp32", SMALL_BATCH_MAX=4),
 }
 
 

@@ -1,6 +1,7 @@
 // libb200plan: handle, weight packing, denoiser program, whole-plan CUDA graph.  Public ABI: include/b200plan.h.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -38,6 +39,8 @@ struct LayerOp {
   int out = BUF_NONE;
   // tensor-core copies (bf16 elements into the 16-bit pack): [taps][Cout][Cin] hi / lo, residual [Cout][RCin] hi / lo
   size_t tcW_hi = NPOS, tcW_lo = NPOS, tcRW_hi = NPOS, tcRW_lo = NPOS;
+  // K-major fp32 copies for the small-batch GEMV path: [Cout][taps][Cin], residual [Cout][RCin], head [head_dim][Cout]
+  size_t Wk = NPOS, resWk = NPOS, headWk = NPOS;
 };
 
 struct Buf { int L, C; size_t off; };  // per-sample floats = L*C; off = prefix sum of per-sample floats
@@ -95,6 +98,7 @@ struct b2p_handle_s {
   int64_t* p_tsteps = nullptr;
   std::vector<GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
+  int small_batch_max = B2P_SMALL_BATCH_DEFAULT;   // largest evaluation batch that takes the GEMV kernels
 
   int fail(int code, const std::string& m) { err = m; return code; }
 };
@@ -164,6 +168,18 @@ void pack_linear_T(const float* w, int out, int in, float* dst, int ld, int col0
     for (int i = 0; i < in; ++i) dst[(size_t)i * ld + col0 + o] = w[(size_t)o * in + i];
 }
 size_t pack_vec(b2p_handle_s* h, Packer& pk, const std::string& key, size_t n) { return pk.push(W(h, key), n); }
+
+// Conv1d weight [Cout][Cin][k] (or ConvTranspose1d [Cin][Cout][k]) -> K-major fp32 [Cout][k][Cin] (GEMV path)
+size_t pack_conv_kmajor(b2p_handle_s* h, Packer& pk, const std::string& key, int cout, int cin, int k, bool transposed) {
+  const float* w = W(h, key);
+  size_t off = pk.alloc((size_t)k * cin * cout);
+  float* o = pk.v.data() + off;
+  for (int co = 0; co < cout; ++co)
+    for (int j = 0; j < k; ++j)
+      for (int c = 0; c < cin; ++c)
+        o[((size_t)co * k + j) * cin + c] = transposed ? w[((size_t)c * cout + co) * k + j] : w[((size_t)co * cin + c) * k + j];
+  return off;
+}
 
 // ---- bf16 hi/lo split (round-to-nearest-even), host side ----
 inline uint16_t f2bf(float f) {
@@ -263,6 +279,7 @@ int add_res_block(b2p_handle_s* h, Packer& pk, const std::string& p, int in0, in
   LayerOp a;
   a.in0 = in0; a.in1 = in1; a.C0 = C0; a.C1 = C1; a.Lin = a.Lout = L; a.Cout = cout; a.taps = 5; a.stride = 1; a.pad = 2;
   a.W = pack_conv(h, pk, p + ".blocks.0.block.0.weight", cout, cin, 5);
+  a.Wk = pack_conv_kmajor(h, pk, p + ".blocks.0.block.0.weight", cout, cin, 5, false);
   if (cin % 64 == 0) pack_conv_tc(h, p + ".blocks.0.block.0.weight", cout, cin, 5, false, &a.tcW_hi, &a.tcW_lo);
   a.bias = pack_vec(h, pk, p + ".blocks.0.block.0.bias", cout);
   a.gamma = pack_vec(h, pk, p + ".blocks.0.block.2.weight", cout);
@@ -278,6 +295,7 @@ int add_res_block(b2p_handle_s* h, Packer& pk, const std::string& p, int in0, in
   LayerOp b;
   b.in0 = a.out; b.C0 = cout; b.Lin = b.Lout = L; b.Cout = cout; b.taps = 5; b.stride = 1; b.pad = 2;
   b.W = pack_conv(h, pk, p + ".blocks.1.block.0.weight", cout, cout, 5);
+  b.Wk = pack_conv_kmajor(h, pk, p + ".blocks.1.block.0.weight", cout, cout, 5, false);
   pack_conv_tc(h, p + ".blocks.1.block.0.weight", cout, cout, 5, false, &b.tcW_hi, &b.tcW_lo);
   b.bias = pack_vec(h, pk, p + ".blocks.1.block.0.bias", cout);
   b.gamma = pack_vec(h, pk, p + ".blocks.1.block.2.weight", cout);
@@ -285,6 +303,7 @@ int add_res_block(b2p_handle_s* h, Packer& pk, const std::string& p, int in0, in
   if (cin != cout) {
     b.rin0 = in0; b.rin1 = in1; b.RC0 = C0; b.RC1 = C1;
     b.resW = pack_conv(h, pk, p + ".residual_conv.weight", cout, cin, 1);
+    b.resWk = pack_conv_kmajor(h, pk, p + ".residual_conv.weight", cout, cin, 1, false);
     if (cin % 64 == 0) pack_conv_tc(h, p + ".residual_conv.weight", cout, cin, 1, false, &b.tcRW_hi, &b.tcRW_lo);
     b.resB = pack_vec(h, pk, p + ".residual_conv.bias", cout);
   } else {
@@ -340,6 +359,7 @@ int build_program(b2p_handle_s* h) {
       LayerOp d;
       d.in0 = x; d.C0 = co; d.Lin = L; d.Lout = L / 2; d.Cout = co; d.taps = 3; d.stride = 2; d.pad = 1;
       d.W = pack_conv(h, pk, p + ".3.conv.weight", co, co, 3);
+      d.Wk = pack_conv_kmajor(h, pk, p + ".3.conv.weight", co, co, 3, false);
       pack_conv_tc(h, p + ".3.conv.weight", co, co, 3, false, &d.tcW_hi, &d.tcW_lo);
       d.bias = pack_vec(h, pk, p + ".3.conv.bias", co);
       d.out = new_buf(h, L / 2, co);
@@ -361,6 +381,7 @@ int build_program(b2p_handle_s* h) {
     LayerOp t;
     t.in0 = x; t.C0 = ci; t.Lin = L; t.Lout = 2 * L; t.Cout = ci; t.taps = 4; t.stride = 2; t.pad = 1; t.transposed = 1;
     t.W = pack_convT(h, pk, p + ".3.conv.weight", ci, ci, 4);
+    t.Wk = pack_conv_kmajor(h, pk, p + ".3.conv.weight", ci, ci, 4, true);
     pack_conv_tc(h, p + ".3.conv.weight", ci, ci, 4, true, &t.tcW_hi, &t.tcW_lo);
     t.bias = pack_vec(h, pk, p + ".3.conv.bias", ci);
     t.out = new_buf(h, 2 * L, ci);
@@ -377,6 +398,9 @@ int build_program(b2p_handle_s* h) {
     LayerOp f;
     f.in0 = x; f.C0 = fin; f.Lin = f.Lout = L; f.Cout = fin; f.taps = 5; f.stride = 1; f.pad = 2;
     f.W = pack_conv(h, pk, p + ".0.block.0.weight", fin, fin, 5);
+    f.Wk = pack_conv_kmajor(h, pk, p + ".0.block.0.weight", fin, fin, 5, false);
+    f.headWk = pack_vec(h, pk, p + ".1.weight", (size_t)(cls ? 3 : h->D) * fin);   // Conv1d(fin, head_dim, 1) weight is already [head_dim][fin]
+    f.out = new_buf(h, L, fin);   // output of the conv block (only the GEMV path, which runs the 1x1 head as its own launch, reads it)
     pack_conv_tc(h, p + ".0.block.0.weight", fin, fin, 5, false, &f.tcW_hi, &f.tcW_lo);
     f.bias = pack_vec(h, pk, p + ".0.block.0.bias", fin);
     f.gamma = pack_vec(h, pk, p + ".0.block.2.weight", fin);
@@ -526,7 +550,10 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
     ++*launches;
     temb_rows = h->d_temb;
   }
-  const int prec = h->cfg.precision;
+  // Small batches take the exact-fp32 GEMV program whatever the precision mode: with a handful of trajectories a layer is
+  // pure weight streaming, the GEMV kernels prefetch weights layers ahead, and no bf16 splitting is needed.
+  const bool use_gemv = rows <= h->small_batch_max;
+  const int prec = use_gemv ? (int)B2P_PREC_FP32 : h->cfg.precision;
   const bool tc = prec != B2P_PREC_FP32;
   const int nsplit = prec == B2P_PREC_BF16X3 ? 2 : 1;
   auto hi_ptr = [&](int id) -> __nv_bfloat16* {
@@ -610,7 +637,7 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
       if (op.gamma != NPOS) { t.gn_gamma = P + op.gamma; t.gn_beta = P + op.beta; t.cg = op.Cout / 8; }
       if (op.temb_off >= 0) { t.temb = temb_rows + op.temb_off; t.temb_stride = h->temb_total; t.temb2 = ttab_row ? ttab_row + op.temb_off : nullptr; }
       if (op.headW != NPOS) { t.headW = P + op.headW; t.headB = P + op.headB; t.head_dim = op.head_dim; t.head_out = head_out; }
-      t.out_hi = hi_ptr(op.out); t.out_lo = lo_ptr(op.out);
+      if (op.headW == NPOS) { t.out_hi = hi_ptr(op.out); t.out_lo = lo_ptr(op.out); }   // the head layer's own output is not materialised
       if ((rc = launch_conv_tc(m, t, nsplit, s))) return h->fail(rc, "tcgen05 conv launch failed");
       ++*launches;
       continue;
@@ -648,6 +675,26 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
         }
       }
     }
+    if (!tc && use_gemv) {
+      // small batch: exact-fp32 GEMV kernels (one per layer; the fused 1x1 head becomes its own tiny launch)
+      ConvArgs g = a;
+      g.Wk = P + op.Wk; g.resWk = op.resWk != NPOS ? P + op.resWk : nullptr;
+      g.headW = nullptr; g.headB = nullptr; g.head_out = nullptr;
+      if (conv_gemv_applicable(g)) {
+        if ((rc = launch_conv_gemv(g, s))) return h->fail(rc, "gemv conv launch failed");
+        ++*launches;
+        if (op.headW != NPOS) {
+          ConvArgs hd{};
+          hd.x0 = g.out; hd.C0 = op.Cout; hd.Lin = hd.Lout = op.Lout; hd.log2Lout = ilog2(op.Lout); hd.nrows = rows * op.Lout;
+          hd.Cout = op.head_dim; hd.taps = 1; hd.jmin = hd.jmax = 0; hd.stride = 1; hd.Wk = P + op.headWk; hd.bias = P + op.headB;
+          hd.out = head_out;
+          if ((rc = launch_conv_gemv(hd, s))) return h->fail(rc, "gemv head launch failed");
+          ++*launches;
+        }
+        continue;
+      }
+    }
+    if (op.headW != NPOS) a.out = nullptr;   // fused head: the conv block's own output is not materialised
     if ((rc = launch_conv_ffma(a, s))) return h->fail(rc, "conv launch failed");
     ++*launches;
   }
@@ -780,6 +827,13 @@ int b2p_finalize_weights(b2p_handle h) {
 int b2p_set_precision(b2p_handle h, int precision) {
   if (!h || precision < 0 || precision > 2) return B2P_ERR_INVALID_ARG;
   h->cfg.precision = precision;
+  drop_graphs(h);
+  return B2P_OK;
+}
+
+int b2p_set_small_batch_max(b2p_handle h, int max_samples) {
+  if (!h || max_samples < 0) return B2P_ERR_INVALID_ARG;
+  h->small_batch_max = max_samples;
   drop_graphs(h);
   return B2P_OK;
 }

@@ -1,5 +1,6 @@
 // Internal declarations shared by the .cu files of libb200plan.  Not part of the public ABI (include/b200plan.h).
 #pragma once
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,6 +36,8 @@ struct ConvArgs {
   int taps, jmin, jmax;               // kernel taps; only taps in [jmin, jmax] can touch a valid position
   int stride, pad, transposed;
   const float* W;                     // packed [taps][C0+C1][Cout]
+  const float* Wk;                    // K-major copy [Cout][taps][C0+C1] (small-batch GEMV path), may be null
+  const float* resWk;                 // K-major residual weights [Cout][RC0+RC1], may be null
   const float* bias;                  // [Cout]
   const float* gn_gamma; const float* gn_beta;  // null => no GroupNorm/Mish
   int cg;                             // channels per group (Cout/8)
@@ -50,6 +53,22 @@ struct ConvArgs {
 };
 
 int launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
+// small-batch (<= 32 output rows) exact-fp32 GEMV path (conv_gemv.cu)
+bool conv_gemv_applicable(const ConvArgs& a);
+int launch_conv_gemv(const ConvArgs& a, cudaStream_t s);
+
+// Ask for the maximum shared-memory carve-out for `kernel` (once per kernel).  Every kernel of the plan uses the same
+// L1/shared split, so kernels that overlap under programmatic dependent launch never wait for an SM to be reconfigured.
+inline void prefer_max_smem_carveout(const void* kernel) {
+  static const void* seen[64];
+  static int nseen = 0;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("B2P_CARVEOUT"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return;
+  for (int i = 0; i < nseen; ++i) if (seen[i] == kernel) return;
+  if (nseen < 64) seen[nseen++] = kernel;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 
 // launch `kernel` with the programmatic-stream-serialization attribute (the kernel must call pdl_wait() before it reads
 // anything produced by the preceding kernel)
@@ -61,6 +80,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  prefer_max_smem_carveout((const void*)kernel);
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 

@@ -271,6 +271,7 @@ template <int TM>
 static int launch_tm(const ConvArgs& a, bool vec, cudaStream_t s) {
   dim3 grid((a.nrows + TM - 1) / TM, a.Cout / TN);
   // plain (fully serialised) launches: these grids fill the machine, so early-resident dependents only take SM slots away
+  prefer_max_smem_carveout(vec ? (const void*)conv_ffma_kernel<TM, true> : (const void*)conv_ffma_kernel<TM, false>);
   if (vec) conv_ffma_kernel<TM, true><<<grid, NT, 0, s>>>(a);
   else conv_ffma_kernel<TM, false><<<grid, NT, 0, s>>>(a);
   return (int)cudaGetLastError();

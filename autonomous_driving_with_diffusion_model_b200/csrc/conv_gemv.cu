@@ -1,0 +1,370 @@
+// Small-batch fused conv layer on CUDA cores, exact fp32 (K3 in SURVEY.md Appendix C: weight-streaming GEMV).
+// Same contract as conv_ffma.cu (ConvArgs; Conv1dBlock / residual block epilogue of modeling/helpers.py:95-112 and
+// modeling/temporal.py:53-55), specialised for single-trajectory plan latency (the closed-loop use of the reference,
+// carla agent -> generate_traj with B = 1).
+//
+// With L_out <= 16 rows per sample the layer is a GEMV and the work is streaming the layer's weights.  Grid =
+// (C_out / NC, samples): a CTA owns NC in {1,2,4,8} output channels of one sample, NC chosen so that every layer runs on
+// ~64 CTAs per sample; its 16 warps are NC channels x 16/NC slices of K = taps x C_in.  The CTA's weight slice
+// ([NC][K] fp32, from a K-major copy of the layer's weights) is fetched with cp.async BEFORE the programmatic-dependency
+// wait, and the kernel releases its dependents at its very first instruction, so weight streaming runs several layers
+// ahead of the dependency chain; after the wait only the (tiny) input activation is read.  A GroupNorm group (C_out/8
+// channels) spans cg/NC CTAs: they form a thread-block cluster and merge their (mean, M2) through distributed shared
+// memory with the parallel-variance formula.  All sums are combined in a fixed order: results are run-to-run identical.
+#include "common.cuh"
+
+namespace b2p {
+
+constexpr int GV_MAXNC = 8;     // max output channels per CTA
+constexpr int GV_NW = 16;       // warps per CTA = channels x K slices
+constexpr int GV_NT = 32 * GV_NW;
+constexpr int GV_MAXL = 16;     // max output positions per sample
+
+#ifdef B2P_GV_TRACE   // developer tracing (scripts/gemv_bench.cu): per-stage clocks of CTA (0,0) of every launch
+__device__ unsigned long long gv_trace[8192 * 8];
+int gv_trace_launch = 0;
+#define GV_T(k)                                                                                      \
+  do {                                                                                               \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {                                    \
+      unsigned long long t_;                                                                         \
+      if ((k) < 6) t_ = clock64(); else asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));     \
+      gv_trace[trace_id * 8 + (k)] = t_;                                                             \
+    }                                                                                                \
+  } while (0)
+#else
+#define GV_T(k)
+#endif
+
+__device__ __forceinline__ void gv_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gv_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gv_st_cluster(const float* local, uint32_t cta, float x) {
+  uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(x) : "memory");
+}
+__device__ __forceinline__ void gv_cp16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gv_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct GvStatic {
+  float P[GV_NW * GV_MAXL];      // per-K-slice partial conv outputs: [slice][row][channel]
+  float RP[GV_NW * GV_MAXL];     // same for the residual 1x1 conv
+  float O[GV_MAXL * GV_MAXNC];   // conv outputs (+bias): [row][channel]
+  int src[5][GV_MAXL];           // offset (floats) into X of the input row feeding (tap, output row); zero row when padding
+  int idsrc[1][GV_MAXL];         // same for the residual 1x1 conv (row r feeds row r)
+  float mean, m2;
+  float cx[2][8];                // cluster exchange: [mean|M2][source CTA]
+};
+
+// x / d for a runtime d that is almost always a power of two
+struct GvDiv {
+  int d, sh;
+  __device__ __forceinline__ int div(int x) const { return sh >= 0 ? x >> sh : x / d; }
+};
+__device__ __forceinline__ GvDiv gv_div(int d) {
+  GvDiv r;
+  r.d = d; r.sh = (d & (d - 1)) == 0 ? 31 - __clz(d) : -1;
+  return r;
+}
+
+// global -> shared copy of n floats: 16-byte cp.async when both sides allow it, scalar otherwise
+__device__ __forceinline__ void gv_copy(float* dst, const float* __restrict__ src, int n, bool vec, int tid) {
+  if (vec) for (int i = tid * 4; i < n; i += GV_NT * 4) gv_cp16(dst + i, src + i);
+  else for (int i = tid; i < n; i += GV_NT) dst[i] = __ldg(src + i);
+}
+
+// rows [nrow][C0 | C1] gathered from two channels-last sources into shared memory
+__device__ __forceinline__ void gv_load_rows(float* dst, const float* __restrict__ g0, int C0, const float* __restrict__ g1, int C1,
+                                             int nrow, int tid) {
+  const int C = C0 + C1;
+  if (((C0 | C1) & 3) == 0) {
+    const GvDiv q = gv_div(C >> 2);
+    const int q0 = C0 >> 2;
+    for (int i = tid; i < nrow * q.d; i += GV_NT) {
+      const int row = q.div(i), c4 = i - row * q.d;
+      gv_cp16(dst + row * C + c4 * 4, c4 < q0 ? g0 + row * C0 + c4 * 4 : g1 + row * C1 + (c4 - q0) * 4);
+    }
+  } else {
+    for (int i = tid; i < nrow * C; i += GV_NT) {
+      const int row = i / C, c = i % C;
+      dst[i] = c < C0 ? __ldg(g0 + row * C0 + c) : __ldg(g1 + row * C1 + (c - C0));
+    }
+  }
+}
+
+// Sum N per-lane partial vectors over the warp with a transposing butterfly (N/2 + N/4 + ... shuffles instead of 5 N):
+// afterwards v[0] of lane l is the warp total of row gv_row<N>(l), replicated over the lanes that share that row.
+template <int N>
+__device__ __forceinline__ void gv_reduce(float* v, int lane, int off) {
+  if constexpr (N > 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const float send = up ? v[i] : v[i + N / 2];
+      const float keep = up ? v[i + N / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    gv_reduce<N / 2>(v, lane, off >> 1);
+  } else {
+    for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  }
+}
+template <int N>
+__device__ __forceinline__ int gv_row(int lane) {
+  int r = 0, off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, off >>= 1)
+    if (lane & off) r += n / 2;
+  return r;
+}
+
+// partial dot products of one channel with RT output rows over K slice `ks` of `ns` (K = taps x C_in, flat; float4
+// granules are dealt round-robin to the ns x 32 lanes working on the channel).  Leaves this lane's row total in acc[0].
+template <int RT, bool VEC>
+__device__ __forceinline__ void gv_dot(const float* __restrict__ wcol, const float* __restrict__ X, int Keff, int Cin,
+                                       const int (*src)[GV_MAXL], int lane, int ks, int ns, float (&acc)[RT]) {
+#pragma unroll
+  for (int r = 0; r < RT; ++r) acc[r] = 0.f;
+  const GvDiv dc = gv_div(Cin);
+  if (VEC) {
+#pragma unroll 2
+    for (int k = (ks * 32 + lane) * 4; k < Keff; k += 128 * ns) {
+      const int jj = dc.div(k), ci = k - jj * Cin;          // C_in % 4 == 0: a float4 never straddles two taps
+      const float4 w = *reinterpret_cast<const float4*>(wcol + k);
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(X + src[jj][r] + ci);
+        acc[r] += fmaf(w.x, x.x, w.y * x.y) + fmaf(w.z, x.z, w.w * x.w);
+      }
+    }
+  } else {
+    for (int k = ks * 32 + lane; k < Keff; k += 32 * ns) {
+      const int jj = dc.div(k), ci = k - jj * Cin;
+      const float w = wcol[k];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) acc[r] = fmaf(w, X[src[jj][r] + ci], acc[r]);
+    }
+  }
+  gv_reduce<RT>(acc, lane, 16);
+}
+
+__host__ __device__ inline int gv_pad4(int n) { return (n + 3) & ~3; }
+
+// NC = channels per CTA (power of two <= 8), cls = CTAs per cluster (= GroupNorm group size / NC, or 1)
+template <int RT>
+__global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, int cls, int trace_id) {
+  extern __shared__ __align__(16) float dyn[];
+  __shared__ GvStatic st;
+  pdl_launch_dependents();       // let the following layers start streaming their weights right away
+  GV_T(6); GV_T(0);
+  if (cls > 1) gv_cluster_arrive();   // phase 1: "every CTA of the cluster is running" (needed before remote smem stores)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int col0 = blockIdx.x * NC, b = blockIdx.y;
+  const int Cin = a.C0 + a.C1, RCin = a.RC0 + a.RC1;
+  const int ntaps = a.jmax - a.jmin + 1;
+  const int Keff = ntaps * Cin;
+  const int L = a.Lout, Lin = a.Lin;
+  const int nc = min(NC, a.Cout - col0);
+  const int lnc = 31 - __clz(NC);                     // NC is a power of two
+  const int ns = GV_NW >> lnc;                        // K slices per channel
+  const bool vecW = (Cin & 3) == 0, vecR = (RCin & 3) == 0;
+  // dynamic shared memory carve-up (every region 16-byte aligned)
+  float* Wsm = dyn;                                   // [NC][Keff]
+  float* RWsm = Wsm + gv_pad4(NC * Keff);             // [NC][RCin]
+  float* X = RWsm + gv_pad4(NC * RCin);               // [Lin + 1][Cin], last row zero (padding taps read it)
+  float* RX = X + gv_pad4((Lin + 1) * Cin);           // [L][RCin]
+
+  // ---- everything that does not depend on the previous layer ----
+  for (int w = 0; w < nc; ++w)
+    gv_copy(Wsm + w * Keff, a.Wk + ((size_t)(col0 + w) * a.taps + a.jmin) * Cin, Keff, vecW, tid);
+  if (a.resWk)
+    for (int w = 0; w < nc; ++w) gv_copy(RWsm + w * RCin, a.resWk + (size_t)(col0 + w) * RCin, RCin, vecR, tid);
+  if (tid < ntaps * GV_MAXL) {   // source-row table: which input row feeds (tap, output row)
+    const int jj = tid / GV_MAXL, l = tid % GV_MAXL, j = a.jmin + jj;
+    int pos;
+    if (!a.transposed) pos = l * a.stride + j - a.pad;
+    else { const int num = l + a.pad - j; pos = (num >= 0 && num % a.stride == 0) ? num / a.stride : -1; }
+    st.src[jj][l] = (l < L && pos >= 0 && pos < Lin) ? pos * Cin : Lin * Cin;
+  }
+  if (tid < GV_MAXL) st.idsrc[0][tid] = (tid < L ? tid : 0) * RCin;
+  for (int i = tid; i < Cin; i += GV_NT) X[Lin * Cin + i] = 0.f;
+  // this thread's epilogue element (row er, channel ec) and its layer constants
+  const int er = tid >> lnc, ew = tid & (NC - 1), ec = col0 + ew;
+  const bool eown = tid < L * NC;                     // owns a (row, channel) slot of O
+  const bool eact = eown && ew < nc;
+  const bool gn = a.gn_gamma != nullptr;
+  float e_gamma = 1.f, e_beta = 0.f, e_add = 0.f;
+  if (eact && gn) { e_gamma = __ldg(a.gn_gamma + ec); e_beta = __ldg(a.gn_beta + ec); }
+  const float e_bias = (eact && a.bias) ? __ldg(a.bias + ec) : 0.f;
+  const float e_rb = (eact && a.resWk) ? __ldg(a.resB + ec) : 0.f;
+  GV_T(1);
+  pdl_wait();                    // inputs are produced by the preceding kernel
+  GV_T(2);
+  // ---- this sample's input activations ----
+  gv_load_rows(X, a.x0 + (size_t)(a.x0_period > 0 ? b % a.x0_period : b) * Lin * a.C0, a.C0,
+               a.C1 ? a.x1 + (size_t)b * Lin * a.C1 : nullptr, a.C1, Lin, tid);
+  if (a.resWk)
+    gv_load_rows(RX, a.rx0 + (size_t)(a.rx0_period > 0 ? b % a.rx0_period : b) * L * a.RC0, a.RC0,
+                 a.RC1 ? a.rx1 + (size_t)b * L * a.RC1 : nullptr, a.RC1, L, tid);
+  if (eact) {                    // additive epilogue terms: in flight while the dot products run
+    if (a.temb) e_add += __ldg(a.temb + (size_t)b * a.temb_stride + ec);
+    if (a.temb2) e_add += __ldg(a.temb2 + ec);
+    if (a.res_id) e_add += __ldg(a.res_id + ((size_t)b * L + er) * a.Cout + ec);
+  }
+  gv_cp_wait_all();
+  __syncthreads();
+  GV_T(3);
+
+  // ---- one warp per (K slice, output channel) ----
+  {
+    const int ch = warp & (NC - 1), ks = warp >> lnc;
+    const int myrow = gv_row<RT>(lane);
+    const bool writer = (lane & (32 / RT - 1)) == 0 && myrow < L;
+    float acc[RT];
+    if (ch < nc) {
+      if (vecW) gv_dot<RT, true>(Wsm + ch * Keff, X, Keff, Cin, st.src, lane, ks, ns, acc);
+      else gv_dot<RT, false>(Wsm + ch * Keff, X, Keff, Cin, st.src, lane, ks, ns, acc);
+      if (writer) st.P[(ks * L + myrow) * NC + ch] = acc[0];
+      if (a.resWk) {
+        if (vecR) gv_dot<RT, true>(RWsm + ch * RCin, RX, RCin, RCin, st.idsrc, lane, ks, ns, acc);
+        else gv_dot<RT, false>(RWsm + ch * RCin, RX, RCin, RCin, st.idsrc, lane, ks, ns, acc);
+        if (writer) st.RP[(ks * L + myrow) * NC + ch] = acc[0];
+      }
+    } else if (writer) {
+      st.P[(ks * L + myrow) * NC + ch] = 0.f;
+      st.RP[(ks * L + myrow) * NC + ch] = 0.f;
+    }
+  }
+  __syncthreads();
+  GV_T(4);
+  // combine the K slices in a fixed order (+ bias): done by the thread that owns (row, channel) in the epilogue
+  float e_val = 0.f, e_res = 0.f;
+  if (eown) {
+    float v = st.P[tid];
+    for (int k = 1; k < ns; ++k) v += st.P[k * L * NC + tid];
+    e_val = ew < nc ? v + e_bias : 0.f;
+    if (a.resWk) {
+      float rv = st.RP[tid];
+      for (int k = 1; k < ns; ++k) rv += st.RP[k * L * NC + tid];
+      e_res = rv + e_rb;
+    }
+  }
+
+  // ---- GroupNorm statistics: this CTA's NC channels x L rows are one part of the sample's group ----
+  const int ne = NC * L;           // <= 128: the owners are the first ne threads
+  float mu = 0.f, m2 = 0.f;
+  if (gn) {
+    if (eown) st.O[tid] = e_val;
+    __syncthreads();
+    if (warp == 0) {
+      float v[4];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[i] = lane + 32 * i < ne ? st.O[lane + 32 * i] : 0.f; s += v[i]; }
+#pragma unroll
+      for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+      const float mean = s / (float)ne;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (lane + 32 * i < ne) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+      for (int k = 16; k > 0; k >>= 1) q += __shfl_xor_sync(0xffffffffu, q, k);
+      if (cls > 1) {
+        gv_cluster_wait();                                  // phase 1 complete: all peers are running
+        if (lane < cls) {                                   // publish this part's (mean, M2) to every CTA of the cluster
+          const int crank = blockIdx.x % cls;
+          gv_st_cluster(&st.cx[0][crank], (uint32_t)lane, mean);
+          gv_st_cluster(&st.cx[1][crank], (uint32_t)lane, q);
+        }
+      } else if (lane == 0) {
+        st.mean = mean; st.m2 = q;
+      }
+    } else if (cls > 1) {
+      gv_cluster_wait();
+    }
+    if (cls > 1) {
+      gv_cluster_arrive();
+      gv_cluster_wait();                                    // phase 2: every part has arrived
+      float ms = 0.f;                                       // merge equal-sized parts in a fixed order (parallel-variance formula)
+      for (int p = 0; p < cls; ++p) ms += st.cx[0][p];
+      mu = ms / (float)cls;
+      for (int p = 0; p < cls; ++p) { const float d = st.cx[0][p] - mu; m2 += st.cx[1][p] + (float)ne * d * d; }
+    } else {
+      __syncthreads();
+      mu = st.mean; m2 = st.m2;
+    }
+  } else if (cls > 1) {
+    gv_cluster_wait();
+  }
+  GV_T(5);
+
+  // ---- epilogue: one thread per (row, channel) ----
+  if (eact) {
+    float v = e_val;
+    if (gn) {
+      const float rstd = 1.0f / sqrtf(m2 / (float)(a.cg * L) + 1e-5f);
+      v = mish_f((v - mu) * rstd * e_gamma + e_beta);
+    }
+    a.out[((size_t)b * L + er) * a.Cout + ec] = v + e_add + e_res;
+  }
+  GV_T(7);
+}
+
+// channels per CTA: aim at ~64 CTAs per sample, GroupNorm groups of at most 8 CTAs
+static int gv_pick_nc(const ConvArgs& a) {
+  int nc = 1;
+  while (nc < GV_MAXNC && (a.Cout + nc - 1) / nc > 64) nc *= 2;
+  if (a.gn_gamma) while (nc < GV_MAXNC && a.cg / nc > 8) nc *= 2;
+  return nc;
+}
+
+static size_t gv_smem_floats(const ConvArgs& a, int nc) {
+  const int Cin = a.C0 + a.C1, RCin = a.RC0 + a.RC1, Keff = (a.jmax - a.jmin + 1) * Cin;
+  return (size_t)gv_pad4(nc * Keff) + gv_pad4(nc * RCin) + gv_pad4((a.Lin + 1) * Cin) + gv_pad4(a.Lout * RCin);
+}
+
+template <int RT>
+static int launch_rt(const ConvArgs& a, int nc, int cls, size_t smem, cudaStream_t s) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    B2P_CUDA_TRY(cudaFuncSetAttribute(conv_gemv_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  prefer_max_smem_carveout((const void*)conv_gemv_kernel<RT>);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((a.Cout + nc - 1) / nc, a.nrows / a.Lout); cfg.blockDim = dim3(GV_NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = cls; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = cls > 1 ? 2 : 1;
+  int trace_id = 0;
+#ifdef B2P_GV_TRACE
+  trace_id = gv_trace_launch++ & 8191;
+#endif
+  return (int)cudaLaunchKernelEx(&cfg, conv_gemv_kernel<RT>, a, nc, cls, trace_id);
+}
+
+bool conv_gemv_applicable(const ConvArgs& a) {
+  if (a.Lout > GV_MAXL || a.Lin > 2 * GV_MAXL || a.nrows % a.Lout != 0 || a.nrows / a.Lout > 65535) return false;
+  if (!a.Wk || (a.resW && !a.resWk) || a.headW || a.out_hi || a.res_out || !a.out) return false;
+  if (a.jmax - a.jmin + 1 > 5) return false;
+  const int nc = gv_pick_nc(a);
+  if (a.gn_gamma && (a.cg % nc != 0 || a.cg / nc > 8 || (a.Cout / nc) % (a.cg / nc) != 0)) return false;
+  return gv_smem_floats(a, nc) * sizeof(float) <= 200 * 1024;
+}
+
+int launch_conv_gemv(const ConvArgs& a, cudaStream_t s) {
+  if (!conv_gemv_applicable(a)) return B2P_ERR_INVALID_ARG;
+  const int nc = gv_pick_nc(a);
+  const size_t smem = gv_smem_floats(a, nc) * sizeof(float);
+  const int cls = a.gn_gamma ? a.cg / nc : 1;               // CTAs sharing one GroupNorm group
+  if (a.Lout <= 2) return launch_rt<2>(a, nc, cls, smem, s);
+  if (a.Lout <= 4) return launch_rt<4>(a, nc, cls, smem, s);
+  if (a.Lout <= 8) return launch_rt<8>(a, nc, cls, smem, s);
+  return launch_rt<16>(a, nc, cls, smem, s);
+}
+
+}  // namespace b2p

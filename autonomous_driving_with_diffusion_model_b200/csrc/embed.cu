@@ -84,6 +84,7 @@ __global__ void embed_kernel(EmbedArgs a) {
 
 int launch_embed(const EmbedArgs& a, cudaStream_t s) {
   if (a.dim * 4 > 1024 || a.dim % 4 != 0 || a.B <= 0 || a.t_count <= 0 || a.feat_rows <= 0) return B2P_ERR_INVALID_ARG;
+  prefer_max_smem_carveout((const void*)embed_kernel);
   embed_kernel<<<a.B, 4 * a.dim, sizeof(float) * 14 * a.dim, s>>>(a);
   return (int)cudaGetLastError();
 }

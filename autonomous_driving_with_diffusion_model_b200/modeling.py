@@ -209,7 +209,8 @@ class StatePredictor(_Tree):
 
 class TemporalMapUnet(nn.Module):
     def __init__(self, horizon, transition_dim=2, attention=False, dim=128, dim_mults=(1, 2, 4, 8),
-                 diffuser_building_block="concat", use_cond=GuidanceType.NO_GUIDANCE, precision: str = "fp32"):
+                 diffuser_building_block="concat", use_cond=GuidanceType.NO_GUIDANCE, precision: str = "fp32",
+                 small_batch_max: int = 4):
         super().__init__()
         if diffuser_building_block != "concat":
             raise NotImplementedError  # modeling/temporal.py:72-75
@@ -220,6 +221,7 @@ class TemporalMapUnet(nn.Module):
         self.horizon, self.transition_dim, self.dim, self.dim_mults = int(horizon), int(transition_dim), int(dim), tuple(int(m) for m in dim_mults)
         self.use_cond = use_cond
         self.precision = precision
+        self.small_batch_max = int(small_batch_max)
         self.magic_num = 23.315
         special = {"perception": ImageEncoder, "state_pred": StatePredictor}
         root = _Tree()
@@ -260,6 +262,7 @@ class TemporalMapUnet(nn.Module):
             cfg.precision = _lib.PRECISIONS[self.precision]
             h = C.c_void_p()
             _lib.check(lib.b2p_create(C.byref(cfg), idx, C.byref(h)), None, "b2p_create")
+            _lib.check(lib.b2p_set_small_batch_max(h, self.small_batch_max), h, "b2p_set_small_batch_max")
             self._handles[idx] = h
         h = self._handles[idx]
         key = self._version_key()
@@ -279,6 +282,17 @@ class TemporalMapUnet(nn.Module):
         lib = _lib.load()
         for h in self._handles.values():
             _lib.check(lib.b2p_set_precision(h, _lib.PRECISIONS[precision]), h, "b2p_set_precision")
+        return self
+
+    def set_small_batch_max(self, max_samples: int) -> "TemporalMapUnet":
+        """Evaluations of at most `max_samples` trajectories (CFG doubling included) run the small-batch exact-fp32 GEMV
+        kernels in every precision mode (single-trajectory closed-loop planning); 0 turns that path off."""
+        if max_samples < 0:
+            raise ValueError("max_samples must be >= 0")
+        self.small_batch_max = int(max_samples)
+        lib = _lib.load()
+        for h in self._handles.values():
+            _lib.check(lib.b2p_set_small_batch_max(h, self.small_batch_max), h, "b2p_set_small_batch_max")
         return self
 
     def __del__(self):
@@ -353,4 +367,5 @@ def build_model(cfg) -> TemporalMapUnet:
     return TemporalMapUnet(horizon=cfg.MODEL.HORIZON, transition_dim=cfg.MODEL.TRANSITION_DIM, attention=cfg.MODEL.USE_ATTN,
                            dim=cfg.MODEL.DIM, dim_mults=cfg.MODEL.DIM_MULTS,
                            diffuser_building_block=cfg.MODEL.DIFFUSER_BUILDING_BLOCK, use_cond=GuidanceType[cfg.TRAIN.USE_COND],
-                           precision=getattr(getattr(cfg, "B200", None), "PRECISION", "fp32") if hasattr(cfg, "B200") else "fp32")
+                           precision=getattr(getattr(cfg, "B200", None), "PRECISION", "fp32") if hasattr(cfg, "B200") else "fp32",
+                           small_batch_max=getattr(getattr(cfg, "B200", None), "SMALL_BATCH_MAX", 4) if hasattr(cfg, "B200") else 4)

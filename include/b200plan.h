@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define B2P_ABI_VERSION 3
+#define B2P_ABI_VERSION 4
 
 typedef enum {
   B2P_OK = 0,
@@ -118,6 +118,11 @@ int b2p_weight_info(b2p_handle h, int index, const char** key, int64_t* numel);
 /* pack + upload; must be called after the last b2p_load_weight and again after any weight change */
 int b2p_finalize_weights(b2p_handle h);
 int b2p_set_precision(b2p_handle h, int precision);
+/* Denoiser evaluations of at most `max_samples` trajectories (classifier-free doubling included) run the small-batch
+ * exact-fp32 GEMV kernels whatever the precision mode (closed-loop planning calls generate_traj with one trajectory,
+ * carla_agent; default B2P_SMALL_BATCH_DEFAULT).  0 disables that path. */
+#define B2P_SMALL_BATCH_DEFAULT 4
+int b2p_set_small_batch_max(b2p_handle h, int max_samples);
 
 /* ---- denoiser: replaces TemporalMapUnet.forward (modeling/temporal.py:197-245) with the image feature hoisted --
  * x        [B, H, D]            noisy trajectories
