@@ -9,12 +9,13 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libb200plan.so")
+TRACE = os.environ.get("B2P_TRACE_BUILD") == "1"   # developer build with in-kernel stage clocks (scripts/tc_trace.py)
+LIB_PATH = os.path.join(PKG_DIR, "libb200plan_trace.so" if TRACE else "libb200plan.so")
 SOURCES = ["api.cu", "sched.cu", "embed.cu", "conv_ffma.cu", "conv_gemv.cu", "conv_tc.cu", "trajpred.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--expt-relaxed-constexpr",
-]
+] + (["-DB2P_TC_TRACE"] if TRACE else [])
 
 
 def _nvcc() -> str:
@@ -37,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     objs = []
     nvcc = _nvcc()
-    obj_dir = os.path.join(PKG_DIR, "build")
+    obj_dir = os.path.join(PKG_DIR, "build_trace" if TRACE else "build")
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
     for src in SOURCES:

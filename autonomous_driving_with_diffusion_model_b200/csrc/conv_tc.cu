@@ -41,6 +41,31 @@ constexpr int TC_UMMA_K = 16;
 constexpr int TC_THREADS = 512;
 constexpr int A_BYTES = TC_M * TC_K * 2;   // 16 KB
 
+#ifdef B2P_TC_TRACE   // developer tracing (scripts/tc_trace.py): per-stage clocks of CTA (0,0) of every launch
+__device__ unsigned long long tc_trace[8192 * 16];
+int tc_trace_launch = 0;
+#define TC_T(k)                                                                                       \
+  do {                                                                                                \
+    if (blockIdx.x == 0 && blockIdx.y == 0) {                                                         \
+      unsigned long long t_;                                                                          \
+      if ((k) < 7) t_ = clock64(); else asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));      \
+      tc_trace[((a.dbg >> 8) & 8191) * 16 + (k)] = t_;                                                \
+    }                                                                                                 \
+  } while (0)
+// slot 8: latest end over ALL CTAs of the launch, slot 9: dependency-wait return of CTA (0,0), both on the global timer
+#define TC_TG(k, all)                                                                                 \
+  do {                                                                                                \
+    if ((all) || (blockIdx.x == 0 && blockIdx.y == 0)) {                                              \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                         \
+      atomicMax(&tc_trace[((a.dbg >> 8) & 8191) * 16 + (k)], t_);                                     \
+    }                                                                                                 \
+  } while (0)
+#else
+#define TC_T(k)
+#define TC_TG(k, all)
+#endif
+
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -282,11 +307,11 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   constexpr int BT_BYTES = TN * TC_K * 2;           // one tap's weight tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  TcShared* sh = reinterpret_cast<TcShared*>(smem + SmemPlan<TN>::shared_off);
+  TcShared* sh = reinterpret_cast<TcShared*>(smem + (TN == 64 ? a.ring : a.ring + 4 * 1024));
 
   const int T = a.T;
   const int stage_bytes = NSPLIT * (A_BYTES + T * BT_BYTES);   // [A hi | A lo | W hi (T taps) | W lo (T taps)]
-  int stages = SmemPlan<TN>::ring / stage_bytes;
+  int stages = a.ring / stage_bytes;
   if (stages > 8) stages = 8;
   const int need_cols = (T + 1) * TN;
   const uint32_t tmem_cols = need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u)));
@@ -309,6 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   const int n_local = (a.dbg & 1) ? 0 : main_iters + res_iters;
 
   if (threadIdx.x == 0) {
+    TC_T(0);
     for (int s = 0; s < stages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], (CL > a.cluster_n) ? CL : 1); }
     mbar_init(&sh->tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -371,6 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     const int npre = n_local < stages ? n_local : stages;
     for (int j = 0; j < npre; ++j) issue(j, true, false);
     griddep_wait();
+    TC_T(1); TC_TG(9, false);
     for (int j = 0; j < npre; ++j) issue(j, false, true);
     for (int j = npre; j < n_local; ++j) {
       mbar_wait(&sh->empty[j % stages], ((j / stages) & 1) ^ 1);
@@ -387,6 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       const int s = it % stages;
       mbar_wait(&sh->full[s], (it / stages) & 1);
       tc_fence_after();
+      if (it == 0) TC_T(2);
       const uint32_t sa = smem_u32(smem + s * stage_bytes);
       const uint32_t sb = sa + NSPLIT * A_BYTES;
       const bool res_phase = it >= main_iters;
@@ -427,6 +455,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       if (CL > a.cluster_n) umma_commit_mc(&sh->empty[s], cmask); else umma_commit(&sh->empty[s]);   // the stage is free in a CTA once ALL cluster consumers released it
     }
     umma_commit(&sh->tmem_full);
+    TC_T(3);
   }
   __syncwarp();
   griddep_wait();                 // everything below may read the previous kernels' outputs (residuals)
@@ -444,7 +473,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     const int b = (int)(grow >> a.log2L), l = (int)(grow & (L - 1));
     EpiScratch es;
     es.xchg = reinterpret_cast<float (*)[TC_M][4]>(smem);
-    es.cx = reinterpret_cast<float (*)[4][TC_M]>(smem + SmemPlan<TN>::cx_off);
+    es.cx = reinterpret_cast<float (*)[4][TC_M]>(smem + a.ring);
     float (*headp)[4][8] = reinterpret_cast<float (*)[4][8]>(smem + EPI_XCHG_BYTES);
     const int gcol = n0 + col0;
     const int n_out = (a.dbg & 2) ? 0 : a.n_out;
@@ -489,6 +518,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     }
     mbar_wait_sleep(&sh->tmem_full, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) TC_T(4);
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + col0;
 
     for (int o = 0; o < n_out; ++o) {
@@ -540,6 +570,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
         }
       }
       const bool ok = row_ok && (a.out_ldiv == 1 || (l % a.out_ldiv) == 0);
+      if (threadIdx.x == 64 && o == 0) TC_T(5);
 #pragma unroll
       for (int c = 0; c < EC; ++c) v[c] += addv[c];
       if (has_res && n_local > 0) {   // residual 1x1 conv accumulated in the TMEM block after the tap blocks
@@ -584,6 +615,8 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       }
     }
     tc_fence_before();
+    if (threadIdx.x == 64) { TC_T(6); TC_T(7); }
+    if (threadIdx.x == 96) TC_TG(8, true);
   }
   if (mcast) cluster_sync_all();                   // no CTA may exit while peers can still signal its barriers / write its smem
   __syncthreads();
@@ -644,9 +677,17 @@ int tc_make_weight_map(CUtensorMap* m, const void* base, int taps, int Cout, int
 }
 
 template <int NSPLIT, int TN>
-static int launch_t(const TcMaps& maps, const TcArgs& a, dim3 grid, cudaStream_t s) {
-  constexpr int smem = SmemPlan<TN>::total;
-  B2P_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<NSPLIT, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+static int launch_t(const TcMaps& maps, const TcArgs& a_in, dim3 grid, cudaStream_t s) {
+  TcArgs a = a_in;
+  // B2P_TC_BIGRING=1 (experiment, off): give a narrow-tile layer that fits the chip with one CTA per SM the deep ring.
+  // Measured no faster — the main loop of those layers is paced by the MMAs' shared-memory operand reads, not by the
+  // bytes in flight — and slightly slower overall because the next layer's CTAs can no longer co-reside.
+  static int bigring = -1;
+  if (bigring < 0) { const char* e = getenv("B2P_TC_BIGRING"); bigring = e ? atoi(e) : 0; }
+  a.ring = SmemPlan<TN>::ring;
+  if (TN == 16 && bigring && (int)(grid.x * grid.y) <= 148) a.ring = SmemPlan<32>::ring;
+  const int smem = (TN == 64 ? a.ring : a.ring + 4 * 1024) + 1024 + (int)sizeof(TcShared);
+  B2P_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<NSPLIT, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan<TN == 16 ? 32 : TN>::total));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -700,6 +741,9 @@ int tc_configure(TcArgs& a) {
 int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStream_t s) {
   TcArgs a = a_in;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("B2P_TC_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
+#ifdef B2P_TC_TRACE
+  a.dbg |= (tc_trace_launch++ & 8191) << 8;
+#endif
   const int TN = a.tile_n;
   if (TN != 64 && TN != 32 && TN != 16) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.T < 1 || a.T > 5 || a.n_out < 1 || a.n_out > 2 || a.out_ldiv < 1) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
@@ -722,3 +766,10 @@ int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStrea
 }
 
 }  // namespace b2p
+
+#ifdef B2P_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int b2p_debug_tc_trace(unsigned long long* out, int* next_launch) {
+  *next_launch = b2p::tc_trace_launch;
+  return (int)cudaMemcpyFromSymbol(out, b2p::tc_trace, sizeof(unsigned long long) * 8192 * 16);
+}
+#endif

@@ -41,6 +41,7 @@ struct TcArgs {
   int tile_n;             // column-tile width: 64, 32 or 16 (tc_pick_tile_n)
   int cluster_n;          // set by launch_conv_tc: CTAs along N sharing one GroupNorm group
   int cluster_l;          // set by launch_conv_tc: cluster size along N (activation-tile multicast), multiple of cluster_n
+  int ring;               // set by launch_conv_tc: bytes of the operand ring in dynamic shared memory
   int dbg;                // developer bisect switch (B2P_TC_DBG): 1 = skip the TMA/MMA main loop, 2 = skip the epilogue math
 };
 
