@@ -975,13 +975,13 @@ static int enqueue_plan(b2p_handle h, const b2p_plan_config& pc, const GraphKey&
       const float* te_row = h->p_tetab + (size_t)i * h->dim;   // one time embedding shared by the batch (stride 0)
       if ((rc = run_unet(h, h->p_x, 0, h->p_feat, B, tp, 1, nullptr, h->p_action, nullptr, B, s, launches, h->p_itab,
                          h->p_ttab + (size_t)i * h->temb_total))) return rc;
-      if ((rc = launch_state_pred(h->tp, h->p_action, te_row, 0, h->p_mo, 1, B, h->H, h->D, s))) return rc;
-      ++*launches;
-      if (!inpaint && k.has_target) {
-        if ((rc = launch_classifier_guidance(h->tp, h->p_mo, te_row, 0, h->p_target, kc.guidance_grad_scale,
-                                             pc.classifier_scale, B, h->H, h->D, s))) return rc;
-        ++*launches;
+      if (!inpaint && k.has_target) {   // state predictor forward + guidance gradient + update in one launch
+        if ((rc = launch_classifier_guidance_from_action(h->tp, h->p_action, h->p_mo, te_row, 0, h->p_target, kc.guidance_grad_scale,
+                                                         pc.classifier_scale, B, h->H, h->D, s))) return rc;
+      } else {
+        if ((rc = launch_state_pred(h->tp, h->p_action, te_row, 0, h->p_mo, 1, B, h->H, h->D, s))) return rc;
       }
+      ++*launches;
     } else {
       if ((rc = run_unet(h, h->p_x, 0, h->p_feat, B, tp, 1, nullptr, h->p_mo, nullptr, B, s, launches, h->p_itab,
                          h->p_ttab + (size_t)i * h->temb_total))) return rc;

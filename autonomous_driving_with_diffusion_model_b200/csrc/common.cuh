@@ -137,6 +137,10 @@ int launch_state_pred_vjp(const TrajPredWeights& w, const float* action, const f
                           float* grad_action, int B, int H, int D, cudaStream_t s);
 int launch_classifier_guidance(const TrajPredWeights& w, float* model_output, const float* time_embed, int te_stride, const float* target,
                                float grad_scale, float scale, int B, int H, int D, cudaStream_t s);
+// same, but the model output is first assembled from the denoiser's action head: model_output = cat[cat[0, state_pred(action)], action]
+// (modeling/temporal.py:237-241) — the TrajPredict forward runs once for both the output and the guidance gradient
+int launch_classifier_guidance_from_action(const TrajPredWeights& w, const float* action, float* model_output, const float* time_embed,
+                                           int te_stride, const float* target, float grad_scale, float scale, int B, int H, int D, cudaStream_t s);
 
 // programmatic dependent launch (PDL): wait for the preceding kernel's results / let the following kernel start its prologue
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -13,7 +13,7 @@ constexpr int TP_H = 4;       // heads
 constexpr int TP_HD = 16;     // head dim
 constexpr int TP_FF = 256;
 constexpr int TP_MAXS = 16;   // tokens (horizon - 1 <= 16)
-constexpr int TP_NT = 256;
+constexpr int TP_NT = 512;
 
 struct LayerAct {            // saved for backward (floats, S = tokens)
   float xin[TP_MAXS * TP_D];
@@ -44,24 +44,42 @@ struct TpSmem {
   int idx;
 };
 
-// Y[s][n] = act( sum_k X[s][k] * Wt[k][n] + b[n] ), one thread per column n, all S rows in registers
-template <bool ACCUM>
+// Y[s][n] = sum_k X[s][k] * Wt[k][n] + b[n].  Work item = (column n, group of RPG rows); the TP_NT threads cover
+// N x G items (G = 8 row groups for N = 64, 2 for N = 192 / 256).  The weight column is read straight from L2 (the 400 KB
+// of weights do not fit beside the 173 KB of saved activations), PF loads in flight per thread; k runs in ascending
+// order with one accumulator per output, so the result does not depend on the thread mapping.
+template <bool ACCUM, int N>
 __device__ __forceinline__ void linear(const float* __restrict__ X, int ldx, const float* __restrict__ Wt, const float* __restrict__ b,
-                                       float* __restrict__ Y, int ldy, int S, int K, int N) {
-  for (int n = threadIdx.x; n < N; n += TP_NT) {
-    float acc[TP_MAXS];
-    float b0 = b ? __ldg(b + n) : 0.f;
+                                       float* __restrict__ Y, int ldy, int S, int K) {
+  constexpr int G = (TP_NT / N) >= 8 ? 8 : ((TP_NT / N) >= 2 ? 2 : 1);
+  constexpr int RPG = TP_MAXS / G;
+  constexpr int PF = 16;
+  const int tid = threadIdx.x;
+  if (tid >= N * G) return;
+  const int n = tid % N, row0 = (tid / N) * RPG;
+  float acc[RPG];
+  const float b0 = b ? __ldg(b + n) : 0.f;
 #pragma unroll
-    for (int s = 0; s < TP_MAXS; ++s) acc[s] = b0;
-    for (int k = 0; k < K; ++k) {
-      float w = __ldg(Wt + (size_t)k * N + n);
+  for (int r = 0; r < RPG; ++r) acc[r] = b0;
+  for (int k0 = 0; k0 < K; k0 += PF) {
+    float w[PF];
 #pragma unroll
-      for (int s = 0; s < TP_MAXS; ++s) acc[s] = fmaf(X[s * ldx + k], w, acc[s]);
+    for (int j = 0; j < PF; ++j) w[j] = __ldg(Wt + (size_t)(k0 + j) * N + n);
+#pragma unroll
+    for (int j4 = 0; j4 < PF; j4 += 4) {
+#pragma unroll
+      for (int r = 0; r < RPG; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(X + (row0 + r) * ldx + k0 + j4);
+        acc[r] = fmaf(x.x, w[j4], acc[r]);
+        acc[r] = fmaf(x.y, w[j4 + 1], acc[r]);
+        acc[r] = fmaf(x.z, w[j4 + 2], acc[r]);
+        acc[r] = fmaf(x.w, w[j4 + 3], acc[r]);
+      }
     }
-#pragma unroll
-    for (int s = 0; s < TP_MAXS; ++s)
-      if (s < S) { if (ACCUM) Y[s * ldy + n] += acc[s]; else Y[s * ldy + n] = acc[s]; }
   }
+#pragma unroll
+  for (int r = 0; r < RPG; ++r)
+    if (row0 + r < S) { if (ACCUM) Y[(row0 + r) * ldy + n] += acc[r]; else Y[(row0 + r) * ldy + n] = acc[r]; }
 }
 
 // y = LN(x) per row of 64; one warp per row.  Saves the normalised value and rstd when xh != null.
@@ -106,7 +124,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 __device__ void encoder_layer_fwd(TpSmem& sm, int l, const TrajPredWeights::Layer& w, float* xout, int S) {
   LayerAct& A = sm.L[l];
-  linear<false>(A.xin, TP_D, w.qkv_wt, w.qkv_b, A.qkv, 3 * TP_D, S, TP_D, 3 * TP_D);
+  linear<false, 3 * TP_D>(A.xin, TP_D, w.qkv_wt, w.qkv_b, A.qkv, 3 * TP_D, S, TP_D);
   __syncthreads();
   for (int i = threadIdx.x; i < TP_H * S * S; i += TP_NT) {   // scores
     int h = i / (S * S), r = (i / S) % S, c = i % S;
@@ -137,17 +155,17 @@ __device__ void encoder_layer_fwd(TpSmem& sm, int l, const TrajPredWeights::Laye
   }
   __syncthreads();
   // y1 = xin + att Wo^T + bo   (into x1 as scratch), then LN1
-  linear<false>(A.att, TP_D, w.out_wt, w.out_b, A.x1, TP_D, S, TP_D, TP_D);
+  linear<false, TP_D>(A.att, TP_D, w.out_wt, w.out_b, A.x1, TP_D, S, TP_D);
   __syncthreads();
   for (int i = threadIdx.x; i < S * TP_D; i += TP_NT) A.x1[i] += A.xin[i];
   __syncthreads();
   layer_norm(A.x1, w.n1_g, w.n1_b, A.x1, A.xh1, A.rstd1, S);
   __syncthreads();
-  linear<false>(A.x1, TP_D, w.l1_wt, w.l1_b, A.h1, TP_FF, S, TP_D, TP_FF);
+  linear<false, TP_FF>(A.x1, TP_D, w.l1_wt, w.l1_b, A.h1, TP_FF, S, TP_D);
   __syncthreads();
   for (int i = threadIdx.x; i < S * TP_FF; i += TP_NT) { float v = A.h1[i]; sm.ga[i] = v * sigmoidf_(v); }  // SiLU
   __syncthreads();
-  linear<false>(sm.ga, TP_FF, w.l2_wt, w.l2_b, xout, TP_D, S, TP_FF, TP_D);
+  linear<false, TP_D>(sm.ga, TP_FF, w.l2_wt, w.l2_b, xout, TP_D, S, TP_FF);
   __syncthreads();
   for (int i = threadIdx.x; i < S * TP_D; i += TP_NT) xout[i] += A.x1[i];
   __syncthreads();
@@ -160,18 +178,18 @@ __device__ void encoder_layer_bwd(TpSmem& sm, int l, const TrajPredWeights::Laye
   LayerAct& A = sm.L[l];
   layer_norm_bwd(sm.gx, A.xh2, A.rstd2, w.n2_g, S);            // gx = d(x1 + ff)
   __syncthreads();
-  linear<false>(sm.gx, TP_D, w.l2_w, nullptr, sm.ga, TP_FF, S, TP_D, TP_FF);   // d silu(h1) = gx W2   (W2 raw [64][256])
+  linear<false, TP_FF>(sm.gx, TP_D, w.l2_w, nullptr, sm.ga, TP_FF, S, TP_D);   // d silu(h1) = gx W2   (W2 raw [64][256])
   __syncthreads();
   for (int i = threadIdx.x; i < S * TP_FF; i += TP_NT) {
     float v = A.h1[i], sg = sigmoidf_(v);
     sm.ga[i] *= sg * (1.f + v * (1.f - sg));
   }
   __syncthreads();
-  linear<true>(sm.ga, TP_FF, w.l1_w, nullptr, sm.gx, TP_D, S, TP_FF, TP_D);    // gx += d_h1 W1  (raw [256][64])  => d x1
+  linear<true, TP_D>(sm.ga, TP_FF, w.l1_w, nullptr, sm.gx, TP_D, S, TP_FF);    // gx += d_h1 W1  (raw [256][64])  => d x1
   __syncthreads();
   layer_norm_bwd(sm.gx, A.xh1, A.rstd1, w.n1_g, S);            // gx = d(xin + o)
   __syncthreads();
-  linear<false>(sm.gx, TP_D, w.out_w, nullptr, sm.gb, TP_D, S, TP_D, TP_D);    // d att = gx Wo  (raw [64][64])
+  linear<false, TP_D>(sm.gx, TP_D, w.out_w, nullptr, sm.gb, TP_D, S, TP_D);    // d att = gx Wo  (raw [64][64])
   __syncthreads();
   for (int i = threadIdx.x; i < TP_H * S * S; i += TP_NT) {    // dP and dV
     int h = i / (S * S), r = (i / S) % S, c = i % S;
@@ -205,7 +223,7 @@ __device__ void encoder_layer_bwd(TpSmem& sm, int l, const TrajPredWeights::Laye
     sm.gqkv[r * 3 * TP_D + TP_D + col] = dk;
   }
   __syncthreads();
-  linear<true>(sm.gqkv, 3 * TP_D, w.qkv_w, nullptr, sm.gx, TP_D, S, 3 * TP_D, TP_D);  // gx += dqkv Wqkv (raw [192][64])
+  linear<true, TP_D>(sm.gqkv, 3 * TP_D, w.qkv_w, nullptr, sm.gx, TP_D, S, 3 * TP_D);  // gx += dqkv Wqkv (raw [192][64])
   __syncthreads();
 }
 
@@ -359,6 +377,16 @@ int launch_classifier_guidance(const TrajPredWeights& w, float* model_output, co
   B2P_CUDA_TRY(cudaFuncSetAttribute(trajpred_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TpSmem)));
   float scale_state = (float)((double)scale / 15.0);   // quirk 5 (control/guidance.py:56)
   trajpred_kernel<1><<<B, TP_NT, sizeof(TpSmem), s>>>(w, model_output, D, D - 3, time_embed, te_stride, model_output, 1, 1, target, grad_scale,
+                                                         scale_state, scale, H, D);
+  return (int)cudaGetLastError();
+}
+
+int launch_classifier_guidance_from_action(const TrajPredWeights& w, const float* action, float* model_output, const float* time_embed,
+                                           int te_stride, const float* target, float grad_scale, float scale, int B, int H, int D, cudaStream_t s) {
+  if (tp_check(H, D)) return B2P_ERR_INVALID_ARG;
+  B2P_CUDA_TRY(cudaFuncSetAttribute(trajpred_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TpSmem)));
+  float scale_state = (float)((double)scale / 15.0);   // quirk 5 (control/guidance.py:56)
+  trajpred_kernel<1><<<B, TP_NT, sizeof(TpSmem), s>>>(w, action, 3, 0, time_embed, te_stride, model_output, 1, 0, target, grad_scale,
                                                          scale_state, scale, H, D);
   return (int)cudaGetLastError();
 }

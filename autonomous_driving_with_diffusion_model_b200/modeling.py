@@ -235,6 +235,7 @@ class TemporalMapUnet(nn.Module):
         self._handles: Dict[int, C.c_void_p] = {}
         self._packed: Dict[int, tuple] = {}
         self._feat_cache: Optional[tuple] = None
+        self._tensor_list: Optional[list] = None
 
     # ---- C handle management --------------------------------------------------------------------------
     def _unet_items(self) -> Iterable[Tuple[str, torch.Tensor]]:
@@ -242,8 +243,24 @@ class TemporalMapUnet(nn.Module):
             if not k.startswith("perception."):
                 yield k, v
 
+    def _unet_tensors(self) -> list:
+        """The denoiser's tensors, listed once (walking state_dict() costs ~0.5 ms, more than a 2-step plan); the list is
+        dropped whenever the module is converted / moved / reloaded (_apply, load_state_dict).  In-place updates are seen
+        through the tensors' version counters."""
+        if self._tensor_list is None:
+            self._tensor_list = [v for _, v in self._unet_items()]
+        return self._tensor_list
+
     def _version_key(self) -> tuple:
-        return tuple((v.data_ptr(), v._version) for _, v in self._unet_items())
+        return tuple([(v.data_ptr(), v._version) for v in self._unet_tensors()])
+
+    def _apply(self, fn, *args, **kwargs):
+        self._tensor_list = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._tensor_list = None
+        return super().load_state_dict(*args, **kwargs)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -48,6 +48,7 @@ def parse():
                     help="bf16x3 = tcgen05 with bf16 hi/lo split operands (3 MMAs, fp32 accumulate): meets the fp32 parity bound (<=1e-3)")
     ap.add_argument("--no-other-precisions", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-modes", action="store_true", help="skip the per-mode report (SURVEY.md 8d configs 1, 3, 4) and the encoder figure")
     ap.add_argument("--cpu-sample-iters", type=int, default=5, help="denoising iterations per timed CPU sample")
     return ap.parse_args()
 
@@ -162,6 +163,101 @@ class ClockSampler:
         out.update(sm_mhz=statistics.median(sm), sm_max_mhz=float(rows[0][2]), reasons=sorted(reasons), samples=len(rows),
                    power_w_max=max(float(r[3]) for r in rows))
         return out
+
+
+def mode_report(P, W, dev, B: int, precision: str):
+    """throughput at B trajectories and batch-1 p50 plan latency for the other BASELINE.json configs, plus the
+    end-to-end figure with the image encoder in front of the loop (rank 0 only, a few plans each; report-only numbers)."""
+    cases = {
+        "config1_noguidance_ddpm100": ("NO_GUIDANCE", "guidance_ddpm", 100),
+        "config2_noguidance_ddim10": ("NO_GUIDANCE", "guidance_ddim", 10),
+        "config3_cfg_ddim10_scale7.5": ("FREE_GUIDANCE", "guidance_ddim", 10),
+        "config4a_classifier_ddim2_scale15": ("CLASSIFIER_GUIDANCE", "guidance_ddim", 2),
+        "config4b_classifier_inpainting_ddim2": ("CLASSIFIER_GUIDANCE", "inpainting_ddim", 2),
+    }
+    classes = {"guidance_ddim": P.GuidanceDDIMScheduler, "guidance_ddpm": P.GuidanceDDPMScheduler,
+               "inpainting_ddim": P.InpaintingDDIMScheduler, "inpainting_ddpm": P.InpaintingDDPMScheduler}
+    models, out = {}, {}
+    for name, (mode, kind, T) in cases.items():
+        cfg = P.load_cfg(TRAIN=dict(USE_COND=mode), EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION=precision),
+                         GUIDANCE=dict(USE_COND=mode, FREE_SCALE=7.5, CLASSIFIER_SCALE=15.0,
+                                       LOSS_LIST=[["TargetGuidance", []]] if mode == "CLASSIFIER_GUIDANCE" else None))
+        if mode not in models:
+            m = P.build_model(cfg)
+            m.load_state_dict(W.make_state_dict(mode, seed=0))
+            models[mode] = m.to(dev).eval()
+        sched = classes[kind](cfg=cfg, **P.scheduler_kwargs(cfg)) if kind.startswith("guidance") else classes[kind](**P.scheduler_kwargs(cfg))
+        planner = P.DiffusionPlanner(models[mode], sched, cfg)
+        inp = W.synth_inputs(B, T, seed=2)
+        needs_noise, inpaint = kind != "guidance_ddim", kind.startswith("inpainting")
+        dd = dict(target=inp["target"].to(dev) if mode != "NO_GUIDANCE" and not inpaint else None,
+                  noise=inp["noise"].to(dev) if needs_noise else None,
+                  target_traj=inp["target_traj"].to(dev) if inpaint else None, target_mask=inp["mask"].to(dev) if inpaint else None)
+        x, f = inp["x"].to(dev), inp["feat"].to(dev)
+        one = {k: (None if v is None else (v[:, :1] if k == "noise" else v[:1]).contiguous()) for k, v in dd.items()}
+        for _ in range(2):
+            planner.plan(x, f, **dd)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            planner.plan(x, f, **dd)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        for _ in range(3):
+            planner.plan(x[:1], f[:1], **one)
+        lat = []
+        for _ in range(20):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            planner.plan(x[:1], f[:1], **one)
+            torch.cuda.synchronize()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        out[name] = {"traj_per_s": B / (ms * 1e-3), "ms_per_plan": ms, "batch": B, "latency_b1_p50_ms": statistics.median(lat),
+                     "launches_per_plan": planner.last_launch_count()}
+    # end to end with the image encoder: one ResNet-34 pass per distinct scene (hoisted out of the loop), then the DDIM-100 loop
+    try:
+        mode, kind, T = "NO_GUIDANCE", "guidance_ddim", 100
+        cfg = P.load_cfg(EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION=precision))
+        m = P.build_model(cfg)
+        m.load_state_dict(W.make_state_dict(mode, seed=0, with_perception=True))
+        m = m.to(dev).eval()
+        planner = P.DiffusionPlanner(m, P.GuidanceDDIMScheduler(cfg=cfg, **P.scheduler_kwargs(cfg)), cfg)
+        for scenes in sorted({min(16, B), B}):
+            img = torch.randn(scenes, 3, 256, 900, device=dev, generator=torch.Generator(device=dev).manual_seed(2))   # ImageNet-normalised frames
+            x = W.synth_inputs(B, 0, seed=2)["x"].to(dev)
+            rep = B // scenes
+
+            def run():
+                with torch.no_grad():
+                    feat = m.perception(img)
+                return planner.plan(x, feat.repeat_interleave(rep, 0) if rep > 1 else feat)
+
+            def enc_only():
+                with torch.no_grad():
+                    return m.perception(img)
+
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            for _ in range(3):
+                enc_only()
+            e1.record()
+            for _ in range(3):
+                run()
+            e2.record()
+            torch.cuda.synchronize()
+            out[f"with_encoder_{scenes}_scenes"] = {"traj_per_s": B / (e1.elapsed_time(e2) / 3 * 1e-3), "ms_per_plan": e1.elapsed_time(e2) / 3,
+                                                    "encoder_ms": e0.elapsed_time(e1) / 3, "batch": B, "image": "3x256x900 fp32 per scene",
+                                                    "encoder": "ResNet-34 on torch/cuDNN (library code, SURVEY 8f rank 1), one pass per scene, hoisted"}
+            del img
+    except Exception as exc:  # report-only: never fail the bench line on the 'next' row
+        out["with_encoder_error"] = repr(exc)[:200]
+    return out
 
 
 def run_b200_arm(a, rank: int, world: int, local_rank: int):
@@ -295,6 +391,10 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
             others[prec] = B * world * 3 / (o0.elapsed_time(o1) * 1e-3)
         model.set_precision(a.precision)
 
+    modes = None
+    if rank == 0 and not a.no_modes:
+        modes = mode_report(P, W, dev, B, a.precision)
+
     # max over ranks
     tot = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -340,7 +440,7 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
                          "traffic": traffic, "peak_source": pk["source"] + ", bf16 sustained",
                          "kernel": "fused conv block (conv_ffma_kernel, CUDA cores)" if a.precision == "fp32" else "fused conv block (conv_tc_kernel: TMA + tcgen05.mma + TMEM epilogue)",
-                         "note": "B=256/GPU: each of the ~40 dependent layer launches per denoising iteration has only 4..32 row tiles (<=128 CTAs of 128x16) and lasts ~9 us of which the MMA is <1 us: the step is bound by the launch/L2-latency chain, not by the tensor pipe; see scripts/sweep.py for the large-batch regime",
+                         "note": "B=256/GPU: ~40 dependent layer launches per denoising iteration, each <=128 CTAs of 128 rows x 16 channels; per layer ~1.15 us dependency release + 0.8 us first-operand latency + a main loop of narrow (N<=80) MMAs paced by shared-memory operand reads + a TMEM-read-bound epilogue (profiles/r01_tc_stage_trace_b256.txt); see scripts/sweep.py for the large-batch regime",
                          "how": f"algorithmic FLOPs ({FLOPS_PER_EVAL[mode]} nominal 2*MAC x {rows} rows x {T} evaluations per plan) / CUDA-event time of the plan "
                                 f"(timed region, CUDA graph replay)",
                          "eager_eval": {"tflops": flops_eval / (eval_ms * 1e-3) / 1e12, "us": eval_ms * 1e3, "launches": eval_launches,
@@ -349,6 +449,8 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
             "precision": {"mode": a.precision, "parity_bound_max_abs": {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 0.3}[a.precision],
                           "other_modes_traj_per_s_rank0_x_world": others},
         }
+        if modes is not None:
+            line["modes"] = modes
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
