@@ -148,26 +148,110 @@ class _Tree(nn.Module):
 
 
 class ImageEncoder(_Tree):
-    """``model.perception``: ResNet-34 -> Linear(512, dim) in eval mode (BatchNorm uses running stats).  Runs on
-    torch/cuDNN (a 'next' row, hoisted out of the sampling loop — it is step-invariant).
-    Inference only: BatchNorm always uses its running statistics, whatever ``self.training`` says."""
+    """``model.perception``: ResNet-34 -> Linear(512, dim) in eval mode (modeling/resnet.py, modeling/temporal.py:83-84).
+    SURVEY.md 8f rank 1, a 'next' row: library kernels (cuDNN through torch), hoisted out of the sampling loop because
+    the feature is step-invariant.  Inference only — BatchNorm always uses its running statistics.
+
+    On CUDA without autograd the forward is restructured for per-tick latency (a closed-loop agent encodes a new camera
+    frame before every plan): BatchNorm folded into the convolution weights, channels-last, cuDNN fused
+    conv+bias(+residual)+ReLU, and the whole network replayed as one CUDA graph per input shape (36 launches instead of
+    ~110 eager ones).  TF32 follows ``torch.backends.cudnn.allow_tf32`` as for any torch convolution."""
 
     def _bn(self, x, m):
         return F.batch_norm(x, m.running_mean, m.running_var, m.weight, m.bias, False, 0.0, 1e-5)
 
-    def forward(self, img: torch.Tensor) -> torch.Tensor:
-        x = F.relu(self._bn(F.conv2d(img, self.conv1.weight, None, 2, 3), self.bn1))
-        x = F.max_pool2d(x, 3, 2, 1)
+    def _blocks(self):
         for stage in (self.layer1, self.layer2, self.layer3, self.layer4):
             for blk in stage._modules.values():
-                stride = 2 if "downsample" in blk._modules else 1   # ResNet-34: a projection shortcut <=> a stride-2 block
-                y = F.relu(self._bn(F.conv2d(x, blk.conv1.weight, None, stride, 1), blk.bn1))
-                y = self._bn(F.conv2d(y, blk.conv2.weight, None, 1, 1), blk.bn2)
-                if "downsample" in blk._modules:
-                    ds = blk.downsample._modules
-                    x = self._bn(F.conv2d(x, ds["0"].weight, None, stride, 0), ds["1"])
-                x = F.relu(y + x)
+                yield blk, (2 if "downsample" in blk._modules else 1)   # ResNet-34: a projection shortcut <=> a stride-2 block
+
+    def _forward_plain(self, img: torch.Tensor) -> torch.Tensor:
+        x = F.relu(self._bn(F.conv2d(img, self.conv1.weight, None, 2, 3), self.bn1))
+        x = F.max_pool2d(x, 3, 2, 1)
+        for blk, stride in self._blocks():
+            y = F.relu(self._bn(F.conv2d(x, blk.conv1.weight, None, stride, 1), blk.bn1))
+            y = self._bn(F.conv2d(y, blk.conv2.weight, None, 1, 1), blk.bn2)
+            if "downsample" in blk._modules:
+                ds = blk.downsample._modules
+                x = self._bn(F.conv2d(x, ds["0"].weight, None, stride, 0), ds["1"])
+            x = F.relu(y + x)
         return F.linear(F.adaptive_avg_pool2d(x, 1).flatten(1), self.fc.weight, self.fc.bias)
+
+    # ---- folded / fused / graphed inference path --------------------------------------------------------
+    @staticmethod
+    def _fold(conv_w, bn):
+        scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + 1e-5)
+        w = (conv_w.detach().float() * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+        return w, (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
+
+    def _tensors(self):
+        if getattr(self, "_tlist", None) is None:
+            object.__setattr__(self, "_tlist", list(self.state_dict(keep_vars=True).values()))
+        return self._tlist
+
+    def _apply(self, fn, *args, **kwargs):
+        object.__setattr__(self, "_tlist", None)
+        return super()._apply(fn, *args, **kwargs)
+
+    def _folded(self):
+        key = tuple([(t.data_ptr(), t._version) for t in self._tensors()])
+        cache = getattr(self, "_fold_cache", None)
+        if cache is None or cache[0] != key:
+            stem = self._fold(self.conv1.weight, self.bn1)
+            blocks = []
+            for blk, stride in self._blocks():
+                ds = None
+                if "downsample" in blk._modules:
+                    d = blk.downsample._modules
+                    ds = self._fold(d["0"].weight, d["1"])
+                blocks.append((stride, self._fold(blk.conv1.weight, blk.bn1), self._fold(blk.conv2.weight, blk.bn2), ds))
+            cache = (key, stem, blocks)
+            object.__setattr__(self, "_fold_cache", cache)
+            object.__setattr__(self, "_graphs", {})
+        return cache
+
+    def _forward_fused(self, img: torch.Tensor) -> torch.Tensor:
+        _, (w, b), blocks = self._folded()
+        one, zero = [1, 1], [0, 0]
+        x = torch.cudnn_convolution_relu(img.contiguous(memory_format=torch.channels_last), w, b, [2, 2], [3, 3], one, 1)
+        x = F.max_pool2d(x, 3, 2, 1)
+        for stride, (w1, b1), (w2, b2), ds in blocks:
+            y = torch.cudnn_convolution_relu(x, w1, b1, [stride, stride], one, one, 1)
+            if ds is not None:
+                x = F.conv2d(x, ds[0], ds[1], stride, 0)
+            x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, one, one, one, 1)
+        return F.linear(x.mean((2, 3)), self.fc.weight, self.fc.bias)
+
+    def _forward_graphed(self, img: torch.Tensor) -> torch.Tensor:
+        self._folded()   # (re)builds the folded weights and drops stale graphs when a parameter changed
+        key = (tuple(img.shape), img.device, torch.backends.cudnn.allow_tf32)
+        g = self._graphs.get(key)
+        if g is None:
+            static_in = torch.empty_like(img, memory_format=torch.channels_last)
+            static_in.copy_(img)
+            side = torch.cuda.Stream(device=img.device)
+            side.wait_stream(torch.cuda.current_stream(img.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):      # cuDNN algorithm selection and workspace allocation happen outside the capture
+                    self._forward_fused(static_in)
+            torch.cuda.current_stream(img.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward_fused(static_in)
+            g = (graph, static_in, static_out)
+            self._graphs[key] = g
+        graph, static_in, static_out = g
+        static_in.copy_(img)
+        graph.replay()
+        return static_out.clone()
+
+    def forward(self, img: torch.Tensor) -> torch.Tensor:
+        if img.is_cuda and img.dtype == torch.float32 and not (torch.is_grad_enabled() and img.requires_grad) and hasattr(torch, "cudnn_convolution_add_relu"):
+            with torch.no_grad():
+                if torch.cuda.is_current_stream_capturing():
+                    return self._forward_fused(img)
+                return self._forward_graphed(img)
+        return self._forward_plain(img)
 
 
 class _StatePredFn(torch.autograd.Function):
@@ -326,12 +410,12 @@ class TemporalMapUnet(nn.Module):
         (modeling/temporal.py:203); in eval mode the feature is step-invariant, so it is computed once per image tensor."""
         if img.dim() == 2:
             return img
-        key = (img.data_ptr(), img._version, tuple(img.shape), img.device)
+        key = (img.data_ptr(), img._version, tuple(img.shape), tuple(img.stride()), img.device)
         if self._feat_cache is not None and self._feat_cache[0] == key:
             return self._feat_cache[1]
         with torch.no_grad():
             feat = self.perception(img).float().contiguous()
-        self._feat_cache = (key, feat)
+        self._feat_cache = (key, feat, img)   # the image is kept alive: its address cannot be recycled for another frame while cached
         return feat
 
     # ---- reference surface ----------------------------------------------------------------------------

@@ -96,7 +96,8 @@ class DiffusionPlanner:
 
     def generate_traj(self, image: torch.Tensor, target: Optional[torch.Tensor] = None) -> torch.Tensor:
         """interact.py:115-168: one trajectory from the agent's fixed initial noise."""
-        self.model.eval()
+        if self.model.training:     # Module.eval() walks ~350 submodules (0.5 ms): only when it changes something
+            self.model.eval()
         dev = next(self.model.parameters()).device
         if self.init_trajs is None:
             self.init_trajs = torch.randn((1, self.model.horizon, self.model.transition_dim), device=dev)

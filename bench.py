@@ -255,6 +255,29 @@ def mode_report(P, W, dev, B: int, precision: str):
                                                     "encoder_ms": e0.elapsed_time(e1) / 3, "batch": B, "image": "3x256x900 fp32 per scene",
                                                     "encoder": "ResNet-34 on torch/cuDNN (library code, SURVEY 8f rank 1), one pass per scene, hoisted"}
             del img
+        # closed-loop tick at batch 1: a NEW camera frame every tick (interact.py:170-176 -> generate_traj), encoder included
+        frames = [torch.randn(1, 3, 256, 900, device=dev) for _ in range(4)]
+        for name, (mode, kind, T) in (("tick_noguidance_ddim100", ("NO_GUIDANCE", "guidance_ddim", 100)), ("tick_cfg_ddim10", cases["config3_cfg_ddim10_scale7.5"]),
+                                      ("tick_classifier_ddim2", cases["config4a_classifier_ddim2_scale15"])):
+            cfg = P.load_cfg(TRAIN=dict(USE_COND=mode), EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION=precision),
+                             GUIDANCE=dict(USE_COND=mode, FREE_SCALE=7.5, CLASSIFIER_SCALE=15.0,
+                                           LOSS_LIST=[["TargetGuidance", []]] if mode == "CLASSIFIER_GUIDANCE" else None))
+            mm = P.build_model(cfg)
+            mm.load_state_dict(W.make_state_dict(mode, seed=0, with_perception=True))
+            mm = mm.to(dev).eval()
+            agent = P.DiffusionPlanner(mm, P.GuidanceDDIMScheduler(cfg=cfg, **P.scheduler_kwargs(cfg)), cfg)
+            tg = torch.tensor([[0.1, 0.3]], device=dev) if mode != "NO_GUIDANCE" else None
+            for i in range(4):
+                agent.generate_traj(frames[i % 4], tg)
+            lat = []
+            for i in range(20):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                agent.generate_traj(frames[i % 4], tg)
+                torch.cuda.synchronize()
+                lat.append((time.perf_counter() - t0) * 1e3)
+            out[name] = {"closed_loop_tick_p50_ms": statistics.median(lat), "batch": 1, "T": T,
+                         "includes": "ResNet-34 encoder on the new frame (cuDNN, folded BN, one CUDA graph) + the whole sampling loop + host call"}
     except Exception as exc:  # report-only: never fail the bench line on the 'next' row
         out["with_encoder_error"] = repr(exc)[:200]
     return out

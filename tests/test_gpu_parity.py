@@ -208,6 +208,48 @@ def test_image_encoder_vs_reference_golden_and_hoisting(golden_dir):
     assert model.encode(img) is model.encode(img)      # one-entry cache: step-invariant feature is not recomputed
 
 
+def test_image_encoder_fused_graph_path_matches_plain_layers():
+    """Inference path of the encoder (BatchNorm folded, channels-last, cuDNN fused conv+bias(+residual)+ReLU, one CUDA graph
+    per input shape) against the layer-by-layer formulation of modeling/resnet.py, TF32 off; refolds when a weight changes."""
+    model, _ = get_model("NO_GUIDANCE")
+    enc = model.perception
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for S in (1, 3):
+            img = W.synth_image(S, seed=40 + S).to(DEV)
+            with torch.no_grad():
+                plain = enc._forward_plain(img)
+                fused = enc(img)
+                again = enc(img)                           # graph replay
+            assert torch.equal(fused, again)
+            assert float((fused - plain).abs().max()) <= 2e-5 * float(plain.abs().max()), S
+        w = enc.layer3._modules["0"].conv1.weight
+        with torch.no_grad():
+            w.mul_(1.25)                                   # in-place update: version counter bumps, folded weights and graphs are rebuilt
+            changed, plain2 = enc(img), enc._forward_plain(img)
+            w.div_(1.25)
+        assert float((changed - fused).abs().max()) > 1e-4 * float(plain.abs().max())
+        assert float((changed - plain2).abs().max()) <= 2e-5 * float(plain2.abs().max())
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_feature_cache_is_not_fooled_by_a_recycled_frame_address():
+    """A closed-loop agent allocates a new frame every tick; the caching allocator hands out the same address again.  The
+    one-entry feature cache keeps the cached frame alive, so a new frame can never alias it."""
+    model, _ = get_model("NO_GUIDANCE")
+    feats = []
+    for i in range(3):
+        frame = torch.randn(1, 3, 256, 900, device=DEV, generator=torch.Generator(device=DEV).manual_seed(100 + i))
+        f = model.encode(frame)
+        with torch.no_grad():
+            assert torch.equal(f, model.perception(frame))
+        feats.append(f.clone())
+        del frame
+    assert not torch.equal(feats[0], feats[1]) and not torch.equal(feats[1], feats[2])
+
+
 # ------------------------------------------------------------------------------------------------------------
 # TrajPredict / classifier guidance
 # ------------------------------------------------------------------------------------------------------------
