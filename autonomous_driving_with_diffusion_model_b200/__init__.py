@@ -7,7 +7,11 @@ from .planner import DiffusionPlanner
 from .scheduler import (SCHEDULER_FUNC, GuidanceDDIMScheduler, GuidanceDDPMScheduler, InpaintingDDIMScheduler,
                         InpaintingDDPMScheduler)
 from .sharding import shard, shard_bounds
+from .checkpoint import copy_parameters, load_checkpoint
+from .control import Controller, PIDController, post_process_control, post_process_control_batch
+from .inputs import preprocess_frames, process_next_waypoint
 
 __all__ = ["GuidanceType", "load_cfg", "scheduler_kwargs", "GuidanceLoss", "TargetGuidance", "TemporalMapUnet", "build_model",
            "DiffusionPlanner", "SCHEDULER_FUNC", "GuidanceDDIMScheduler", "GuidanceDDPMScheduler", "InpaintingDDIMScheduler",
-           "InpaintingDDPMScheduler", "shard", "shard_bounds"]
+           "InpaintingDDPMScheduler", "shard", "shard_bounds", "copy_parameters", "load_checkpoint", "Controller", "PIDController",
+           "post_process_control", "post_process_control_batch", "preprocess_frames", "process_next_waypoint"]

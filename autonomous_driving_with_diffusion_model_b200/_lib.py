@@ -40,7 +40,7 @@ class PlanConfig(C.Structure):
                 ("classifier_scale", C.c_float), ("magic_num", C.c_float), ("postprocess", C.c_int32), ("use_graph", C.c_int32)]
 
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 SCHED_KINDS = {"guidance_ddim": 0, "guidance_ddpm": 1, "inpainting_ddim": 2, "inpainting_ddpm": 3}
 PRED_TYPES = {"epsilon": 0, "sample": 1, "v_prediction": 2}
 BETA_SCHEDULES = {"squaredcos_cap_v2": 0, "linear": 1, "scaled_linear": 2}
@@ -62,6 +62,7 @@ SYMBOLS = {
     "b2p_finalize_weights": (C.c_int, [_VP]),
     "b2p_set_precision": (C.c_int, [_VP, C.c_int]),
     "b2p_set_small_batch_max": (C.c_int, [_VP, C.c_int]),
+    "b2p_preprocess_frames": (C.c_int, [_VP, _VP, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), _VP]),
     "b2p_unet_forward": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "b2p_state_pred": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "b2p_state_pred_vjp": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),

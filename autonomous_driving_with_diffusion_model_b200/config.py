@@ -16,6 +16,8 @@ _DEFAULTS = {
                   NOISE_SCHEDULER=dict(BETA_START=1e-4, BETA_END=0.02, TYPE="squaredcos_cap_v2", PRED_TYPE="sample")),
     "GUIDANCE": dict(USE_COND="NO_GUIDANCE", LOSS_LIST=None, STEP=1, CLASSIFIER_SCALE=0.1, FREE_SCALE=1.0),
     "EVAL": dict(BATCH_SIZE=4, ETA=0, CHECKPOINT=None, SCHEDULER="ddim", SAMPLE_STEPS=100),
+    "PID": dict(TURN_KP=1, TURN_KI=0.5, TURN_KD=1.0, TURN_N=40, SPEED_KP=5, SPEED_KI=0.5, SPEED_KD=1.0, SPEED_N=40),   # config.py:67-76
+    "CONTROL": dict(AIM_DIST=4.0, ANGLE_THRESH=0.3, DIST_THRESH=10, BRAKE_SPEED=0.4, BRAKE_RATIO=1.1, CLIP_DELTA=0.25, MAX_THROTTLE=9),   # config.py:79-86
     "B200": dict(PRECISION="fp32", SMALL_BATCH_MAX=4),
 }
 

@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define B2P_ABI_VERSION 4
+#define B2P_ABI_VERSION 5
 
 typedef enum {
   B2P_OK = 0,
@@ -123,6 +123,13 @@ int b2p_set_precision(b2p_handle h, int precision);
  * carla_agent; default B2P_SMALL_BATCH_DEFAULT).  0 disables that path. */
 #define B2P_SMALL_BATCH_DEFAULT 4
 int b2p_set_small_batch_max(b2p_handle h, int max_samples);
+
+/* ---- camera frame -> encoder input: replaces T.ToTensor() + T.Normalize(mean, std) (interact.py:72-77, 170-172) for
+ * uint8 frames already on the device.  frames [N,H,W,3] uint8 (4-byte aligned), out [N,H,W,3] fp32 (16-byte aligned; the
+ * channels-last memory of the logical [N,3,H,W] tensor), n_pixels = N*H*W.  out = ((u8 / 255) - mean[c]) / std[c],
+ * bit-identical to the host transform.  No handle: the transform has no state. */
+int b2p_preprocess_frames(const uint8_t* frames_nhwc, float* out_nhwc, int64_t n_pixels, const float mean[3], const float std_[3],
+                          void* stream);
 
 /* ---- denoiser: replaces TemporalMapUnet.forward (modeling/temporal.py:197-245) with the image feature hoisted --
  * x        [B, H, D]            noisy trajectories

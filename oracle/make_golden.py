@@ -212,6 +212,40 @@ def run_encoder():
     print(f"resnet34 feature oracle-vs-reference {d:.3e}  |feat|max {float(f_ref.abs().max()):.3f}")
 
 
+def run_control():
+    """The reference's own Controller / PIDController (control/controller.py, control/pid.py) over 60 ticks of one vehicle,
+    and interact.py:218-229 post_process_control restated on the same triples (interact.py cannot be imported: it needs carla)."""
+    RL.load()                                                    # puts /root/reference on sys.path
+    from control.controller import Controller as RefController   # the reference's class
+    from types import SimpleNamespace as NS
+
+    cfg = NS(PID=NS(TURN_KP=1, TURN_KI=0.5, TURN_KD=1.0, TURN_N=40, SPEED_KP=5, SPEED_KI=0.5, SPEED_KD=1.0, SPEED_N=40),
+             CONTROL=NS(AIM_DIST=4.0, ANGLE_THRESH=0.3, DIST_THRESH=10, BRAKE_SPEED=0.4, BRAKE_RATIO=1.1, CLIP_DELTA=0.25, MAX_THROTTLE=9))
+    ctl = RefController(cfg)
+    ticks = 60
+    way = (W.hash_normal("ctl/way", (ticks, 4, 2)) * 0.6 + torch.tensor([0.0, 1.0]) * torch.arange(1, 5).view(1, 4, 1) * 1.5).to(torch.float32)
+    vel = torch.from_numpy((W.hash_uniform("ctl/vel", ticks) * 6.0).astype(np.float32).reshape(ticks, 1))
+    tgt = (W.hash_normal("ctl/tgt", (ticks, 2)) * 3.0 + torch.tensor([0.0, 6.0])).to(torch.float32)
+    out = np.zeros((ticks, 3), dtype=np.float64)
+    for i in range(ticks):
+        th, st, br = ctl.control_pid(way[i], vel[i], tgt[i])
+        out[i] = [float(th), float(st), float(br)]
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "control_pid.npz"), waypoints=way.numpy(), velocity=vel.numpy(), target=tgt.numpy(), controls=out)
+    print(f"control: {ticks} ticks, brake fraction {out[:, 2].mean():.2f}, |steer| max {np.abs(out[:, 1]).max():.3f}")
+
+
+def run_preprocess():
+    """torchvision's ToTensor + Normalize exactly as interact.py:72-77 composes them, on a small uint8 frame."""
+    import torchvision.transforms as T
+
+    tf = T.Compose([T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    frame = np.clip(np.floor(W.hash_uniform("pre/frame", 37 * 53 * 3) * 256.0), 0, 255).astype(np.uint8).reshape(37, 53, 3)   # odd sizes: tail pixels
+    frame[0, 0] = [0, 255, 128]
+    out = tf(frame)                                               # [3,H,W] fp32
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "preprocess_frame.npz"), frame=frame, out=out.numpy())
+    print("preprocess golden written", out.shape, float(out.min()), float(out.max()))
+
+
 def write_spec():
     spec = {}
     for mode in W.MODES:
@@ -238,6 +272,8 @@ def main():
     for name in PLAN_CASES:
         worst = max(worst, run_plan_case(name, models, sds))
     run_encoder()
+    run_control()
+    run_preprocess()
     print("worst plan oracle-vs-reference:", worst)
 
 
