@@ -37,10 +37,30 @@ int gv_trace_launch = 0;
 
 __device__ __forceinline__ void gv_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void gv_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void gv_st_cluster(const float* local, uint32_t cta, float x) {
-  uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(x) : "memory");
+// 8-byte asynchronous store into CTA `cta` of the cluster that also signals the bytes on THAT CTA's mbarrier: the
+// receiver needs no cluster-wide barrier, only a wait on its own mbarrier
+__device__ __forceinline__ void gv_st_async(const void* local_dst, const void* local_bar, uint32_t cta, float a, float b) {
+  uint32_t ld = (uint32_t)__cvta_generic_to_shared(local_dst), lb = (uint32_t)__cvta_generic_to_shared(local_bar), rd, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rd) : "r"(ld), "r"(cta));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"(cta));
+  const unsigned long long v = ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(a);
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(rd), "l"(v), "r"(rb) : "memory");
+}
+__device__ __forceinline__ void gv_bar_init_expect(unsigned long long* bar, uint32_t bytes) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gv_bar_wait(unsigned long long* bar) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "GVW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+      "@p bra GVD_%=;\n\t"
+      "bra GVW_%=;\n\t"
+      "GVD_%=:\n\t}" ::"r"(a) : "memory");
 }
 __device__ __forceinline__ void gv_cp16(float* dst, const float* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
@@ -54,7 +74,8 @@ struct GvStatic {
   int src[5][GV_MAXL];           // offset (floats) into X of the input row feeding (tap, output row); zero row when padding
   int idsrc[1][GV_MAXL];         // same for the residual 1x1 conv (row r feeds row r)
   float mean, m2;
-  float cx[2][8];                // cluster exchange: [mean|M2][source CTA]
+  float2 cx[8];                  // cluster exchange: (mean, M2) of every CTA of the cluster, written by the peers
+  unsigned long long bar;        // mbarrier: counts the bytes of cx that have arrived
 };
 
 // x / d for a runtime d that is almost always a power of two
@@ -158,8 +179,11 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
   __shared__ GvStatic st;
   pdl_launch_dependents();       // let the following layers start streaming their weights right away
   GV_T(6); GV_T(0);
-  if (cls > 1) gv_cluster_arrive();   // phase 1: "every CTA of the cluster is running" (needed before remote smem stores)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (cls > 1) {
+    if (tid == 0) gv_bar_init_expect(&st.bar, 8u * cls);   // this CTA will receive one (mean, M2) pair from every CTA of its cluster
+    gv_cluster_arrive();         // "my mbarrier is initialised and I am running": peers wait for this before they send
+  }
   const int col0 = blockIdx.x * NC, b = blockIdx.y;
   const int Cin = a.C0 + a.C1, RCin = a.RC0 + a.RC1;
   const int ntaps = a.jmax - a.jmin + 1;
@@ -271,25 +295,21 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
 #pragma unroll
       for (int k = 16; k > 0; k >>= 1) q += __shfl_xor_sync(0xffffffffu, q, k);
       if (cls > 1) {
-        gv_cluster_wait();                                  // phase 1 complete: all peers are running
-        if (lane < cls) {                                   // publish this part's (mean, M2) to every CTA of the cluster
-          const int crank = blockIdx.x % cls;
-          gv_st_cluster(&st.cx[0][crank], (uint32_t)lane, mean);
-          gv_st_cluster(&st.cx[1][crank], (uint32_t)lane, q);
-        }
+        gv_cluster_wait();                                  // every peer is running and has initialised its mbarrier
+        if (lane < cls)                                     // publish this part's (mean, M2) to every CTA of the cluster
+          gv_st_async(&st.cx[blockIdx.x % cls], &st.bar, (uint32_t)lane, mean, q);
       } else if (lane == 0) {
         st.mean = mean; st.m2 = q;
       }
     } else if (cls > 1) {
-      gv_cluster_wait();
+      gv_cluster_wait();                                    // (every thread that arrived also waits once)
     }
     if (cls > 1) {
-      gv_cluster_arrive();
-      gv_cluster_wait();                                    // phase 2: every part has arrived
+      gv_bar_wait(&st.bar);                                 // all cls parts have landed in this CTA's cx (no CTA exits before that)
       float ms = 0.f;                                       // merge equal-sized parts in a fixed order (parallel-variance formula)
-      for (int p = 0; p < cls; ++p) ms += st.cx[0][p];
+      for (int p = 0; p < cls; ++p) ms += st.cx[p].x;
       mu = ms / (float)cls;
-      for (int p = 0; p < cls; ++p) { const float d = st.cx[0][p] - mu; m2 += st.cx[1][p] + (float)ne * d * d; }
+      for (int p = 0; p < cls; ++p) { const float d = st.cx[p].x - mu; m2 += st.cx[p].y + (float)ne * d * d; }
     } else {
       __syncthreads();
       mu = st.mean; m2 = st.m2;

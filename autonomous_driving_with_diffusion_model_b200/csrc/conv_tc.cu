@@ -204,10 +204,20 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t local_saddr, uint32_t ct
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(x) : "memory");
 }
 
+// 8-byte asynchronous store into CTA `cta` of the cluster that also signals the bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_cluster_f32x2(uint32_t local_dst, uint32_t local_bar, uint32_t cta, float a, float b) {
+  uint32_t rd, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rd) : "r"(local_dst), "r"(cta));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(local_bar), "r"(cta));
+  const unsigned long long v = ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(a);
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(rd), "l"(v), "r"(rb) : "memory");
+}
+
 struct __align__(16) TcShared {
   uint64_t full[8];
   uint64_t empty[8];
   uint64_t tmem_full;
+  uint64_t gn_bar;                                 // counts the GroupNorm partials arriving from the cluster peers
   uint32_t tmem_base;
   uint32_t pad;
   float bias[64], gamma[64], beta[64], resb[64];   // per-tile epilogue vectors (first TN entries used)
@@ -229,7 +239,8 @@ template <int TN> struct SmemPlan {
 constexpr int EPI_XCHG_BYTES = 2 * TC_M * 4 * 4;
 struct EpiScratch {
   float (*xchg)[TC_M][4];   // [pass][row][slice]
-  float (*cx)[4][TC_M];     // [pass][source CTA][row]
+  float2 (*cx)[TC_M];       // [source CTA][row] = (mean, M2), written by the peers (st.async)
+  uint64_t* gn_bar;
 };
 
 // GroupNorm(8) + Mish for the EC channels a thread holds.  A group is CG consecutive channels x the L rows (adjacent
@@ -278,18 +289,21 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
     mean[0] = mu; m2[0] = qs;
   }
   if (CN > 1) {                                      // merge the CTAs of the cluster sub-group
+    // every CTA pushes its per-row (mean, M2) into all CN CTAs with asynchronous stores that signal the receiver's
+    // mbarrier; nobody waits for a cluster-wide barrier, each CTA only waits until ITS CN x 128 pairs have landed
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers are running and their mbarrier is initialised (arrive: prologue)
     if ((slice & (SL - 1)) == 0) {
-      const uint32_t la0 = smem_u32(&es.cx[0][crank][row]), la1 = smem_u32(&es.cx[1][crank][row]);
+      const uint32_t dst = smem_u32(&es.cx[crank][row]), bar = smem_u32(es.gn_bar);
 #pragma unroll
-      for (int c = 0; c < CN; ++c) { st_cluster_f32(la0, (uint32_t)(cbase + c), mean[0]); st_cluster_f32(la1, (uint32_t)(cbase + c), m2[0]); }
+      for (int c = 0; c < CN; ++c) st_async_cluster_f32x2(dst, bar, (uint32_t)(cbase + c), mean[0], m2[0]);
     }
-    cluster_sync_all();
+    mbar_wait(es.gn_bar, 0);
     float ms = 0.f, qs = 0.f;
 #pragma unroll
-    for (int c = 0; c < CN; ++c) ms += es.cx[0][c][row];
+    for (int c = 0; c < CN; ++c) ms += es.cx[c][row].x;
     const float mu = ms * (1.0f / CN);
 #pragma unroll
-    for (int c = 0; c < CN; ++c) { float d = es.cx[0][c][row] - mu; qs += es.cx[1][c][row] + (float)(WC * L) * d * d; }
+    for (int c = 0; c < CN; ++c) { float d = es.cx[c][row].x - mu; qs += es.cx[c][row].y + (float)(WC * L) * d * d; }
     mean[0] = mu; m2[0] = qs;
   }
   const float inv_n = 1.0f / (float)(CG * L);
@@ -337,7 +351,9 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     TC_T(0);
     for (int s = 0; s < stages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], (CL > a.cluster_n) ? CL : 1); }
     mbar_init(&sh->tmem_full, 1);
+    mbar_init(&sh->gn_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (a.cluster_n > 1 && a.gn_gamma) mbar_expect_tx(&sh->gn_bar, (uint32_t)a.cluster_n * TC_M * 8u);   // one (mean, M2) pair per row from every CTA of the sub-group
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
@@ -354,6 +370,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (a.cluster_n > 1 && a.gn_gamma) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // "my GroupNorm mbarrier is ready" (waited for in group_norm_mish)
   const bool mcast = CL > a.cluster_n;             // activation multicast active (off by default: measured slower)
   if (mcast) cluster_sync_all();                   // peers' barriers are initialised before anyone multicasts / commits into them
   const uint32_t tmem_base = sh->tmem_base;
@@ -473,7 +490,8 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     const int b = (int)(grow >> a.log2L), l = (int)(grow & (L - 1));
     EpiScratch es;
     es.xchg = reinterpret_cast<float (*)[TC_M][4]>(smem);
-    es.cx = reinterpret_cast<float (*)[4][TC_M]>(smem + a.ring);
+    es.cx = reinterpret_cast<float2 (*)[TC_M]>(smem + a.ring);
+    es.gn_bar = &sh->gn_bar;
     float (*headp)[4][8] = reinterpret_cast<float (*)[4][8]>(smem + EPI_XCHG_BYTES);
     const int gcol = n0 + col0;
     const int n_out = (a.dbg & 2) ? 0 : a.n_out;
@@ -751,6 +769,7 @@ int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStrea
   if (a.Cout % TN || a.C[0] % TC_K || a.C[1] % TC_K || a.RC[0] % TC_K || a.RC[1] % TC_K || a.nrows <= 0) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.Lrows > 32 || (a.Lrows & (a.Lrows - 1)) || TC_M % a.Lrows) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.headW && (a.Cout != 64 || TN != 64 || a.head_dim > 8)) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
+  if (a.n_out == 2 && a.gn_gamma) { fprintf(stderr, "launch_conv_tc: GroupNorm with two outputs per row is not supported (single-use exchange barrier)\n"); return B2P_ERR_INVALID_ARG; }
   if (a.n_out == 2 && (a.RC[0] || a.RC[1])) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.cluster_n < 1 || a.cluster_l < a.cluster_n || a.cluster_l % a.cluster_n) { fprintf(stderr, "launch_conv_tc: tc_configure() was not applied\n"); return B2P_ERR_INVALID_ARG; }
   if ((a.Cout / TN) % a.cluster_l) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
