@@ -239,7 +239,11 @@ class ImageEncoder(_Tree):
             with torch.cuda.graph(graph):
                 static_out = self._forward_fused(static_in)
             g = (graph, static_in, static_out)
+            while len(self._graphs) >= 4:       # a graph pins its activation pool (GBs at large batch): keep the 4 most recent shapes
+                self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = g
+        else:
+            self._graphs[key] = self._graphs.pop(key)   # most recently used last
         graph, static_in, static_out = g
         static_in.copy_(img)
         graph.replay()

@@ -217,6 +217,29 @@ def mode_report(P, W, dev, B: int, precision: str):
             lat.append((time.perf_counter() - t0) * 1e3)
         out[name] = {"traj_per_s": B / (ms * 1e-3), "ms_per_plan": ms, "batch": B, "latency_b1_p50_ms": statistics.median(lat),
                      "launches_per_plan": planner.last_launch_count()}
+    # large-batch regime: the same kernels when a layer has hundreds of row tiles instead of 4..32
+    try:
+        mode, kind, T, BL = "NO_GUIDANCE", "guidance_ddim", 10, 4096
+        cfg = P.load_cfg(EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION=precision))
+        planner = P.DiffusionPlanner(models[mode], P.GuidanceDDIMScheduler(cfg=cfg, **P.scheduler_kwargs(cfg)), cfg)
+        g = torch.Generator(device=dev).manual_seed(5)
+        x, f = torch.randn(BL, 16, 7, device=dev, generator=g), torch.randn(BL, 64, device=dev, generator=g)
+        for _ in range(2):
+            planner.plan(x, f)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            planner.plan(x, f)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        tf = FLOPS_PER_EVAL[mode] * BL * T / (ms * 1e-3) / 1e12
+        out["large_batch_ddim10"] = {"batch": BL, "traj_per_s": BL / (ms * 1e-3), "ms_per_plan": ms, "nominal_tflops": tf,
+                                     "frac_of_bf16_sustained_peak": tf / peaks()["tensor"]}
+        del x, f
+    except Exception as exc:
+        out["large_batch_error"] = repr(exc)[:200]
     # end to end with the image encoder: one ResNet-34 pass per distinct scene (hoisted out of the loop), then the DDIM-100 loop
     try:
         mode, kind, T = "NO_GUIDANCE", "guidance_ddim", 100
