@@ -136,3 +136,18 @@ def test_shard_bounds_cover_batch():
             b = P.shard_bounds(B, ws)
             assert b[0][0] == 0 and b[-1][1] == B and all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_preprocess_frames_argument_checks_without_a_gpu():
+    """b2p_preprocess_frames validates its arguments before touching the device (n_pixels, NULLs, alignment, zero std)."""
+    import ctypes as C
+    from autonomous_driving_with_diffusion_model_b200 import _lib
+    lib = _lib.load()
+    mean, std, bad = (C.c_float * 3)(0.5, 0.5, 0.5), (C.c_float * 3)(1, 1, 1), (C.c_float * 3)(1, 0, 1)
+    assert lib.b2p_preprocess_frames(None, None, 0, mean, std, None) == 0            # empty batch: nothing to do
+    assert lib.b2p_preprocess_frames(None, None, -1, mean, std, None) != 0
+    assert lib.b2p_preprocess_frames(None, None, 8, mean, std, None) != 0
+    assert lib.b2p_preprocess_frames(C.c_void_p(4098), C.c_void_p(8192), 8, mean, std, None) != 0   # input not 4-byte aligned
+    assert lib.b2p_preprocess_frames(C.c_void_p(4096), C.c_void_p(8200), 8, mean, std, None) != 0   # output not 16-byte aligned
+    assert lib.b2p_preprocess_frames(C.c_void_p(4096), C.c_void_p(8192), 8, mean, bad, None) != 0   # zero std
+    assert lib.b2p_set_small_batch_max(None, 4) != 0

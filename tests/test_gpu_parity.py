@@ -558,6 +558,28 @@ def test_small_batch_path_is_precision_independent_and_batch_independent():
         model.set_precision("fp32").set_small_batch_max(4)
 
 
+def test_small_batch_limit_is_a_runtime_knob():
+    """b2p_set_small_batch_max: any limit gives the same answer to fp32 rounding; 0 disables the path; negative is rejected."""
+    model, sd = get_model("NO_GUIDANCE")
+    B = 7
+    inp = W.synth_inputs(B, 0, 91)
+    t = torch.tensor([(11 * i + 5) % 100 for i in range(B)])
+    ref = U.unet_forward(sd, inp["x"], inp["feat"], t, None, "NO_GUIDANCE")
+    outs = []
+    try:
+        for limit in (0, 4, 7, 16):                       # 7 and 16: the GEMV kernels run with 7 samples per launch
+            model.set_small_batch_max(limit)
+            out = model(inp["x"].to(DEV), inp["feat"].to(DEV), t.to(DEV))
+            assert float((out.cpu() - ref).abs().max()) <= 1e-4, limit
+            outs.append(out)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[2], outs[3])      # 0 and 4: tiled kernels; 7 and 16: GEMV kernels
+        assert not torch.equal(outs[0], outs[2])
+        with pytest.raises(ValueError):
+            model.set_small_batch_max(-1)
+    finally:
+        model.set_small_batch_max(4)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # BASELINE.json full-size properties (oracle too slow there): determinism, batch independence, shard equivalence
 # ------------------------------------------------------------------------------------------------------------
