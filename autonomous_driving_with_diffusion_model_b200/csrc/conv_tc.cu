@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   const int stage_bytes = NSPLIT * (A_BYTES + T * BT_BYTES);   // [A hi | A lo | W hi (T taps) | W lo (T taps)]
   int stages = a.ring / stage_bytes;
   if (stages > 8) stages = 8;
-  const int need_cols = (T + 1) * TN;
+  const int TB = (NSPLIT == 2 && a.concat) ? 2 * T : T;        // tap blocks in TMEM (hi*lo products separate when concatenated)
+  const int need_cols = (TB + 1) * TN;
   const uint32_t tmem_cols = need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -427,6 +428,8 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     // stage and advanced by adding to the address field.
     const int nA = (T * TN <= 256) ? T : 4;                              // taps covered by the first instruction
     const uint32_t idescA = umma_idesc_n(nA * TN), idescB = umma_idesc_n(TN);
+    const bool concat = NSPLIT == 2 && a.concat;                         // W_hi and W_lo are adjacent in N: A_hi x [W_hi | W_lo] is one instruction
+    const uint32_t idescC = umma_idesc_n(concat ? 2 * T * TN : TN);
     for (int it = 0; it < n_local; ++it) {
       const int s = it % stages;
       mbar_wait(&sh->full[s], (it / stages) & 1);
@@ -443,6 +446,13 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
         for (int k = 0; k < TC_K / TC_UMMA_K; ++k) {
           const uint64_t ko = (uint64_t)(k * TC_UMMA_K * 2 / 16);       // +32 B per K step, in 16-byte units
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
+          if (concat) {
+            // an M = 128 MMA fetches its operands from shared memory at ~64 B/clk: with N = 48 the 4 KB A slice dominates, so
+            // two instructions that read A_hi once and A_lo once beat three that read A_hi twice
+            umma(tmem_base, a_hi + ko, b_hi + ko, idescC, acc);          // blocks [0,T): hi*hi, blocks [T,2T): hi*lo
+            umma(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);           // blocks [0,T) += lo*hi
+            continue;
+          }
           umma(tmem_base, a_hi + ko, b_hi + ko, idescA, acc);
           if (NSPLIT == 2) {
             umma(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);
@@ -458,7 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
           }
         }
       } else {
-        const uint32_t d = tmem_base + T * TN;
+        const uint32_t d = tmem_base + TB * TN;
 #pragma unroll
         for (int k = 0; k < TC_K / TC_UMMA_K; ++k) {
           const uint64_t ko = (uint64_t)(k * TC_UMMA_K * 2 / 16);
@@ -562,6 +572,22 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
               for (int c = 0; c < EC; ++c) { float g = __shfl_sync(0xffffffffu, y[i][c], src); v[c] += valid ? g : 0.f; }
             }
           }
+          if (NSPLIT == 2 && a.concat) {   // second round: the hi*lo products (shifts are linear, so they are added the same way)
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+              if (i < a.nt[o]) tmem_ld<EC, false>(taddr + (T + a.tap_blk[o][i]) * TN, y[i]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              if (i < a.nt[o]) {
+                const int d = a.tap_shift[o][i];
+                const bool valid = (l + d >= 0) && (l + d < L);
+                const int src = (lane + d) & 31;
+#pragma unroll
+                for (int c = 0; c < EC; ++c) { float g = __shfl_sync(0xffffffffu, y[i][c], src); v[c] += valid ? g : 0.f; }
+              }
+            }
+          }
         } else {
           for (int i = 0; i < a.nt[o]; ++i) {
             const int t = a.tap_blk[o][i], d = a.tap_shift[o][i];
@@ -593,9 +619,10 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       for (int c = 0; c < EC; ++c) v[c] += addv[c];
       if (has_res && n_local > 0) {   // residual 1x1 conv accumulated in the TMEM block after the tap blocks
         float rv[EC];
-        tmem_ld<EC>(taddr + T * TN, rv);
+        tmem_ld<EC>(taddr + TB * TN, rv);
 #pragma unroll
         for (int c = 0; c < EC; ++c) v[c] += rv[c];
+
       }
       if (ok) {
         const size_t orow = (size_t)b * a.out_L + (size_t)(l / a.out_ldiv) * a.out_lmul + o;
@@ -702,6 +729,9 @@ static int launch_t(const TcMaps& maps, const TcArgs& a_in, dim3 grid, cudaStrea
   // bytes in flight — and slightly slower overall because the next layer's CTAs can no longer co-reside.
   static int bigring = -1;
   if (bigring < 0) { const char* e = getenv("B2P_TC_BIGRING"); bigring = e ? atoi(e) : 0; }
+  static int concat = -1;
+  if (concat < 0) { const char* e = getenv("B2P_TC_CONCAT"); concat = e ? atoi(e) : 1; }
+  a.concat = (NSPLIT == 2 && concat && TN <= 32 && 2 * a.T * TN <= 256) ? 1 : 0;
   a.ring = SmemPlan<TN>::ring;
   if (TN == 16 && bigring && (int)(grid.x * grid.y) <= 148) a.ring = SmemPlan<32>::ring;
   const int smem = (TN == 64 ? a.ring : a.ring + 4 * 1024) + 1024 + (int)sizeof(TcShared);
