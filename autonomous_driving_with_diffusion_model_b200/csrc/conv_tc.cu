@@ -731,7 +731,10 @@ static int launch_t(const TcMaps& maps, const TcArgs& a_in, dim3 grid, cudaStrea
   if (bigring < 0) { const char* e = getenv("B2P_TC_BIGRING"); bigring = e ? atoi(e) : 0; }
   static int concat = -1;
   if (concat < 0) { const char* e = getenv("B2P_TC_CONCAT"); concat = e ? atoi(e) : 1; }
-  a.concat = (NSPLIT == 2 && concat && TN <= 32 && 2 * a.T * TN <= 256) ? 1 : 0;
+  // worth it when the A_hi re-reads it saves (64 cycles per K step, 4 K steps per 64-channel chunk) outweigh the extra TMEM
+  // reads of the epilogue (T*TN more columns of 128 rows at 64 B/clk = 8*T*TN cycles): not for the 1-chunk layers
+  const int chunks = (a.C[0] + a.C[1]) / TC_K;
+  a.concat = (NSPLIT == 2 && concat && TN <= 32 && 2 * a.T * TN <= 256 && (concat > 1 || chunks * 256 > 10 * a.T * TN)) ? 1 : 0;
   a.ring = SmemPlan<TN>::ring;
   if (TN == 16 && bigring && (int)(grid.x * grid.y) <= 148) a.ring = SmemPlan<32>::ring;
   const int smem = (TN == 64 ? a.ring : a.ring + 4 * 1024) + 1024 + (int)sizeof(TcShared);
