@@ -15,34 +15,37 @@ constexpr int TP_FF = 256;
 constexpr int TP_MAXS = 16;   // tokens (horizon - 1 <= 16)
 constexpr int TP_NT = 512;
 
+// Shared-memory plan: 103.5 KB, so TWO trajectories (CTAs) share an SM and 256 of them fit the chip in one wave.  Only what
+// the backward pass needs is kept per layer (qkv, attention probabilities, the normalised LayerNorm inputs and the FFN
+// input x1 — the FFN pre-activation is recomputed from x1 in the backward pass, bit-identical to the forward value);
+// everything else lives in scratch buffers that the forward and the backward pass use for different things.
 struct LayerAct {            // saved for backward (floats, S = tokens)
-  float xin[TP_MAXS * TP_D];
   float qkv[TP_MAXS * 3 * TP_D];
   float P[TP_H * TP_MAXS * TP_MAXS];
-  float att[TP_MAXS * TP_D];
   float xh1[TP_MAXS * TP_D];   // normalised (pre-affine) LN1
-  float x1[TP_MAXS * TP_D];    // LN1 output
-  float h1[TP_MAXS * TP_FF];   // FFN pre-activation
+  float x1[TP_MAXS * TP_D];    // LN1 output = FFN input
   float xh2[TP_MAXS * TP_D];   // normalised LN2
   float rstd1[TP_MAXS], rstd2[TP_MAXS];
 };
 struct TpSmem {
   LayerAct L[2];
-  float xfin[TP_MAXS * TP_D];  // input of the final LayerNorm
-  float xhf[TP_MAXS * TP_D];
-  float xf[TP_MAXS * TP_D];
+  float xhf[TP_MAXS * TP_D];   // normalised final LayerNorm
   float rstdf[TP_MAXS];
   float out[TP_MAXS * 4];
   float act[TP_MAXS * 4];      // action rows (3 used)
   float te[TP_D];
-  // backward scratch
-  float ga[TP_MAXS * TP_FF];   // generic gradient buffers
-  float gb[TP_MAXS * TP_FF];
-  float gx[TP_MAXS * TP_D];
-  float gqkv[TP_MAXS * 3 * TP_D];
-  float gP[TP_H * TP_MAXS * TP_MAXS];
+  float ga[TP_MAXS * TP_FF];   // forward: attention output (first S*D), then FFN hidden.  backward: d(FFN hidden), then d(qkv)
+  float gb[TP_MAXS * TP_FF];   // forward: final LayerNorm input / output.  backward: recomputed FFN pre-activation, then d(attention output)
+  float gx[TP_MAXS * TP_D];    // forward: input of layer 0.  backward: running gradient wrt the layer input
+  float gP[TP_H * TP_MAXS * TP_MAXS];   // forward: input of layer 1.  backward: d(P)
   int idx;
+  __device__ __forceinline__ float* xin(int l) { return l == 0 ? gx : gP; }
+  __device__ __forceinline__ float* att() { return ga; }
+  __device__ __forceinline__ float* gqkv() { return ga; }
+  __device__ __forceinline__ float* xfin() { return gb; }
+  __device__ __forceinline__ float* xf() { return gb + TP_MAXS * TP_D; }
 };
+static_assert(sizeof(TpSmem) <= 110 * 1024, "two TrajPredict CTAs must fit one SM");
 
 // Y[s][n] = sum_k X[s][k] * Wt[k][n] + b[n].  Work item = (column n, group of RPG rows); the TP_NT threads cover
 // N x G items (G = 8 row groups for N = 64, 2 for N = 192 / 256).  The weight column is read straight from L2 (the 400 KB
@@ -124,7 +127,9 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 __device__ void encoder_layer_fwd(TpSmem& sm, int l, const TrajPredWeights::Layer& w, float* xout, int S) {
   LayerAct& A = sm.L[l];
-  linear<false, 3 * TP_D>(A.xin, TP_D, w.qkv_wt, w.qkv_b, A.qkv, 3 * TP_D, S, TP_D);
+  const float* xin = sm.xin(l);
+  float* att = sm.att();
+  linear<false, 3 * TP_D>(xin, TP_D, w.qkv_wt, w.qkv_b, A.qkv, 3 * TP_D, S, TP_D);
   __syncthreads();
   for (int i = threadIdx.x; i < TP_H * S * S; i += TP_NT) {   // scores
     int h = i / (S * S), r = (i / S) % S, c = i % S;
@@ -151,19 +156,19 @@ __device__ void encoder_layer_fwd(TpSmem& sm, int l, const TrajPredWeights::Laye
     const float* p = A.P + (size_t)(h * TP_MAXS + r) * TP_MAXS;
     float s = 0.f;
     for (int c = 0; c < S; ++c) s = fmaf(p[c], A.qkv[c * 3 * TP_D + 2 * TP_D + col], s);
-    A.att[i] = s;
+    att[i] = s;
   }
   __syncthreads();
   // y1 = xin + att Wo^T + bo   (into x1 as scratch), then LN1
-  linear<false, TP_D>(A.att, TP_D, w.out_wt, w.out_b, A.x1, TP_D, S, TP_D);
+  linear<false, TP_D>(att, TP_D, w.out_wt, w.out_b, A.x1, TP_D, S, TP_D);
   __syncthreads();
-  for (int i = threadIdx.x; i < S * TP_D; i += TP_NT) A.x1[i] += A.xin[i];
+  for (int i = threadIdx.x; i < S * TP_D; i += TP_NT) A.x1[i] += xin[i];
   __syncthreads();
   layer_norm(A.x1, w.n1_g, w.n1_b, A.x1, A.xh1, A.rstd1, S);
   __syncthreads();
-  linear<false, TP_FF>(A.x1, TP_D, w.l1_wt, w.l1_b, A.h1, TP_FF, S, TP_D);
+  linear<false, TP_FF>(A.x1, TP_D, w.l1_wt, w.l1_b, sm.ga, TP_FF, S, TP_D);   // FFN pre-activation (the attention output in ga is dead)
   __syncthreads();
-  for (int i = threadIdx.x; i < S * TP_FF; i += TP_NT) { float v = A.h1[i]; sm.ga[i] = v * sigmoidf_(v); }  // SiLU
+  for (int i = threadIdx.x; i < S * TP_FF; i += TP_NT) { float v = sm.ga[i]; sm.ga[i] = v * sigmoidf_(v); }  // SiLU, in place
   __syncthreads();
   linear<false, TP_D>(sm.ga, TP_FF, w.l2_wt, w.l2_b, xout, TP_D, S, TP_FF);
   __syncthreads();
@@ -176,12 +181,14 @@ __device__ void encoder_layer_fwd(TpSmem& sm, int l, const TrajPredWeights::Laye
 // gradient wrt the layer output is in sm.gx on entry; gradient wrt the layer input is in sm.gx on exit
 __device__ void encoder_layer_bwd(TpSmem& sm, int l, const TrajPredWeights::Layer& w, int S) {
   LayerAct& A = sm.L[l];
+  float* gqkv = sm.gqkv();
   layer_norm_bwd(sm.gx, A.xh2, A.rstd2, w.n2_g, S);            // gx = d(x1 + ff)
   __syncthreads();
   linear<false, TP_FF>(sm.gx, TP_D, w.l2_w, nullptr, sm.ga, TP_FF, S, TP_D);   // d silu(h1) = gx W2   (W2 raw [64][256])
+  linear<false, TP_FF>(A.x1, TP_D, w.l1_wt, w.l1_b, sm.gb, TP_FF, S, TP_D);    // h1 recomputed (same code, same inputs as the forward pass)
   __syncthreads();
   for (int i = threadIdx.x; i < S * TP_FF; i += TP_NT) {
-    float v = A.h1[i], sg = sigmoidf_(v);
+    float v = sm.gb[i], sg = sigmoidf_(v);
     sm.ga[i] *= sg * (1.f + v * (1.f - sg));
   }
   __syncthreads();
@@ -202,7 +209,7 @@ __device__ void encoder_layer_bwd(TpSmem& sm, int l, const TrajPredWeights::Laye
     int c = i / TP_D, col = i % TP_D, h = col / TP_HD;
     float s = 0.f;
     for (int r = 0; r < S; ++r) s = fmaf(A.P[(h * TP_MAXS + r) * TP_MAXS + c], sm.gb[r * TP_D + col], s);
-    sm.gqkv[c * 3 * TP_D + 2 * TP_D + col] = s;
+    gqkv[c * 3 * TP_D + 2 * TP_D + col] = s;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < TP_H * S; i += TP_NT) {        // softmax backward per row -> dS (scaled by 1/4)
@@ -219,11 +226,11 @@ __device__ void encoder_layer_bwd(TpSmem& sm, int l, const TrajPredWeights::Laye
       dq = fmaf(sm.gP[(h * TP_MAXS + r) * TP_MAXS + c], A.qkv[c * 3 * TP_D + TP_D + col], dq);
       dk = fmaf(sm.gP[(h * TP_MAXS + c) * TP_MAXS + r], A.qkv[c * 3 * TP_D + col], dk);
     }
-    sm.gqkv[r * 3 * TP_D + col] = dq;
-    sm.gqkv[r * 3 * TP_D + TP_D + col] = dk;
+    gqkv[r * 3 * TP_D + col] = dq;
+    gqkv[r * 3 * TP_D + TP_D + col] = dk;
   }
   __syncthreads();
-  linear<true, TP_D>(sm.gqkv, 3 * TP_D, w.qkv_w, nullptr, sm.gx, TP_D, S, 3 * TP_D);  // gx += dqkv Wqkv (raw [192][64])
+  linear<true, TP_D>(gqkv, 3 * TP_D, w.qkv_w, nullptr, sm.gx, TP_D, S, 3 * TP_D);  // gx += dqkv Wqkv (raw [192][64])
   __syncthreads();
 }
 
@@ -233,7 +240,7 @@ __device__ void encoder_layer_bwd(TpSmem& sm, int l, const TrajPredWeights::Laye
 //                 index rule / state gradient, else they are written first.  Then the guidance update is applied in place.
 // MODE 0: forward only; 1: guidance update; 2: VJP with an arbitrary cotangent `target` = grad_state [B,S,SD] -> out = grad_action [B,H,3]
 template <int MODE>
-__global__ void __launch_bounds__(TP_NT) trajpred_kernel(TrajPredWeights w, const float* __restrict__ action, int action_stride,
+__global__ void __launch_bounds__(TP_NT, 2) trajpred_kernel(TrajPredWeights w, const float* __restrict__ action, int action_stride,
                                                          int action_col0, const float* __restrict__ time_embed, int te_stride, float* out, int full,
                                                          int state_given, const float* __restrict__ target, float grad_scale,
                                                          float scale_state, float scale_action, int H, int D) {
@@ -249,17 +256,18 @@ __global__ void __launch_bounds__(TP_NT) trajpred_kernel(TrajPredWeights w, cons
     v = fmaf(sm.act[s * 4 + 0], __ldg(w.in_w + 0 * TP_D + n), v);
     v = fmaf(sm.act[s * 4 + 1], __ldg(w.in_w + 1 * TP_D + n), v);
     v = fmaf(sm.act[s * 4 + 2], __ldg(w.in_w + 2 * TP_D + n), v);
-    sm.L[0].xin[i] = v + __ldg(w.pos + i) + sm.te[n];
+    sm.xin(0)[i] = v + __ldg(w.pos + i) + sm.te[n];
   }
   __syncthreads();
-  encoder_layer_fwd(sm, 0, w.layer[0], sm.L[1].xin, S);
-  encoder_layer_fwd(sm, 1, w.layer[1], sm.xfin, S);
-  layer_norm(sm.xfin, w.fn_g, w.fn_b, sm.xf, sm.xhf, sm.rstdf, S);
+  encoder_layer_fwd(sm, 0, w.layer[0], sm.xin(1), S);
+  encoder_layer_fwd(sm, 1, w.layer[1], sm.xfin(), S);
+  layer_norm(sm.xfin(), w.fn_g, w.fn_b, sm.xf(), sm.xhf, sm.rstdf, S);
   __syncthreads();
+  const float* xf = sm.xf();
   for (int i = tid; i < S * SD; i += TP_NT) {
     int s = i / SD, c = i % SD;
     float v = __ldg(w.out_b + c);
-    for (int k = 0; k < TP_D; ++k) v = fmaf(sm.xf[s * TP_D + k], __ldg(w.out_wt + k * SD + c), v);
+    for (int k = 0; k < TP_D; ++k) v = fmaf(xf[s * TP_D + k], __ldg(w.out_wt + k * SD + c), v);
     sm.out[s * 4 + c] = v;
   }
   __syncthreads();
