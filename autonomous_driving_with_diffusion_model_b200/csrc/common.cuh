@@ -60,13 +60,16 @@ int launch_conv_gemv(const ConvArgs& a, cudaStream_t s);
 // Ask for the maximum shared-memory carve-out for `kernel` (once per kernel).  Every kernel of the plan uses the same
 // L1/shared split, so kernels that overlap under programmatic dependent launch never wait for an SM to be reconfigured.
 inline void prefer_max_smem_carveout(const void* kernel) {
-  static const void* seen[64];
+  static const void* seen[256];          // (kernel, device) pairs already configured
+  static int seen_dev[256];
   static int nseen = 0;
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("B2P_CARVEOUT"); enabled = e ? atoi(e) : 1; }
   if (!enabled) return;
-  for (int i = 0; i < nseen; ++i) if (seen[i] == kernel) return;
-  if (nseen < 64) seen[nseen++] = kernel;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  for (int i = 0; i < nseen; ++i) if (seen[i] == kernel && seen_dev[i] == dev) return;
+  if (nseen < 256) { seen[nseen] = kernel; seen_dev[nseen] = dev; ++nseen; }
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 

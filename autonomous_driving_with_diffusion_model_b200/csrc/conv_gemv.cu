@@ -346,10 +346,12 @@ static size_t gv_smem_floats(const ConvArgs& a, int nc) {
 
 template <int RT>
 static int launch_rt(const ConvArgs& a, int nc, int cls, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[64] = {};     // per device: function attributes belong to the device's context
+  int dev = 0;
+  B2P_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || smem > configured[dev]) {
     B2P_CUDA_TRY(cudaFuncSetAttribute(conv_gemv_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
   }
   prefer_max_smem_carveout((const void*)conv_gemv_kernel<RT>);
   cudaLaunchConfig_t cfg = {};
