@@ -606,3 +606,24 @@ def test_full_size_batch_independence_and_sharding_equivalence():
     ref = OP.plan(sd, "NO_GUIDANCE", "guidance_ddim", inp["x"][:4], inp["feat"][:4], T)  # oracle on a slice it can finish quickly
     d = (full[:4].cpu() - ref).abs()
     assert float(d[..., :2].max()) <= 1e-3 * MAGIC and float(d[..., 2:].max()) <= 1e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_two_devices_give_identical_results():
+    """The model keeps one C handle per device; kernel attributes, constant tables and packed weights are per device."""
+    sd = W.make_state_dict("NO_GUIDANCE", seed=0, with_perception=False)
+    outs = []
+    for B in (1, 40):                                  # GEMV kernels and tiled kernels
+        inp = W.synth_inputs(B, 0, 61)
+        per_dev = []
+        for d in (0, 1):
+            dev = torch.device(f"cuda:{d}")
+            m = P.build_model(P.load_cfg(B200=dict(PRECISION="bf16x3")))
+            m.load_state_dict(sd, strict=False)
+            m = m.to(dev).eval()
+            planner = P.DiffusionPlanner(m, make_sched("guidance_ddim"), _cfg("NO_GUIDANCE", 4))
+            with torch.cuda.device(dev):
+                per_dev.append(planner.plan(inp["x"].to(dev), inp["feat"].to(dev)).cpu())
+        assert torch.equal(per_dev[0], per_dev[1]), B
+        outs.append(per_dev[0])
+    assert all(bool(torch.isfinite(o).all()) for o in outs)
