@@ -324,6 +324,7 @@ class TemporalMapUnet(nn.Module):
         self._packed: Dict[int, tuple] = {}
         self._feat_cache: Optional[tuple] = None
         self._tensor_list: Optional[list] = None
+        self._tensor_gen = 0
 
     # ---- C handle management --------------------------------------------------------------------------
     def _unet_items(self) -> Iterable[Tuple[str, torch.Tensor]]:
@@ -340,14 +341,17 @@ class TemporalMapUnet(nn.Module):
         return self._tensor_list
 
     def _version_key(self) -> tuple:
-        return tuple([(v.data_ptr(), v._version) for v in self._unet_tensors()])
+        """Changes whenever a denoiser tensor is modified in place (version counters) or replaced / moved (the tensor list is
+        rebuilt by _apply / load_state_dict, which bump the generation term)."""
+        ts = self._unet_tensors()
+        return (self._tensor_gen, sum([t._version for t in ts]))
 
     def _apply(self, fn, *args, **kwargs):
-        self._tensor_list = None
+        self._tensor_list, self._tensor_gen = None, getattr(self, "_tensor_gen", 0) + 1
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
-        self._tensor_list = None
+        self._tensor_list, self._tensor_gen = None, getattr(self, "_tensor_gen", 0) + 1
         return super().load_state_dict(*args, **kwargs)
 
     def _stream(self):
