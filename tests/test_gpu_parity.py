@@ -627,3 +627,24 @@ def test_one_process_two_devices_give_identical_results():
         assert torch.equal(per_dev[0], per_dev[1]), B
         outs.append(per_dev[0])
     assert all(bool(torch.isfinite(o).all()) for o in outs)
+
+
+def test_weight_updates_reach_the_device_copy():
+    """Packed weights are re-uploaded when a denoiser tensor changes: in-place update, load_state_dict, and module conversion."""
+    sd = W.make_state_dict("NO_GUIDANCE", seed=0, with_perception=False)
+    m = P.build_model(P.load_cfg())
+    m.load_state_dict(sd, strict=False)
+    m = m.to(DEV).eval()
+    inp = W.synth_inputs(2, 0, 71)
+    x, f, t = inp["x"].to(DEV), inp["feat"].to(DEV), torch.tensor([20, 60], device=DEV)
+    base = m(x, f, t).clone()
+    w = m.final_conv._modules["1"].weight
+    with torch.no_grad():
+        w.mul_(2.0)                                       # in place: version counter
+    doubled = m(x, f, t).clone()
+    bias = m.final_conv._modules["1"].bias.detach().view(1, 1, -1)
+    assert float(((doubled - bias) - 2.0 * (base - bias)).abs().max()) <= 1e-5        # the 1x1 head is linear in its weight
+    m.load_state_dict(sd, strict=False)                   # reload: back to the original
+    assert torch.equal(m(x, f, t), base)
+    m.double().float()                                    # conversion round trip replaces the tensors
+    assert torch.equal(m(x, f, t), base)
