@@ -325,8 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
 
   const int T = a.T;
   const int stage_bytes = NSPLIT * (A_BYTES + T * BT_BYTES);   // [A hi | A lo | W hi (T taps) | W lo (T taps)]
-  int stages = a.ring / stage_bytes;
-  if (stages > 8) stages = 8;
+  const int stages = a.stages;                                   // min(ring / stage_bytes, 8), computed by the host (no division here)
   const int TB = (NSPLIT == 2 && a.concat) ? 2 * T : T;        // tap blocks in TMEM (hi*lo products separate when concatenated)
   const int need_cols = (TB + 1) * TN;
   const uint32_t tmem_cols = need_cols <= 32 ? 32u : (need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u)));
@@ -336,8 +335,8 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   // cluster = (1, CL, 1) consecutive column tiles of the same row tile: they share the activation tile (TMA multicast: every
   // CTA loads 1/CL of it and broadcasts) and, in sub-groups of cluster_n, a GroupNorm group (statistics exchange)
   const int CL = a.cluster_l;
-  const int lrank = blockIdx.y % CL;               // rank inside the cluster (== %cluster_ctarank)
-  const int crank = lrank % a.cluster_n;           // rank inside the GroupNorm sub-group
+  const int lrank = blockIdx.y & (CL - 1);         // rank inside the cluster (== %cluster_ctarank); cluster sizes are powers of two
+  const int crank = lrank & (a.cluster_n - 1);     // rank inside the GroupNorm sub-group
   const int cbase = lrank - crank;                 // first cluster rank of the sub-group
   const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   const int b0 = tile_m * a.samples_per_tile;
@@ -383,8 +382,8 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     if (NSPLIT == 2) { prefetch_tmap(&maps.a[0][1]); prefetch_tmap(&maps.w[1]); }
     // The weights do not depend on the previous layer: their TMA loads for the first ring pass are issued BEFORE the
     // grid-dependency wait and overlap the tail of the preceding kernel; only the activation loads wait for it.
-    auto issue = [&](int it, bool do_w, bool do_a) {
-      const int s = it % stages;
+    const int mc_sub = mcast ? a.samples_per_tile / CL : 0, mc_bytes = mcast ? A_BYTES / CL : 0;   // multicast slices (off the hot path: once)
+    auto issue = [&](int it, int s, bool do_w, bool do_a) {   // s = it % stages, tracked by the callers (no runtime division)
       uint8_t* st = smem + s * stage_bytes;
       uint8_t* sb = st + NSPLIT * A_BYTES;
       const bool res_phase = it >= main_iters;
@@ -403,23 +402,23 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       }
       if (do_a) {
         // this CTA fetches samples [lrank*spt/CL, (lrank+1)*spt/CL) of the tile and broadcasts them to the whole cluster
-        const int sub = a.samples_per_tile / CL;
 #pragma unroll
         for (int h = 0; h < NSPLIT; ++h) {
           const CUtensorMap* mp = res_phase ? &maps.r[src][h] : &maps.a[src][h];
-          if (mcast) tma_load_3d_mc(st + h * A_BYTES + lrank * (A_BYTES / CL), mp, &sh->full[s], c0, 0, b0 + lrank * sub, cmask);
+          if (mcast) tma_load_3d_mc(st + h * A_BYTES + lrank * mc_bytes, mp, &sh->full[s], c0, 0, b0 + lrank * mc_sub, cmask);
           else tma_load_3d(st + h * A_BYTES, mp, &sh->full[s], c0, 0, b0);
         }
       }
     };
     const int npre = n_local < stages ? n_local : stages;
-    for (int j = 0; j < npre; ++j) issue(j, true, false);
+    for (int j = 0; j < npre; ++j) issue(j, j, true, false);
     griddep_wait();
     TC_T(1); TC_TG(9, false);
-    for (int j = 0; j < npre; ++j) issue(j, false, true);
-    for (int j = npre; j < n_local; ++j) {
-      mbar_wait(&sh->empty[j % stages], ((j / stages) & 1) ^ 1);
-      issue(j, true, true);
+    for (int j = 0; j < npre; ++j) issue(j, j, false, true);
+    for (int j = npre, s = 0, par = 0; j < n_local; ++j) {      // s = j % stages, par = ((j / stages) & 1) ^ 1 (npre == stages here)
+      mbar_wait(&sh->empty[s], par);
+      issue(j, s, true, true);
+      if (++s == stages) { s = 0; par ^= 1; }
     }
   } else if (threadIdx.x == 32) {
     // =============================== MMA issuer (one thread) ===============================
@@ -430,9 +429,8 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     const uint32_t idescA = umma_idesc_n(nA * TN), idescB = umma_idesc_n(TN);
     const bool concat = NSPLIT == 2 && a.concat;                         // W_hi and W_lo are adjacent in N: A_hi x [W_hi | W_lo] is one instruction
     const uint32_t idescC = umma_idesc_n(concat ? 2 * T * TN : TN);
-    for (int it = 0; it < n_local; ++it) {
-      const int s = it % stages;
-      mbar_wait(&sh->full[s], (it / stages) & 1);
+    for (int it = 0, s = 0, par = 0; it < n_local; ++it, s = (s + 1 == stages ? 0 : s + 1), par ^= (s == 0)) {   // s = it % stages, par = (it / stages) & 1
+      mbar_wait(&sh->full[s], par);
       tc_fence_after();
       if (it == 0) TC_T(2);
       const uint32_t sa = smem_u32(smem + s * stage_bytes);
@@ -613,7 +611,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
           default: group_norm_mish<64, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0); break;
         }
       }
-      const bool ok = row_ok && (a.out_ldiv == 1 || (l % a.out_ldiv) == 0);
+      const bool ok = row_ok && (l & (a.out_ldiv - 1)) == 0;   // out_ldiv is 1 or 2 (stride of the conv): masks and shifts, not divisions
       if (threadIdx.x == 64 && o == 0) TC_T(5);
 #pragma unroll
       for (int c = 0; c < EC; ++c) v[c] += addv[c];
@@ -625,7 +623,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
 
       }
       if (ok) {
-        const size_t orow = (size_t)b * a.out_L + (size_t)(l / a.out_ldiv) * a.out_lmul + o;
+        const size_t orow = (size_t)b * a.out_L + (size_t)(l >> (a.out_ldiv >> 1)) * a.out_lmul + o;
         if (a.out_hi) {
           __nv_bfloat16* oh = a.out_hi + orow * a.Cout + gcol;
           __nv_bfloat16* ol = a.out_lo ? a.out_lo + orow * a.Cout + gcol : nullptr;
@@ -737,6 +735,10 @@ static int launch_t(const TcMaps& maps, const TcArgs& a_in, dim3 grid, cudaStrea
   a.concat = (NSPLIT == 2 && concat && TN <= 32 && 2 * a.T * TN <= 256 && (concat > 1 || chunks * 256 > 10 * a.T * TN)) ? 1 : 0;
   a.ring = SmemPlan<TN>::ring;
   if (TN == 16 && bigring && (int)(grid.x * grid.y) <= 148) a.ring = SmemPlan<32>::ring;
+  {
+    const int stage_bytes = NSPLIT * (A_BYTES + a.T * TN * TC_K * 2);
+    a.stages = a.ring / stage_bytes > 8 ? 8 : a.ring / stage_bytes;
+  }
   const int smem = (TN == 64 ? a.ring : a.ring + 4 * 1024) + 1024 + (int)sizeof(TcShared);
   B2P_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<NSPLIT, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPlan<TN == 16 ? 32 : TN>::total));
   cudaLaunchConfig_t cfg;
@@ -797,14 +799,14 @@ int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStrea
 #endif
   const int TN = a.tile_n;
   if (TN != 64 && TN != 32 && TN != 16) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  if (a.T < 1 || a.T > 5 || a.n_out < 1 || a.n_out > 2 || a.out_ldiv < 1) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
+  if (a.T < 1 || a.T > 5 || a.n_out < 1 || a.n_out > 2 || (a.out_ldiv != 1 && a.out_ldiv != 2)) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (nsplit * (A_BYTES + a.T * TN * TC_K * 2) * 2 > (TN == 64 ? SmemPlan<64>::ring : (TN == 32 ? SmemPlan<32>::ring : SmemPlan<16>::ring))) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.Cout % TN || a.C[0] % TC_K || a.C[1] % TC_K || a.RC[0] % TC_K || a.RC[1] % TC_K || a.nrows <= 0) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.Lrows > 32 || (a.Lrows & (a.Lrows - 1)) || TC_M % a.Lrows) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.headW && (a.Cout != 64 || TN != 64 || a.head_dim > 8)) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   if (a.n_out == 2 && a.gn_gamma) { fprintf(stderr, "launch_conv_tc: GroupNorm with two outputs per row is not supported (single-use exchange barrier)\n"); return B2P_ERR_INVALID_ARG; }
   if (a.n_out == 2 && (a.RC[0] || a.RC[1])) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  if (a.cluster_n < 1 || a.cluster_l < a.cluster_n || a.cluster_l % a.cluster_n) { fprintf(stderr, "launch_conv_tc: tc_configure() was not applied\n"); return B2P_ERR_INVALID_ARG; }
+  if (a.cluster_n < 1 || a.cluster_l < a.cluster_n || a.cluster_l % a.cluster_n || (a.cluster_n & (a.cluster_n - 1)) || (a.cluster_l & (a.cluster_l - 1))) { fprintf(stderr, "launch_conv_tc: tc_configure() was not applied\n"); return B2P_ERR_INVALID_ARG; }
   if ((a.Cout / TN) % a.cluster_l) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
   dim3 grid((a.nrows + TC_M - 1) / TC_M, a.Cout / TN, 1);
   if (nsplit == 2) {

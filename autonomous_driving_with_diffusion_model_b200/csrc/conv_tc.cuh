@@ -42,6 +42,7 @@ struct TcArgs {
   int cluster_n;          // set by launch_conv_tc: CTAs along N sharing one GroupNorm group
   int cluster_l;          // set by launch_conv_tc: cluster size along N (activation-tile multicast), multiple of cluster_n
   int ring;               // set by launch_conv_tc: bytes of the operand ring in dynamic shared memory
+  int stages;             // set by launch_conv_tc: ring stages = min(ring / stage bytes, 8)
   int concat;             // set by launch_conv_tc (bf16x3): hi x [W_hi | W_lo] as ONE MMA of N = 2*T*tile_n; the hi*lo products get their own TMEM block
   int dbg;                // developer bisect switch (B2P_TC_DBG): 1 = skip the TMA/MMA main loop, 2 = skip the epilogue math
 };

@@ -37,7 +37,9 @@ __device__ __forceinline__ float x0_of(const SchedK& a, float m, float x) {
   return sub(mul(a.k.sqrt_alpha_prod_t, x), mul(a.k.sqrt_beta_prod_t, m));
 }
 
-__device__ __forceinline__ float step_one(const SchedK& a, int idx, float m, float mu, float x, float nz, float tj, float mk,
+// sample = index of the trajectory, pos = offset inside its [H*D] block, col = pos % D (tracked by the caller: one division per
+// thread instead of three per element)
+__device__ __forceinline__ float step_one(const SchedK& a, int sample, int pos, int col, float m, float mu, float x, float nz, float tj, float mk,
                                           float* x0_store) {
   if (a.mo_u) m = add(mu, mul(a.cfg_scale, sub(m, mu)));  // u + s*(c - u)
   float x0 = x0_of(a, m, x);
@@ -49,7 +51,7 @@ __device__ __forceinline__ float step_one(const SchedK& a, int idx, float m, flo
   }
   if (a.clip_mode == 1) x0 = clampf(x0, -a.clip_range, a.clip_range);
   else if (a.clip_mode == 2) x0 = dvd(clampf(x0, -1.f, 1.f), 1.f);
-  else if (a.clip_mode == 3) { float s = a.thr_s[idx / a.HD]; x0 = dvd(clampf(x0, -s, s), s); }
+  else if (a.clip_mode == 3) { float s = a.thr_s[sample]; x0 = dvd(clampf(x0, -s, s), s); }
   *x0_store = x0;
   float prev;
   if (!a.ddpm) {
@@ -68,11 +70,10 @@ __device__ __forceinline__ float step_one(const SchedK& a, int idx, float m, flo
     prev = add(mul(mk, known), mul(sub(1.0f, mk), prev));
   }
   if (!a.ddpm && a.eta > 0.f) prev = add(prev, mul(a.k.std_dev_t, nz));
-  int pos = idx % a.HD;
   if ((a.flags & B2P_STEP_ZERO_FIRST_WAYPOINT) && pos < 3) prev = 0.f;
   if (a.flags & B2P_STEP_FINAL_POSTPROCESS) {
     prev = clampf(prev, -1.f, 1.f);
-    if (pos % a.D < 2) prev = mul(prev, a.magic);
+    if (col < 2) prev = mul(prev, a.magic);
   }
   return prev;
 }
@@ -91,10 +92,13 @@ __global__ void __launch_bounds__(256) sched_step_kernel(SchedK a) {
   float4 tj = a.traj ? __ldg(reinterpret_cast<const float4*>(a.traj) + i4) : z;
   float4 mk = a.mask ? __ldg(reinterpret_cast<const float4*>(a.mask) + i4) : z;
   float4 o, x0;
-  o.x = step_one(a, base + 0, m.x, mu.x, x.x, nz.x, tj.x, mk.x, &x0.x);
-  o.y = step_one(a, base + 1, m.y, mu.y, x.y, nz.y, tj.y, mk.y, &x0.y);
-  o.z = step_one(a, base + 2, m.z, mu.z, x.z, nz.z, tj.z, mk.z, &x0.z);
-  o.w = step_one(a, base + 3, m.w, mu.w, x.w, nz.w, tj.w, mk.w, &x0.w);
+  // H*D is a multiple of 4 (checked by the launcher), so the 4 elements of a thread belong to one trajectory
+  const int sample = base / a.HD, pos = base - sample * a.HD;
+  int c0 = pos % a.D, c1 = c0 + 1 == a.D ? 0 : c0 + 1, c2 = c1 + 1 == a.D ? 0 : c1 + 1, c3 = c2 + 1 == a.D ? 0 : c2 + 1;
+  o.x = step_one(a, sample, pos + 0, c0, m.x, mu.x, x.x, nz.x, tj.x, mk.x, &x0.x);
+  o.y = step_one(a, sample, pos + 1, c1, m.y, mu.y, x.y, nz.y, tj.y, mk.y, &x0.y);
+  o.z = step_one(a, sample, pos + 2, c2, m.z, mu.z, x.z, nz.z, tj.z, mk.z, &x0.z);
+  o.w = step_one(a, sample, pos + 3, c3, m.w, mu.w, x.w, nz.w, tj.w, mk.w, &x0.w);
   reinterpret_cast<float4*>(a.prev)[i4] = o;
   if (a.x0_out) reinterpret_cast<float4*>(a.x0_out)[i4] = x0;
 }
