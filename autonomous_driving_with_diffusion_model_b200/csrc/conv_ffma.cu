@@ -12,6 +12,18 @@
 
 namespace b2p {
 
+// x / d, x % d for a runtime d that is a power of two for every layer of the model (shift / mask), any d otherwise
+struct FastDiv {
+  int d, sh;
+  __device__ __forceinline__ int div(int x) const { return sh >= 0 ? x >> sh : x / d; }
+  __device__ __forceinline__ int mod(int x) const { return sh >= 0 ? x & (d - 1) : x % d; }
+};
+__device__ __forceinline__ FastDiv fast_div(int d) {
+  FastDiv r;
+  r.d = d; r.sh = (d > 0 && (d & (d - 1)) == 0) ? 31 - __clz(d) : -1;
+  return r;
+}
+
 constexpr int TN = 64;     // output channels per CTA
 constexpr int KC = 16;     // K chunk
 constexpr int NT = 256;    // threads
@@ -62,12 +74,12 @@ __device__ __forceinline__ void gemm_phase(Smem<TM>& sm, float (&acc)[TM / 16][4
   if (VEC) nchunks = (taps_hi - taps_lo + 1) * (Cin / KC);
   else nchunks = ((taps_hi - taps_lo + 1) * Cin + KC - 1) / KC;
 
+  const FastDiv dpt = fast_div(VEC ? Cin / KC : 1);   // chunks per tap
   float4 areg = make_float4(0.f, 0.f, 0.f, 0.f), wreg;
   auto load_chunk = [&](int ch) {
     if (VEC) {
-      int per_tap = Cin / KC;
-      int j = taps_lo + ch / per_tap;
-      int c = (ch % per_tap) * KC;
+      int j = taps_lo + dpt.div(ch);
+      int c = dpt.mod(ch) * KC;
       areg = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row_ok) {
         int pos = tap_pos(al, j, stride, pad, transposed, Lin);
@@ -179,15 +191,16 @@ __global__ void __launch_bounds__(NT) conv_ffma_kernel(ConvArgs a) {
     const int npairs = spt * gpt;
     const int ne = L * cg;
     const int warp = tid >> 5, lane = tid & 31;
+    const FastDiv dcg = fast_div(cg), dgpt = fast_div(gpt), dL = fast_div(L);
     for (int p = warp; p < npairs; p += NT / 32) {
-      int s = p / gpt, g = p % gpt;
+      int s = dgpt.div(p), g = dgpt.mod(p);
       float sum = 0.f;
-      for (int e = lane; e < ne; e += 32) sum += sm.C[s * L + e / cg][g * cg + e % cg];
+      for (int e = lane; e < ne; e += 32) sum += sm.C[s * L + dcg.div(e)][g * cg + dcg.mod(e)];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       float mean = sum / (float)ne;
       float sq = 0.f;
-      for (int e = lane; e < ne; e += 32) { float d = sm.C[s * L + e / cg][g * cg + e % cg] - mean; sq = fmaf(d, d, sq); }
+      for (int e = lane; e < ne; e += 32) { float d = sm.C[s * L + dcg.div(e)][g * cg + dcg.mod(e)] - mean; sq = fmaf(d, d, sq); }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
       if (lane == 0) { sm.mean[p] = mean; sm.rstd[p] = 1.0f / sqrtf(sq / (float)ne + 1e-5f); }
@@ -195,11 +208,11 @@ __global__ void __launch_bounds__(NT) conv_ffma_kernel(ConvArgs a) {
     __syncthreads();
     float4 gm = __ldg(reinterpret_cast<const float4*>(a.gn_gamma + gc));
     float4 bt = __ldg(reinterpret_cast<const float4*>(a.gn_beta + gc));
-    const int g = (tx * 4) / cg;
+    const int g = dcg.div(tx * 4);
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
       int lr = ty * RM + r;
-      int p = (lr / L) * gpt + g;
+      int p = dL.div(lr) * gpt + g;
       float mean = sm.mean[p], rstd = sm.rstd[p];
       acc[r][0] = mish_f((acc[r][0] - mean) * rstd * gm.x + bt.x);
       acc[r][1] = mish_f((acc[r][1] - mean) * rstd * gm.y + bt.y);
