@@ -1059,7 +1059,16 @@ static int plan_impl(b2p_handle h, const b2p_plan_config* pc, const float* x_ini
       ce = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) return (int)ce;
+      if (h->graphs.size() >= 16) {            // a replayable plan holds thousands of kernel nodes: keep the 16 most recent shapes
+        cudaGraphExecDestroy(h->graphs.front().exec);
+        h->graphs.erase(h->graphs.begin());
+      }
       h->graphs.push_back(GraphEntry{key, exec, nl});
+      ge = &h->graphs.back();
+    } else if (ge != &h->graphs.back()) {      // most recently used last
+      GraphEntry hit = *ge;
+      h->graphs.erase(h->graphs.begin() + (ge - h->graphs.data()));
+      h->graphs.push_back(hit);
       ge = &h->graphs.back();
     }
     B2P_CUDA_TRY(cudaGraphLaunch(ge->exec, s));

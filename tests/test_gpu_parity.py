@@ -648,3 +648,21 @@ def test_weight_updates_reach_the_device_copy():
     assert torch.equal(m(x, f, t), base)
     m.double().float()                                    # conversion round trip replaces the tensors
     assert torch.equal(m(x, f, t), base)
+
+
+def test_plan_graph_cache_is_bounded_and_reusable():
+    """More distinct (batch, T) shapes than the graph cache holds: results stay right and an evicted shape is recaptured."""
+    model, sd = get_model("NO_GUIDANCE")
+    sched = make_sched("guidance_ddim")
+    inp = W.synth_inputs(24, 0, 83)
+    x, f = inp["x"].to(DEV), inp["feat"].to(DEV)
+    first = {}
+    for B in list(range(5, 24)) + [5, 6, 23]:                   # 19 shapes (> 16), then the oldest ones again
+        planner = P.DiffusionPlanner(model, sched, _cfg("NO_GUIDANCE", 3))
+        out = planner.plan(x[:B], f[:B])
+        if B in first:
+            assert torch.equal(out, first[B]), B
+        first[B] = out.clone()
+    ref = OP.plan(sd, "NO_GUIDANCE", "guidance_ddim", inp["x"][:5], inp["feat"][:5], 3)
+    d = (first[5].cpu() - ref).abs()
+    assert float(d[..., :2].max()) <= 1e-3 * MAGIC and float(d[..., 2:].max()) <= 1e-3
