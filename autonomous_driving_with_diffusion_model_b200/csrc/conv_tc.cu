@@ -225,7 +225,7 @@ struct __align__(16) TcShared {
 // Shared-memory map (dynamic, 1024-aligned base):
 //   [0, 224 KB)            TMA ring (TN == 64) — or ring in [0, 208 KB) and, for TN < 64, the cluster exchange buffer
 //                          cx[2][4][128] (GroupNorm partials written by PEER CTAs, so it may never alias live stages) at 208 KB
-//   ring start, reused after the main loop:  xchg[2][128][4] (partials between the column slices of this CTA), head[128][4][8]
+//   ring start, reused after the main loop:  xchg[2][4][128] (partials between the column slices of this CTA), head[4][8][128], head weights
 //   [224 KB, ...)          TcShared (barriers, TMEM base, epilogue vectors)
 //   TN == 16 uses a 106 KB ring (+ cx) so that TWO CTAs fit on an SM: a 128-CTA layer then leaves room for the next layer's
 //   CTAs to become resident early (programmatic dependent launch) instead of waiting for SMs to drain.
@@ -238,7 +238,7 @@ template <int TN> struct SmemPlan {
 };
 constexpr int EPI_XCHG_BYTES = 2 * TC_M * 4 * 4;
 struct EpiScratch {
-  float (*xchg)[TC_M][4];   // [pass][row][slice]
+  float (*xchg)[4][TC_M];   // [pass][slice][row]: row fastest, so the lanes of a warp hit distinct banks
   float2 (*cx)[TC_M];       // [source CTA][row] = (mean, M2), written by the peers (st.async)
   uint64_t* gn_bar;
 };
@@ -276,16 +276,16 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
     m2[g] = q;
   }
   if (SL > 1) {                                      // merge the slices of this CTA (NG == 1 here)
-    es.xchg[0][row][slice] = mean[0];
-    es.xchg[1][row][slice] = m2[0];
+    es.xchg[0][slice][row] = mean[0];
+    es.xchg[1][slice][row] = m2[0];
     __syncthreads();
     const int base = slice & ~(SL - 1);
     float ms = 0.f, qs = 0.f;
 #pragma unroll
-    for (int j = 0; j < SL; ++j) ms += es.xchg[0][row][base + j];
+    for (int j = 0; j < SL; ++j) ms += es.xchg[0][base + j][row];
     const float mu = ms * (1.0f / SL);
 #pragma unroll
-    for (int j = 0; j < SL; ++j) { float d = es.xchg[0][row][base + j] - mu; qs += es.xchg[1][row][base + j] + (float)(W * L) * d * d; }
+    for (int j = 0; j < SL; ++j) { float d = es.xchg[0][base + j][row] - mu; qs += es.xchg[1][base + j][row] + (float)(W * L) * d * d; }
     mean[0] = mu; m2[0] = qs;
   }
   if (CN > 1) {                                      // merge the CTAs of the cluster sub-group
@@ -497,10 +497,11 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     const bool row_ok = grow < a.nrows;
     const int b = (int)(grow >> a.log2L), l = (int)(grow & (L - 1));
     EpiScratch es;
-    es.xchg = reinterpret_cast<float (*)[TC_M][4]>(smem);
+    es.xchg = reinterpret_cast<float (*)[4][TC_M]>(smem);
     es.cx = reinterpret_cast<float2 (*)[TC_M]>(smem + a.ring);
     es.gn_bar = &sh->gn_bar;
-    float (*headp)[4][8] = reinterpret_cast<float (*)[4][8]>(smem + EPI_XCHG_BYTES);
+    float (*headp)[8][TC_M] = reinterpret_cast<float (*)[8][TC_M]>(smem + EPI_XCHG_BYTES);   // [slice][d][row]: row fastest, conflict-free
+    float* headw = reinterpret_cast<float*>(smem + EPI_XCHG_BYTES + TC_M * 4 * 8 * 4);   // [8][64] head weights + [8] bias, after headp
     const int gcol = n0 + col0;
     const int n_out = (a.dbg & 2) ? 0 : a.n_out;
     const bool has_res = res_iters > 0;
@@ -542,6 +543,9 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
         }
       }
     }
+    // fused head: this thread's element of the 1x1 head weights / bias, in flight during the accumulator wait
+    const float hw_reg = (a.headW && (int)threadIdx.x < 64 * a.head_dim) ? __ldg(a.headW + threadIdx.x) : 0.f;
+    const float hb_reg = (a.headW && (int)threadIdx.x < a.head_dim) ? __ldg(a.headB + threadIdx.x) : 0.f;
     mbar_wait_sleep(&sh->tmem_full, 0);
     tc_fence_after();
     if (threadIdx.x == 64) TC_T(4);
@@ -644,16 +648,29 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
         }
       }
       if (a.headW) {   // fused 1x1 head (TN == Cout == 64): partial dot products per column slice, summed by slice 0
-        for (int d = 0; d < a.head_dim; ++d) {
-          float s = 0.f;
+        // head weights as [d][64] (+ bias) in the idle operand ring (a TN == 64 launch has no peers writing into it); the
+        // values were fetched before the accumulator wait, so no global latency is exposed here
+        const int hd = a.head_dim;
+        if (threadIdx.x < 64 * hd) { const int c = threadIdx.x / hd, d = threadIdx.x - c * hd; headw[d * 64 + c] = hw_reg; }
+        if (threadIdx.x < 8) headw[8 * 64 + threadIdx.x] = hb_reg;
+        __syncthreads();
 #pragma unroll
-          for (int c = 0; c < EC; ++c) s = fmaf(v[c], __ldg(a.headW + (col0 + c) * a.head_dim + d), s);
-          headp[r][slice][d] = s;
+        for (int d = 0; d < 8; ++d) {
+          if (d < hd) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < EC; c += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(headw + d * 64 + col0 + c);
+              s = fmaf(v[c], w4.x, fmaf(v[c + 1], w4.y, fmaf(v[c + 2], w4.z, fmaf(v[c + 3], w4.w, s))));
+            }
+            headp[slice][d][r] = s;
+          }
         }
         __syncthreads();
         if (slice == 0 && ok) {
-          for (int d = 0; d < a.head_dim; ++d)
-            a.head_out[(size_t)grow * a.head_dim + d] = __ldg(a.headB + d) + headp[r][0][d] + headp[r][1][d] + headp[r][2][d] + headp[r][3][d];
+#pragma unroll
+          for (int d = 0; d < 8; ++d)
+            if (d < hd) a.head_out[(size_t)grow * hd + d] = headw[8 * 64 + d] + headp[0][d][r] + headp[1][d][r] + headp[2][d][r] + headp[3][d][r];
         }
       }
     }

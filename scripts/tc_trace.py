@@ -47,5 +47,7 @@ for i, r in enumerate(rows):
     tails.append(tail); rels.append(rel)
     print(f"{i:4d}   " + "  ".join(f"{v:16d}" for v in d) + f"   {nxt:8d} {tail:8d} {rel:8d}")
 print("sum    " + "  ".join(f"{int(v):16d}" for v in tot))
+hr = rows[-1]
+print(f"head layer (TN=64): GroupNorm done {hr[5]-hr[4]}, end {hr[6]-hr[4]} cycles after the accumulators were ready")
 print(f"tail total {sum(tails) / 1e3:.1f} us, release total {sum(rels) / 1e3:.1f} us (includes non-tcgen05 kernels between steps)")
 print("us@1.965GHz " + "  ".join(f"{v / 1965:16.1f}" for v in tot))
