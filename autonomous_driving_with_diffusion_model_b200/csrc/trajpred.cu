@@ -14,13 +14,14 @@ constexpr int TP_HD = 16;     // head dim
 constexpr int TP_FF = 256;
 constexpr int TP_MAXS = 16;   // tokens (horizon - 1 <= 16)
 constexpr int TP_NT = 512;
+constexpr int TP_QS = 3 * TP_D + 4;   // row stride of the qkv buffers: 196 = 4 (mod 32), so the score loops (one key row per lane) spread over 8 banks instead of 1
 
 // Shared-memory plan: 103.5 KB, so TWO trajectories (CTAs) share an SM and 256 of them fit the chip in one wave.  Only what
 // the backward pass needs is kept per layer (qkv, attention probabilities, the normalised LayerNorm inputs and the FFN
 // input x1 — the FFN pre-activation is recomputed from x1 in the backward pass, bit-identical to the forward value);
 // everything else lives in scratch buffers that the forward and the backward pass use for different things.
 struct LayerAct {            // saved for backward (floats, S = tokens)
-  float qkv[TP_MAXS * 3 * TP_D];
+  float qkv[TP_MAXS * TP_QS];
   float P[TP_H * TP_MAXS * TP_MAXS];
   float xh1[TP_MAXS * TP_D];   // normalised (pre-affine) LN1
   float x1[TP_MAXS * TP_D];    // LN1 output = FFN input
@@ -129,12 +130,12 @@ __device__ void encoder_layer_fwd(TpSmem& sm, int l, const TrajPredWeights::Laye
   LayerAct& A = sm.L[l];
   const float* xin = sm.xin(l);
   float* att = sm.att();
-  linear<false, 3 * TP_D>(xin, TP_D, w.qkv_wt, w.qkv_b, A.qkv, 3 * TP_D, S, TP_D);
+  linear<false, 3 * TP_D>(xin, TP_D, w.qkv_wt, w.qkv_b, A.qkv, TP_QS, S, TP_D);
   __syncthreads();
   for (int i = threadIdx.x; i < TP_H * S * S; i += TP_NT) {   // scores
     int h = i / (S * S), r = (i / S) % S, c = i % S;
-    const float* q = A.qkv + r * 3 * TP_D + h * TP_HD;
-    const float* k = A.qkv + c * 3 * TP_D + TP_D + h * TP_HD;
+    const float* q = A.qkv + r * TP_QS + h * TP_HD;
+    const float* k = A.qkv + c * TP_QS + TP_D + h * TP_HD;
     float s = 0.f;
 #pragma unroll
     for (int e = 0; e < TP_HD; ++e) s = fmaf(q[e], k[e], s);
@@ -155,7 +156,7 @@ __device__ void encoder_layer_fwd(TpSmem& sm, int l, const TrajPredWeights::Laye
     int r = i / TP_D, col = i % TP_D, h = col / TP_HD;
     const float* p = A.P + (size_t)(h * TP_MAXS + r) * TP_MAXS;
     float s = 0.f;
-    for (int c = 0; c < S; ++c) s = fmaf(p[c], A.qkv[c * 3 * TP_D + 2 * TP_D + col], s);
+    for (int c = 0; c < S; ++c) s = fmaf(p[c], A.qkv[c * TP_QS + 2 * TP_D + col], s);
     att[i] = s;
   }
   __syncthreads();
@@ -202,14 +203,14 @@ __device__ void encoder_layer_bwd(TpSmem& sm, int l, const TrajPredWeights::Laye
     int h = i / (S * S), r = (i / S) % S, c = i % S;
     float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < TP_HD; ++e) s = fmaf(sm.gb[r * TP_D + h * TP_HD + e], A.qkv[c * 3 * TP_D + 2 * TP_D + h * TP_HD + e], s);
+    for (int e = 0; e < TP_HD; ++e) s = fmaf(sm.gb[r * TP_D + h * TP_HD + e], A.qkv[c * TP_QS + 2 * TP_D + h * TP_HD + e], s);
     sm.gP[(h * TP_MAXS + r) * TP_MAXS + c] = s;
   }
   for (int i = threadIdx.x; i < S * TP_D; i += TP_NT) {        // dV[c][col] = sum_r P[h][r][c] datt[r][col]
     int c = i / TP_D, col = i % TP_D, h = col / TP_HD;
     float s = 0.f;
     for (int r = 0; r < S; ++r) s = fmaf(A.P[(h * TP_MAXS + r) * TP_MAXS + c], sm.gb[r * TP_D + col], s);
-    gqkv[c * 3 * TP_D + 2 * TP_D + col] = s;
+    gqkv[c * TP_QS + 2 * TP_D + col] = s;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < TP_H * S; i += TP_NT) {        // softmax backward per row -> dS (scaled by 1/4)
@@ -223,14 +224,14 @@ __device__ void encoder_layer_bwd(TpSmem& sm, int l, const TrajPredWeights::Laye
     int r = i / TP_D, col = i % TP_D, h = col / TP_HD;
     float dq = 0.f, dk = 0.f;
     for (int c = 0; c < S; ++c) {
-      dq = fmaf(sm.gP[(h * TP_MAXS + r) * TP_MAXS + c], A.qkv[c * 3 * TP_D + TP_D + col], dq);
-      dk = fmaf(sm.gP[(h * TP_MAXS + c) * TP_MAXS + r], A.qkv[c * 3 * TP_D + col], dk);
+      dq = fmaf(sm.gP[(h * TP_MAXS + r) * TP_MAXS + c], A.qkv[c * TP_QS + TP_D + col], dq);
+      dk = fmaf(sm.gP[(h * TP_MAXS + c) * TP_MAXS + r], A.qkv[c * TP_QS + col], dk);
     }
-    gqkv[r * 3 * TP_D + col] = dq;
-    gqkv[r * 3 * TP_D + TP_D + col] = dk;
+    gqkv[r * TP_QS + col] = dq;
+    gqkv[r * TP_QS + TP_D + col] = dk;
   }
   __syncthreads();
-  linear<true, TP_D>(gqkv, 3 * TP_D, w.qkv_w, nullptr, sm.gx, TP_D, S, 3 * TP_D);  // gx += dqkv Wqkv (raw [192][64])
+  linear<true, TP_D>(gqkv, TP_QS, w.qkv_w, nullptr, sm.gx, TP_D, S, 3 * TP_D);  // gx += dqkv Wqkv (raw [192][64])
   __syncthreads();
 }
 
