@@ -12,6 +12,7 @@
 // channels) spans cg/NC CTAs: they form a thread-block cluster and merge their (mean, M2) through distributed shared
 // memory with the parallel-variance formula.  All sums are combined in a fixed order: results are run-to-run identical.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b2p {
 
@@ -68,7 +69,7 @@ __device__ __forceinline__ void gv_cp16(float* dst, const float* src) {
 __device__ __forceinline__ void gv_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct GvStatic {
-  float P[GV_NW * GV_MAXL];      // per-K-slice partial conv outputs: [slice][row][channel]
+  float P[GV_NW * GV_MAXL];      // per-K-slice partial conv outputs: [slice][row][channel]: (16 CW / NC) slices x L x NC <= 256 floats
   float RP[GV_NW * GV_MAXL];     // same for the residual 1x1 conv
   float O[GV_MAXL * GV_MAXNC];   // conv outputs (+bias): [row][channel]
   int src[5][GV_MAXL];           // offset (floats) into X of the input row feeding (tap, output row); zero row when padding
@@ -140,40 +141,49 @@ __device__ __forceinline__ int gv_row(int lane) {
   return r;
 }
 
-// partial dot products of one channel with RT output rows over K slice `ks` of `ns` (K = taps x C_in, flat; float4
-// granules are dealt round-robin to the ns x 32 lanes working on the channel).  Leaves this lane's row total in acc[0].
-template <int RT, bool VEC>
-__device__ __forceinline__ void gv_dot(const float* __restrict__ wcol, const float* __restrict__ X, int Keff, int Cin,
-                                       const int (*src)[GV_MAXL], int lane, int ks, int ns, float (&acc)[RT]) {
+// partial dot products of CW adjacent channels with RT output rows over K slice `ks` of `ns` (K = taps x C_in, flat; float4
+// granules are dealt round-robin to the ns x 32 lanes working on the channels).  With CW = 2 every activation granule read
+// from shared memory feeds two channels.  acc[cw * RT + r]; afterwards lane l holds in acc[0] the warp total of the
+// flattened index gv_row<CW * RT>(l).
+template <int RT, int CW, bool VEC>
+__device__ __forceinline__ void gv_dot(const float* __restrict__ wcol, int wstride, const float* __restrict__ X, int Keff, int Cin,
+                                       const int (*src)[GV_MAXL], int lane, int ks, int ns, float (&acc)[CW * RT]) {
 #pragma unroll
-  for (int r = 0; r < RT; ++r) acc[r] = 0.f;
+  for (int r = 0; r < CW * RT; ++r) acc[r] = 0.f;
   const GvDiv dc = gv_div(Cin);
   if (VEC) {
 #pragma unroll 2
     for (int k = (ks * 32 + lane) * 4; k < Keff; k += 128 * ns) {
       const int jj = dc.div(k), ci = k - jj * Cin;          // C_in % 4 == 0: a float4 never straddles two taps
-      const float4 w = *reinterpret_cast<const float4*>(wcol + k);
+      float4 w[CW];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) w[c] = *reinterpret_cast<const float4*>(wcol + c * wstride + k);
 #pragma unroll
       for (int r = 0; r < RT; ++r) {
         const float4 x = *reinterpret_cast<const float4*>(X + src[jj][r] + ci);
-        acc[r] += fmaf(w.x, x.x, w.y * x.y) + fmaf(w.z, x.z, w.w * x.w);
+#pragma unroll
+        for (int c = 0; c < CW; ++c) acc[c * RT + r] += fmaf(w[c].x, x.x, w[c].y * x.y) + fmaf(w[c].z, x.z, w[c].w * x.w);
       }
     }
   } else {
     for (int k = ks * 32 + lane; k < Keff; k += 32 * ns) {
       const int jj = dc.div(k), ci = k - jj * Cin;
-      const float w = wcol[k];
 #pragma unroll
-      for (int r = 0; r < RT; ++r) acc[r] = fmaf(w, X[src[jj][r] + ci], acc[r]);
+      for (int r = 0; r < RT; ++r) {
+        const float x = X[src[jj][r] + ci];
+#pragma unroll
+        for (int c = 0; c < CW; ++c) acc[c * RT + r] = fmaf(wcol[c * wstride + k], x, acc[c * RT + r]);
+      }
     }
   }
-  gv_reduce<RT>(acc, lane, 16);
+  gv_reduce<CW * RT>(acc, lane, 16);
 }
 
 __host__ __device__ inline int gv_pad4(int n) { return (n + 3) & ~3; }
 
 // NC = channels per CTA (power of two <= 8), cls = CTAs per cluster (= GroupNorm group size / NC, or 1)
-template <int RT>
+// CW = output channels per warp (2 when the CTA owns >= 2 channels: activation reads from shared memory are shared)
+template <int RT, int CW>
 __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, int cls, int trace_id) {
   extern __shared__ __align__(16) float dyn[];
   __shared__ GvStatic st;
@@ -191,7 +201,8 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
   const int L = a.Lout, Lin = a.Lin;
   const int nc = min(NC, a.Cout - col0);
   const int lnc = 31 - __clz(NC);                     // NC is a power of two
-  const int ns = GV_NW >> lnc;                        // K slices per channel
+  const int lng = lnc - (CW == 2 ? 1 : 0);            // log2(channel groups of CW channels)
+  const int ns = GV_NW >> lng;                        // K slices per channel group
   const bool vecW = (Cin & 3) == 0, vecR = (RCin & 3) == 0;
   // dynamic shared memory carve-up (every region 16-byte aligned)
   float* Wsm = dyn;                                   // [NC][Keff]
@@ -240,19 +251,21 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
   __syncthreads();
   GV_T(3);
 
-  // ---- one warp per (K slice, output channel) ----
+  // ---- one warp per (K slice, group of CW output channels) ----
   {
-    const int ch = warp & (NC - 1), ks = warp >> lnc;
-    const int myrow = gv_row<RT>(lane);
-    const bool writer = (lane & (32 / RT - 1)) == 0 && myrow < L;
-    float acc[RT];
-    if (ch < nc) {
-      if (vecW) gv_dot<RT, true>(Wsm + ch * Keff, X, Keff, Cin, st.src, lane, ks, ns, acc);
-      else gv_dot<RT, false>(Wsm + ch * Keff, X, Keff, Cin, st.src, lane, ks, ns, acc);
+    constexpr int NV = CW * RT;
+    const int ch0 = (warp & ((NC >> (CW == 2 ? 1 : 0)) - 1)) * CW, ks = warp >> lng;
+    const int f = gv_row<NV>(lane);                    // flattened (channel-in-group, row) this lane ends up holding
+    const int ch = ch0 + f / RT, myrow = f % RT;
+    const bool writer = (lane & (32 / NV - 1)) == 0 && myrow < L;
+    float acc[NV];
+    if (ch0 < nc) {                                     // nc == NC whenever CW == 2 (checked by the launcher)
+      if (vecW) gv_dot<RT, CW, true>(Wsm + ch0 * Keff, Keff, X, Keff, Cin, st.src, lane, ks, ns, acc);
+      else gv_dot<RT, CW, false>(Wsm + ch0 * Keff, Keff, X, Keff, Cin, st.src, lane, ks, ns, acc);
       if (writer) st.P[(ks * L + myrow) * NC + ch] = acc[0];
       if (a.resWk) {
-        if (vecR) gv_dot<RT, true>(RWsm + ch * RCin, RX, RCin, RCin, st.idsrc, lane, ks, ns, acc);
-        else gv_dot<RT, false>(RWsm + ch * RCin, RX, RCin, RCin, st.idsrc, lane, ks, ns, acc);
+        if (vecR) gv_dot<RT, CW, true>(RWsm + ch0 * RCin, RCin, RX, RCin, RCin, st.idsrc, lane, ks, ns, acc);
+        else gv_dot<RT, CW, false>(RWsm + ch0 * RCin, RCin, RX, RCin, RCin, st.idsrc, lane, ks, ns, acc);
         if (writer) st.RP[(ks * L + myrow) * NC + ch] = acc[0];
       }
     } else if (writer) {
@@ -344,16 +357,16 @@ static size_t gv_smem_floats(const ConvArgs& a, int nc) {
   return (size_t)gv_pad4(nc * Keff) + gv_pad4(nc * RCin) + gv_pad4((a.Lin + 1) * Cin) + gv_pad4(a.Lout * RCin);
 }
 
-template <int RT>
+template <int RT, int CW>
 static int launch_rt(const ConvArgs& a, int nc, int cls, size_t smem, cudaStream_t s) {
   static size_t configured[64] = {};     // per device: function attributes belong to the device's context
   int dev = 0;
   B2P_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || smem > configured[dev]) {
-    B2P_CUDA_TRY(cudaFuncSetAttribute(conv_gemv_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2P_CUDA_TRY(cudaFuncSetAttribute(conv_gemv_kernel<RT, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < 64) configured[dev] = smem;
   }
-  prefer_max_smem_carveout((const void*)conv_gemv_kernel<RT>);
+  prefer_max_smem_carveout((const void*)conv_gemv_kernel<RT, CW>);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((a.Cout + nc - 1) / nc, a.nrows / a.Lout); cfg.blockDim = dim3(GV_NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[2];
@@ -366,7 +379,7 @@ static int launch_rt(const ConvArgs& a, int nc, int cls, size_t smem, cudaStream
 #ifdef B2P_GV_TRACE
   trace_id = gv_trace_launch++ & 8191;
 #endif
-  return (int)cudaLaunchKernelEx(&cfg, conv_gemv_kernel<RT>, a, nc, cls, trace_id);
+  return (int)cudaLaunchKernelEx(&cfg, conv_gemv_kernel<RT, CW>, a, nc, cls, trace_id);
 }
 
 bool conv_gemv_applicable(const ConvArgs& a) {
@@ -383,10 +396,19 @@ int launch_conv_gemv(const ConvArgs& a, cudaStream_t s) {
   const int nc = gv_pick_nc(a);
   const size_t smem = gv_smem_floats(a, nc) * sizeof(float);
   const int cls = a.gn_gamma ? a.cg / nc : 1;               // CTAs sharing one GroupNorm group
-  if (a.Lout <= 2) return launch_rt<2>(a, nc, cls, smem, s);
-  if (a.Lout <= 4) return launch_rt<4>(a, nc, cls, smem, s);
-  if (a.Lout <= 8) return launch_rt<8>(a, nc, cls, smem, s);
-  return launch_rt<16>(a, nc, cls, smem, s);
+  // two channels per warp when the CTA owns >= 2 complete channels (CW * RT accumulators must fit a warp's butterfly)
+  // Two channels per warp halve the activation re-reads from shared memory but cost 64 instead of 40 registers per thread: a win
+  // while the launch has at most one CTA per SM (1-2 samples: -4 % / -10 % per iteration), a loss once two CTAs share an SM and
+  // the following layers' early-resident CTAs no longer fit the register file (4 samples: +7 %).
+  static int cw_env = -1;
+  if (cw_env < 0) { const char* e = getenv("B2P_GV_CW"); cw_env = e ? atoi(e) : 0; }
+  const int ctas = ((a.Cout + nc - 1) / nc) * (a.nrows / a.Lout);
+  const bool two = nc >= 2 && a.Cout % nc == 0 && a.Lout <= GV_MAXL / 2 &&   // (partials: 16 * CW * L floats must fit P)
+                   (cw_env == 2 || (cw_env == 0 && ctas <= 148));
+  if (a.Lout <= 2) return two ? launch_rt<2, 2>(a, nc, cls, smem, s) : launch_rt<2, 1>(a, nc, cls, smem, s);
+  if (a.Lout <= 4) return two ? launch_rt<4, 2>(a, nc, cls, smem, s) : launch_rt<4, 1>(a, nc, cls, smem, s);
+  if (a.Lout <= 8) return two ? launch_rt<8, 2>(a, nc, cls, smem, s) : launch_rt<8, 1>(a, nc, cls, smem, s);
+  return launch_rt<16, 1>(a, nc, cls, smem, s);
 }
 
 }  // namespace b2p
