@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
   if (eact && gn) { e_gamma = __ldg(a.gn_gamma + ec); e_beta = __ldg(a.gn_beta + ec); }
   const float e_bias = (eact && a.bias) ? __ldg(a.bias + ec) : 0.f;
   const float e_rb = (eact && a.resWk) ? __ldg(a.resB + ec) : 0.f;
+  if (cls > 1) gv_cluster_wait();   // every peer is running and has initialised its mbarrier (off the dependency chain: before the wait)
   GV_T(1);
   pdl_wait();                    // inputs are produced by the preceding kernel
   GV_T(2);
@@ -308,14 +309,11 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
 #pragma unroll
       for (int k = 16; k > 0; k >>= 1) q += __shfl_xor_sync(0xffffffffu, q, k);
       if (cls > 1) {
-        gv_cluster_wait();                                  // every peer is running and has initialised its mbarrier
         if (lane < cls)                                     // publish this part's (mean, M2) to every CTA of the cluster
           gv_st_async(&st.cx[blockIdx.x % cls], &st.bar, (uint32_t)lane, mean, q);
       } else if (lane == 0) {
         st.mean = mean; st.m2 = q;
       }
-    } else if (cls > 1) {
-      gv_cluster_wait();                                    // (every thread that arrived also waits once)
     }
     if (cls > 1) {
       gv_bar_wait(&st.bar);                                 // all cls parts have landed in this CTA's cx (no CTA exits before that)
@@ -327,8 +325,6 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
       __syncthreads();
       mu = st.mean; m2 = st.m2;
     }
-  } else if (cls > 1) {
-    gv_cluster_wait();
   }
   GV_T(5);
 

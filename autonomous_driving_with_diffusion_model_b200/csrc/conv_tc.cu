@@ -291,7 +291,6 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
   if (CN > 1) {                                      // merge the CTAs of the cluster sub-group
     // every CTA pushes its per-row (mean, M2) into all CN CTAs with asynchronous stores that signal the receiver's
     // mbarrier; nobody waits for a cluster-wide barrier, each CTA only waits until ITS CN x 128 pairs have landed
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers are running and their mbarrier is initialised (arrive: prologue)
     if ((slice & (SL - 1)) == 0) {
       const uint32_t dst = smem_u32(&es.cx[crank][row]), bar = smem_u32(es.gn_bar);
 #pragma unroll
@@ -370,7 +369,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (a.cluster_n > 1 && a.gn_gamma) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // "my GroupNorm mbarrier is ready" (waited for in group_norm_mish)
+  if (a.cluster_n > 1 && a.gn_gamma) cluster_sync_all();   // every peer's GroupNorm mbarrier is ready before anyone sends (in the prologue: off the dependency chain)
   const bool mcast = CL > a.cluster_n;             // activation multicast active (off by default: measured slower)
   if (mcast) cluster_sync_all();                   // peers' barriers are initialised before anyone multicasts / commits into them
   const uint32_t tmem_base = sh->tmem_base;
