@@ -5,12 +5,14 @@
 //
 // With L_out <= 16 rows per sample the layer is a GEMV and the work is streaming the layer's weights.  Grid =
 // (C_out / NC, samples): a CTA owns NC in {1,2,4,8} output channels of one sample, NC chosen so that every layer runs on
-// ~64 CTAs per sample; its 16 warps are NC channels x 16/NC slices of K = taps x C_in.  The CTA's weight slice
+// ~64 CTAs per sample; its 16 warps are groups of 1-2 channels x slices of K = taps x C_in (two channels per warp, sharing
+// every activation read, while the launch has at most one CTA per SM).  The CTA's weight slice
 // ([NC][K] fp32, from a K-major copy of the layer's weights) is fetched with cp.async BEFORE the programmatic-dependency
 // wait, and the kernel releases its dependents at its very first instruction, so weight streaming runs several layers
 // ahead of the dependency chain; after the wait only the (tiny) input activation is read.  A GroupNorm group (C_out/8
-// channels) spans cg/NC CTAs: they form a thread-block cluster and merge their (mean, M2) through distributed shared
-// memory with the parallel-variance formula.  All sums are combined in a fixed order: results are run-to-run identical.
+// channels) spans cg/NC CTAs: they form a thread-block cluster and push their (mean, M2) into each other's shared memory
+// with st.async stores that signal the receiver's mbarrier; the parts are merged with the parallel-variance formula.  All
+// sums are combined in a fixed order: results are run-to-run identical.
 #include "common.cuh"
 #include <stdlib.h>
 
