@@ -11,12 +11,14 @@
 //   M = 128, N = T*TN <= 256, K = 16) computes every Y_t into its own TN-column TMEM block.  The conv sum is a ROW shift
 //   of the accumulator, done in the epilogue with warp shuffles (the L rows of a sample are adjacent lanes); zero padding
 //   is "source lane outside the sample".  The activation tile is loaded once per chunk, not once per tap; no im2col.
-// * precision modes: NSPLIT = 1 -> single bf16 pass;  NSPLIT = 2 -> operands stored as bf16 hi/lo pairs and three MMAs
-//   (hi*hi + lo*hi + hi*lo) accumulate in fp32 in TMEM ("bf16x3", fp32-class parity).
+// * precision modes: NSPLIT = 1 -> single bf16 pass;  NSPLIT = 2 -> operands stored as bf16 hi/lo pairs, the products
+//   hi*hi + lo*hi + hi*lo accumulate in fp32 in TMEM ("bf16x3", fp32-class parity).  W_hi and W_lo are adjacent in N, so
+//   they are TWO instructions: A_hi x [W_hi | W_lo] (the hi*lo products in their own TMEM blocks) and A_lo x W_hi — an
+//   M = 128 MMA fetches its operands from shared memory at ~64 B/clk, so with narrow N the 4 KB A slice is its cost.
 // * tile = 128 rows x TN output channels, TN in {64, 32, 16}: at small batch a layer has few row tiles, so narrow
 //   column tiles are what spreads it over the 148 SMs.  When a GroupNorm group (Cout/8 channels) is wider than TN the
-//   CTAs that share it form a thread-block cluster along N and exchange their per-row partial statistics (a few hundred
-//   bytes) through distributed shared memory.
+//   CTAs that share it form a thread-block cluster along N and push their per-row partial statistics into each other's
+//   shared memory with st.async stores that signal the receiver's mbarrier (no cluster-wide barrier on the critical path).
 // * epilogue on all 16 warps: warp w owns TMEM lane quadrant (w & 3) and column slice (w >> 2) of the tile: tap combine,
 //   bias, GroupNorm(8) by warp shuffles over the L rows of a sample (+ smem / DSMEM exchange between column slices /
 //   CTAs), Mish (SFU), + time embedding terms, + residual (identity or a 1x1 conv accumulated in a further TMEM block),
