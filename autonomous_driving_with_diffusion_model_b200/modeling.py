@@ -13,7 +13,6 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-import os
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import torch

@@ -5,7 +5,6 @@ Tolerances (normalised trajectory units, i.e. before the x23.315 scale):
   * denoiser forward, fp32 mode ..... max-abs <= 1e-4
   * full plan, fp32 mode ............ max-abs <= 1e-3 (north_star bound)
 """
-import json
 import os
 
 import numpy as np
