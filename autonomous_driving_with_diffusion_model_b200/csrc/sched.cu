@@ -186,7 +186,9 @@ extern "C" int b2p_alphas_cumprod(const char* schedule, int32_t n, float beta_st
       betas[i] = (float)(b < 0.999 ? b : 0.999);
     }
   } else if (s == "linear" || s == "scaled_linear") {
-    // torch.linspace(start, end, n, dtype=float32): step = (end-start)/(n-1) in fp32, symmetric fill from both ends
+    // torch.linspace(start, end, n, dtype=float32): step = (end-start)/(n-1) in fp32, symmetric fill from both ends.  torch's CPU
+    // kernel is vectorised (base + step * lane), so its last bit depends on the host ISA: this scalar form agrees to 1 ulp
+    // (tests/test_abi.py).  The shipped schedule (squaredcos_cap_v2) is exact; the Python scheduler classes use torch's betas.
     float a = beta_start, b = beta_end;
     if (s == "scaled_linear") { a = (float)sqrt((double)beta_start); b = (float)sqrt((double)beta_end); }
     float step = n > 1 ? (b - a) / (float)(n - 1) : 0.f;

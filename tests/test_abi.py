@@ -151,3 +151,31 @@ def test_preprocess_frames_argument_checks_without_a_gpu():
     assert lib.b2p_preprocess_frames(C.c_void_p(4096), C.c_void_p(8200), 8, mean, std, None) != 0   # output not 16-byte aligned
     assert lib.b2p_preprocess_frames(C.c_void_p(4096), C.c_void_p(8192), 8, mean, bad, None) != 0   # zero std
     assert lib.b2p_set_small_batch_max(None, 4) != 0
+
+
+def test_schedule_tables_property(lib):
+    """Random (num_train_timesteps, schedule, beta range, inference steps): the C host tables equal the oracle's (which follows
+    diffusers 0.28.0: scheduling_ddim.py betas / set_timesteps 'leading')."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(2, 400), sched=st.sampled_from(["squaredcos_cap_v2", "linear", "scaled_linear"]),
+           b0=st.floats(1e-5, 5e-3), span=st.floats(1e-3, 5e-2), frac=st.floats(0.01, 1.0))
+    def check(n, sched, b0, span, frac):
+        b1 = b0 + span
+        ac = np.empty(n, np.float32)
+        assert lib.b2p_alphas_cumprod(sched.encode(), n, b0, b1, ac.ctypes.data_as(_lib.c_float_p)) == 0
+        want = S.alphas_cumprod(n, sched, b0, b1).numpy()
+        if sched == "squaredcos_cap_v2":
+            assert np.array_equal(ac, want), (n, float(np.abs(ac - want).max()))      # the shipped schedule: Python float math, exact
+        else:
+            # torch.linspace's CPU kernel is vectorised (base + step * lane, width depends on the host's ISA), so its last bit is
+            # machine dependent; the C table uses the scalar formula.  The Python scheduler classes take their betas from torch.
+            assert np.allclose(ac, want, rtol=3e-7, atol=0), (n, sched, b0, b1, float(np.abs(ac - want).max()))
+        n_inf = max(1, min(n, int(round(frac * n))))
+        ts = np.empty(n_inf, np.int64)
+        assert lib.b2p_timesteps(n, n_inf, ts.ctypes.data_as(_lib.c_int64_p)) == 0
+        assert list(ts) == list(S.leading_timesteps(n, n_inf))
+        assert all(0 <= t < n for t in ts) and all(ts[i] > ts[i + 1] for i in range(n_inf - 1)) or n_inf == 1 or len(set(ts)) < n_inf
+
+    check()
