@@ -61,6 +61,17 @@ def peaks():
     return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, source="fallback (B200_PROFILING.md)")
 
 
+def b1_roofline(p50_ms: float, nfe: int, weight_bytes: int, pk: dict) -> dict:
+    """Batch-1 bound: every denoiser evaluation streams the fp32 weights once (the GEMV path computes in
+    exact fp32 whatever the precision mode); achieved = weight bytes x evaluations / p50 plan latency."""
+    achieved = weight_bytes * nfe / (p50_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+            "algorithmic_bytes_per_evaluation": weight_bytes, "evaluations_per_plan": nfe, "peak_source": pk["source"] + ", copy bandwidth",
+            "note": "weights (fp32, K-major) are L2-resident across the iterations, so the HBM copy peak is the conservative denominator; "
+                    "the plan is a chain of ~43 dependent launches per iteration at ~3.9 us each (profiles/r01_gemv_stage_trace_b1.txt), "
+                    "latency-bound, not bandwidth-bound"}
+
+
 def workload_name(a):
     return f"configs/default.yaml {a.mode} {SCHED[a.sched]} T={a.timesteps} B={a.batch}/GPU precomputed-feature (BASELINE.json configs[1])"
 
@@ -98,6 +109,26 @@ def cpu_iterations(a, n_iters: int, B: int):
                 x, _ = S.ddpm_step(cfg, ac, mo, t, x, variance_noise=inp["noise"][i], inpainting=a.sched.startswith("inpainting"))
             x[:, 0, :3] = 0.0
     return (time.perf_counter() - t0) / len(ts)
+
+
+def cpu_config0(reps: int = 3):
+    """BASELINE.json configs[0]: default.yaml, no guidance, DDPM, T=100, batch 1, on the host cores (whole plans, loop only:
+    the image feature is precomputed as on the GPU arm)."""
+    from oracle import plan as OP
+    from oracle import weights as W
+
+    sd = W.make_state_dict("NO_GUIDANCE", seed=0, with_perception=False)
+    inp = W.synth_inputs(1, 100, seed=1)
+    run = lambda: OP.plan(sd, "NO_GUIDANCE", "guidance_ddpm", inp["x"], inp["feat"], 100, noise=inp["noise"])  # noqa: E731
+    run()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t0)
+    ms = statistics.median(ts) * 1e3
+    return {"ms_per_plan_p50": ms, "traj_per_s": 1e3 / ms, "batch": 1, "T": 100, "sched": "guidance_ddpm", "cores": torch.get_num_threads(),
+            "sample": f"{reps} whole plans (oracle port, fp32, precomputed feature)"}
 
 
 def run_reference_arm(a, rank: int):
@@ -325,7 +356,9 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
                      GUIDANCE=dict(USE_COND=mode, FREE_SCALE=7.5, CLASSIFIER_SCALE=15.0,
                                    LOSS_LIST=[["TargetGuidance", []]] if mode == "CLASSIFIER_GUIDANCE" else None))
     model = P.build_model(cfg)
-    model.load_state_dict(W.make_state_dict(mode, seed=0))
+    sd = W.make_state_dict(mode, seed=0)
+    weight_bytes = 4 * sum(int(v.numel()) for k, v in sd.items() if not k.startswith("perception.") and "num_batches_tracked" not in k)
+    model.load_state_dict(sd)
     model = model.to(dev).eval()
     kind = SCHED[a.sched]
     cls = {"guidance_ddim": P.GuidanceDDIMScheduler, "guidance_ddpm": P.GuidanceDDPMScheduler,
@@ -458,6 +491,10 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
             reps += 1
         cpu = {"value": B / (statistics.mean(per) * T), "unit": "trajectories/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{reps} x {n} of the {T} denoising iterations at B={B} (oracle port of the reference PyTorch code, fp32), extrapolated x{T}/{n}"}
+        try:
+            cpu["config0_b1_ddpm100"] = cpu_config0()
+        except Exception as exc:  # report-only figure: never lose the bench line over it
+            cpu["config0_b1_ddpm100"] = {"error": repr(exc)}
 
     if rank == 0:
         pk = peaks()
@@ -491,7 +528,8 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
                                 f"(timed region, CUDA graph replay)",
                          "eager_eval": {"tflops": flops_eval / (eval_ms * 1e-3) / 1e12, "us": eval_ms * 1e3, "launches": eval_launches,
                                         "note": "one denoiser evaluation launched eagerly (no graph), CUDA events, avg of %d" % n_eval}},
-            "latency_b1": {"p50_ms": statistics.median(lat), "p95_ms": sorted(lat)[int(0.95 * len(lat)) - 1], "T": T, "sched": kind},
+            "latency_b1": {"p50_ms": statistics.median(lat), "p95_ms": sorted(lat)[int(0.95 * len(lat)) - 1], "T": T, "sched": kind,
+                           "roofline": b1_roofline(statistics.median(lat), nfe, weight_bytes, pk)},
             "precision": {"mode": a.precision, "parity_bound_max_abs": {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 0.3}[a.precision],
                           "other_modes_traj_per_s_rank0_x_world": others},
         }

@@ -23,5 +23,5 @@ Parity status: the reference has no tests / golden vectors of its own (SURVEY.md
 against outputs of the reference itself executed in the build container (``oracle/make_golden.py``); the
 ``diffusers`` base-class arithmetic is a restatement of the published 0.28.0 algorithm ("parity unpinned" for
 that third-party part: its source is not in the container), self-checked against the known-answer constants
-in ``tests/test_oracle_schedulers.py``.
+in ``tests/test_oracle.py``.
 """
