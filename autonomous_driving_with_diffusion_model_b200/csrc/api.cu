@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "unet_cluster.cuh"
 
 namespace b2p {
 int upload_freq_table(const float* f, int n);
@@ -99,6 +100,10 @@ struct b2p_handle_s {
   std::vector<GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
   int small_batch_max = B2P_SMALL_BATCH_DEFAULT;   // largest evaluation batch that takes the GEMV kernels
+  // EXPERIMENTAL one-cluster-per-trajectory evaluation (unet_cluster.cu), only with B2P_CLUSTER_EVAL=1 in the environment
+  int cluster_eval = 0;
+  UcProgram* d_cprog = nullptr;
+  float* d_cstream = nullptr;
 
   int fail(int code, const std::string& m) { err = m; return code; }
 };
@@ -519,6 +524,122 @@ inline const float* buf_ptr(b2p_handle_s* h, int id, const float* x) {
   return h->d_act + h->bufs[id].off * (size_t)h->cap;
 }
 
+// ---- EXPERIMENTAL: program + per-CTA weight streams of the one-cluster-per-trajectory kernel (unet_cluster.cu) ----
+int pad4i(int n) { return (n + 3) & ~3; }
+
+// host part: the program table and the 16 per-CTA weight streams (pure host code: also driven by tests/native/uc_emulate.cu)
+int build_cluster_program_host(b2p_handle_s* h, UcProgram& pg, std::vector<float>& stream) {
+  if (h->cfg.guidance != B2P_NO_GUIDANCE || h->H > UC_MAXL || (int)h->ops.size() > UC_MAXOPS) return B2P_ERR_INVALID_ARG;
+  memset(&pg, 0, sizeof(pg));
+  const int nops = (int)h->ops.size();
+  auto bid = [](int id) { return id == BUF_X ? 0 : id + 1; };   // buffer index: 0 = input trajectory, i + 1 = bufs[i]
+  const int nb = (int)h->bufs.size() + 1;
+  std::vector<int> last(nb, -1), slot_of(nb, -1);
+  for (int i = 0; i < nops; ++i) {
+    const LayerOp& op = h->ops[i];
+    const int ids[5] = {op.in0, op.in1, op.res_id, op.resW != NPOS ? op.rin0 : BUF_NONE, op.resW != NPOS ? op.rin1 : BUF_NONE};
+    for (int id : ids) if (id != BUF_NONE) last[bid(id)] = i;
+  }
+  int owner[UC_NSLOT];
+  for (int s = 0; s < UC_NSLOT; ++s) owner[s] = -1;
+  slot_of[0] = 0; owner[0] = 0; pg.x_slot = 0;
+  auto slot = [&](int id) { return id == BUF_NONE ? -1 : slot_of[bid(id)]; };
+  struct ChunkSrc { int op, is_res, k0, klen, kstride; };
+  std::vector<ChunkSrc> csrc;
+  int off = 0;
+  for (int i = 0; i < nops; ++i) {
+    const LayerOp& op = h->ops[i];
+    for (int s = 0; s < UC_NSLOT; ++s) if (owner[s] >= 0 && last[owner[s]] < i) owner[s] = -1;   // no longer read by op i or later
+    int os = -1;
+    for (int s = 0; s < UC_NSLOT; ++s) if (owner[s] < 0) { os = s; break; }
+    if (os < 0 || op.out == BUF_NONE) return B2P_ERR_INVALID_ARG;
+    owner[os] = bid(op.out); slot_of[bid(op.out)] = os;
+    UcOp& u = pg.ops[i];
+    u.in0 = slot(op.in0); u.in1 = slot(op.in1); u.C0 = op.C0; u.C1 = op.C1;
+    u.Lin = op.Lin; u.Lout = op.Lout; u.Cout = op.Cout; u.nc = op.Cout / UC_CL;
+    int jmin = 0, jmax = op.taps - 1;
+    if (!op.transposed && op.stride == 1) {
+      jmin = op.pad - (op.Lout - 1) > 0 ? op.pad - (op.Lout - 1) : 0;
+      jmax = op.pad + op.Lin - 1 < op.taps - 1 ? op.pad + op.Lin - 1 : op.taps - 1;
+    }
+    u.ntaps = jmax - jmin + 1; u.jmin = jmin; u.stride = op.stride; u.pad = op.pad; u.transposed = op.transposed;
+    u.gn = op.gamma != NPOS; u.temb_off = op.temb_off;
+    u.res_id = slot(op.res_id);
+    const bool rc = op.resW != NPOS;
+    u.rin0 = rc ? slot(op.rin0) : -1; u.rin1 = rc ? slot(op.rin1) : -1; u.RC0 = rc ? op.RC0 : 0; u.RC1 = rc ? op.RC1 : 0;
+    u.out = os;
+    u.bias = op.bias != NPOS ? (int)op.bias : -1; u.gamma = u.gn ? (int)op.gamma : -1; u.beta = u.gn ? (int)op.beta : -1;
+    u.resB = rc ? (int)op.resB : -1;
+    u.head = op.headW != NPOS;
+    // shapes the kernel is written for
+    const bool pow2 = (op.Cout & (op.Cout - 1)) == 0;
+    if (!pow2 || op.Cout % (2 * UC_CL) != 0 || u.nc > 32 || op.Lout * u.nc > 64 || op.Lout * op.Cout > UC_SLOT_FLOATS ||
+        op.Lin * (op.C0 > op.C1 ? op.C0 : op.C1) > UC_SLOT_FLOATS || u.ntaps > 5 || u.in0 < 0 ||
+        (op.Lout != 2 && op.Lout != 4 && op.Lout != 8 && op.Lout != 16) || (u.head && op.Cout != 64) || (rc && op.resWk == NPOS) ||
+        op.Wk == NPOS)
+      return B2P_ERR_INVALID_ARG;
+    // chunks: [nc][kstride] blocks of at most one ring stage
+    const int kc_max = (UC_STAGE_FLOATS / u.nc) & ~3;
+    auto add_chunks = [&](int K, int is_res) {
+      int n = 0;
+      for (int k0 = 0; k0 < K; k0 += kc_max, ++n) {
+        const int klen = K - k0 < kc_max ? K - k0 : kc_max;
+        csrc.push_back(ChunkSrc{i, is_res, k0, klen, pad4i(klen)});
+      }
+      return n;
+    };
+    u.chunk0 = (int)csrc.size();
+    u.nchunks = add_chunks(u.ntaps * (op.C0 + op.C1), 0);
+    u.rnchunks = rc ? add_chunks(op.RC0 + op.RC1, 1) : 0;
+    if (u.head) { pg.head_dim = op.head_dim; pg.headWk = (int)op.headWk; pg.headB = (int)op.headB; }
+  }
+  if ((int)csrc.size() > UC_MAXCHUNKS || pg.head_dim <= 0 || pg.head_dim * 64 > 448) return B2P_ERR_INVALID_ARG;
+  pg.n_ops = nops; pg.n_chunks = (int)csrc.size();
+  for (size_t q = 0; q < csrc.size(); ++q) {
+    const ChunkSrc& c = csrc[q];
+    const int nc = pg.ops[c.op].nc;
+    UcChunk& k = pg.chunks[q];
+    k.k0 = c.k0; k.klen = c.klen; k.kstride = c.kstride; k.off = off; k.bytes = nc * c.kstride * 4;
+    off += nc * c.kstride;
+  }
+  pg.stream_floats_per_cta = off;
+  stream.assign((size_t)off * UC_CL, 0.f);
+  const float* P = h->pack_host.data();
+  for (int r = 0; r < UC_CL; ++r)
+    for (size_t q = 0; q < csrc.size(); ++q) {
+      const ChunkSrc& c = csrc[q];
+      const LayerOp& op = h->ops[c.op];
+      const UcOp& u = pg.ops[c.op];
+      float* dst = stream.data() + (size_t)r * off + pg.chunks[q].off;
+      for (int cl = 0; cl < u.nc; ++cl) {
+        const int ch = r * u.nc + cl;
+        // K-major sources: conv [Cout][taps][Cin] (row of channel ch starts at tap jmin), residual [Cout][RCin]
+        const float* src = c.is_res ? P + op.resWk + (size_t)ch * (op.RC0 + op.RC1)
+                                    : P + op.Wk + ((size_t)ch * op.taps + u.jmin) * (op.C0 + op.C1);
+        memcpy(dst + (size_t)cl * c.kstride, src + c.k0, sizeof(float) * c.klen);
+      }
+    }
+  return B2P_OK;
+}
+
+int ensure_cluster_program(b2p_handle_s* h) {
+  if (h->d_cprog) return B2P_OK;
+  std::vector<UcProgram> pg(1);
+  std::vector<float> stream;
+  int rc = build_cluster_program_host(h, pg[0], stream);
+  if (rc) return rc;
+  B2P_CUDA_TRY(cudaMalloc((void**)&h->d_cstream, stream.size() * sizeof(float)));
+  B2P_CUDA_TRY(cudaMemcpy(h->d_cstream, stream.data(), stream.size() * sizeof(float), cudaMemcpyHostToDevice));
+  B2P_CUDA_TRY(cudaMalloc((void**)&h->d_cprog, sizeof(UcProgram)));
+  B2P_CUDA_TRY(cudaMemcpy(h->d_cprog, pg.data(), sizeof(UcProgram), cudaMemcpyHostToDevice));
+  return B2P_OK;
+}
+
+void drop_cluster_program(b2p_handle_s* h) {
+  if (h->d_cprog) { cudaFree(h->d_cprog); h->d_cprog = nullptr; }
+  if (h->d_cstream) { cudaFree(h->d_cstream); h->d_cstream = nullptr; }
+}
+
 // the denoiser on `rows` batch rows; x rows may repeat with period x_period (CFG feeds [x; x]).
 // itab/ttab_row != null: "table mode" (inside a plan, no CFG): the per-block time-MLP outputs were precomputed as an
 // image term itab[rows, temb_total] (step-invariant) and a time vector ttab_row[temb_total] for this step, so the
@@ -549,6 +670,16 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
     if ((rc = launch_conv_ffma(a, s))) return rc;
     ++*launches;
     temb_rows = h->d_temb;
+  }
+  // EXPERIMENTAL (B2P_CLUSTER_EVAL=1): one launch per evaluation, one 16-CTA cluster per trajectory (unet_cluster.cu)
+  if (h->cluster_eval && rows <= 8 && h->cfg.guidance == B2P_NO_GUIDANCE && x_period == 0 && head_out) {
+    if ((rc = ensure_cluster_program(h))) return h->fail(rc, "cluster evaluation: unsupported architecture");
+    UcLaunch u{};
+    u.prog = h->d_cprog; u.stream = h->d_cstream; u.pack = P; u.x = x; u.temb = temb_rows; u.temb_stride = h->temb_total;
+    u.temb2 = ttab_row; u.head_out = head_out; u.B = rows; u.H = h->H; u.D = h->D;
+    if ((rc = launch_unet_cluster(u, s))) return h->fail(rc, "cluster evaluation launch failed");
+    ++*launches;
+    return B2P_OK;
   }
   // Small batches take the exact-fp32 GEMV program whatever the precision mode: with a handful of trajectories a layer is
   // pure weight streaming, the GEMV kernels prefetch weights layers ahead, and no bf16 splitting is needed.
@@ -701,6 +832,23 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
   return B2P_OK;
 }
 
+// architecture tables and the state_dict slot table of a fresh handle (pure host code)
+int init_handle_host(b2p_handle_s* h, const b2p_model_config* cfg) {
+  h->cfg = *cfg;
+  h->H = cfg->horizon; h->D = cfg->transition_dim; h->dim = cfg->dim; h->nlev = cfg->n_mults;
+  h->chans[0] = h->D;
+  h->temb_total = 0;
+  for (int i = 0; i < h->nlev; ++i) {
+    h->chans[i + 1] = cfg->dim * cfg->dim_mults[i];
+    if (h->chans[i + 1] % 64 != 0) return B2P_ERR_INVALID_ARG;
+  }
+  for (int i = 0; i < h->nlev; ++i) h->temb_total += 2 * h->chans[i + 1];       // downs
+  h->temb_total += 2 * h->chans[h->nlev];                                         // mid
+  for (int u = 0; u < h->nlev - 1; ++u) h->temb_total += 2 * h->chans[h->nlev - 1 - u];  // ups
+  build_slots(h);
+  return B2P_OK;
+}
+
 }  // namespace
 
 // ================================================= C ABI ====================================================
@@ -739,18 +887,8 @@ int b2p_create(const b2p_model_config* cfg, int device, b2p_handle* out) {
   if (prop.major != 10) return B2P_ERR_NO_DEVICE;  // sm_100a cubin only: no fallback
   B2P_CUDA_TRY(cudaSetDevice(device));
   b2p_handle_s* h = new b2p_handle_s();
-  h->cfg = *cfg; h->device = device;
-  h->H = cfg->horizon; h->D = cfg->transition_dim; h->dim = cfg->dim; h->nlev = cfg->n_mults;
-  h->chans[0] = h->D;
-  h->temb_total = 0;
-  for (int i = 0; i < h->nlev; ++i) {
-    h->chans[i + 1] = cfg->dim * cfg->dim_mults[i];
-    if (h->chans[i + 1] % 64 != 0) { delete h; return B2P_ERR_INVALID_ARG; }
-  }
-  for (int i = 0; i < h->nlev; ++i) h->temb_total += 2 * h->chans[i + 1];       // downs
-  h->temb_total += 2 * h->chans[h->nlev];                                         // mid
-  for (int u = 0; u < h->nlev - 1; ++u) h->temb_total += 2 * h->chans[h->nlev - 1 - u];  // ups
-  build_slots(h);
+  h->device = device;
+  if (int rc = init_handle_host(h, cfg)) { delete h; return rc; }
   {  // sinusoidal frequencies, fp32 as torch computes them (modeling/helpers.py:69-71)
     int half = h->dim / 2;
     std::vector<float> f(half);
@@ -760,6 +898,7 @@ int b2p_create(const b2p_model_config* cfg, int device, b2p_handle* out) {
     if (rc) { delete h; return rc; }
   }
   cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+  { const char* e = getenv("B2P_CLUSTER_EVAL"); h->cluster_eval = e ? atoi(e) : 0; }
   *out = h;
   return B2P_OK;
 }
@@ -772,6 +911,7 @@ int b2p_destroy(b2p_handle h) {
   if (h->d_pack16) cudaFree(h->d_pack16);
   if (h->d_ws) cudaFree(h->d_ws);
   if (h->p_x) cudaFree(h->p_x);
+  drop_cluster_program(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
   return B2P_OK;
@@ -811,6 +951,7 @@ int b2p_finalize_weights(b2p_handle h) {
     build_trajpred(h, pk, tp_offs);
   }
   drop_graphs(h);
+  drop_cluster_program(h);         // rebuilt lazily from the new weights
   if (h->d_pack) { B2P_CUDA_TRY(cudaFree(h->d_pack)); h->d_pack = nullptr; }
   B2P_CUDA_TRY(cudaMalloc((void**)&h->d_pack, h->pack_host.size() * sizeof(float)));
   B2P_CUDA_TRY(cudaMemcpy(h->d_pack, h->pack_host.data(), h->pack_host.size() * sizeof(float), cudaMemcpyHostToDevice));
