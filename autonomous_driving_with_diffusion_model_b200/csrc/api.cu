@@ -672,11 +672,11 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
     temb_rows = h->d_temb;
   }
   // EXPERIMENTAL (B2P_CLUSTER_EVAL=1): one launch per evaluation, one 16-CTA cluster per trajectory (unet_cluster.cu)
-  if (h->cluster_eval && rows <= 8 && h->cfg.guidance == B2P_NO_GUIDANCE && x_period == 0 && head_out) {
+  if ((h->cluster_eval & 1) && rows <= 8 && h->cfg.guidance == B2P_NO_GUIDANCE && x_period == 0 && head_out) {
     if ((rc = ensure_cluster_program(h))) return h->fail(rc, "cluster evaluation: unsupported architecture");
     UcLaunch u{};
     u.prog = h->d_cprog; u.stream = h->d_cstream; u.pack = P; u.x = x; u.temb = temb_rows; u.temb_stride = h->temb_total;
-    u.temb2 = ttab_row; u.head_out = head_out; u.B = rows; u.H = h->H; u.D = h->D;
+    u.temb2 = ttab_row; u.head_out = head_out; u.B = rows; u.H = h->H; u.D = h->D; u.dbg = h->cluster_eval & ~1;
     if ((rc = launch_unet_cluster(u, s))) return h->fail(rc, "cluster evaluation launch failed");
     ++*launches;
     return B2P_OK;
@@ -962,6 +962,9 @@ int b2p_finalize_weights(b2p_handle h) {
   // workspace offsets depend on the buffer table: force re-allocation
   if (h->d_ws) { B2P_CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; h->cap = 0; }
   h->finalized = true;
+  // experimental cluster evaluation: its program and weight streams are device allocations, which must exist before a plan is
+  // captured into a CUDA graph (an unsupported architecture is reported by the first evaluation instead)
+  if ((h->cluster_eval & 1) && h->cfg.guidance == B2P_NO_GUIDANCE) (void)ensure_cluster_program(h);
   return B2P_OK;
 }
 

@@ -1,4 +1,9 @@
-// EXPERIMENTAL, OPT-IN (B2P_CLUSTER_EVAL=1), NOT ON ANY DEFAULT PATH, NOT YET VALIDATED ON HARDWARE.
+// EXPERIMENTAL, OPT-IN (B2P_CLUSTER_EVAL=1), NOT ON ANY DEFAULT PATH.
+// Status (round 1, profiles/r01_cluster_eval_experiment.txt): CORRECT on B200 (forward within 7.6e-7 of the GEMV path, DDIM-10
+// plan within 8.4e-7; program builder + algorithm also checked on the CPU by tests/test_cluster_program.py) but NOT YET FASTER:
+// 224 us per denoising iteration against 172 us.  Timing bisect per evaluation: dot products 43 us, DSMEM exchange + cluster
+// barrier 42 us, waiting for weights 13 us, and a 127 us skeleton (tables, ~8 block barriers and one exposed L2 round trip for
+// the per-channel constants per layer, instruction fetch of four inlined variants) that the estimate below did not foresee.
 //
 // Whole-denoiser evaluation (TemporalMapUnet.forward, modeling/temporal.py:197-245, NO_GUIDANCE) of ONE trajectory by ONE
 // thread-block cluster of 16 CTAs in ONE launch, for closed-loop planning (one trajectory per tick,
@@ -13,7 +18,7 @@
 //   * raw conv outputs (+bias) are pushed to all 16 CTAs with DSMEM stores, one cluster barrier per layer, and EVERY CTA
 //     normalises the whole tensor itself (GroupNorm statistics + Mish + time term + residual on <= 1024 elements: two per
 //     thread), so there is no statistics exchange at all ("normalisation at the consumer").
-// Expected: ~1.2 us per layer (cluster barrier 0.25 + block barriers 0.4 + dot 0.3 + epilogue 0.2) => ~50 us per
+// Design estimate (not met, see status): ~1.2 us per layer (cluster barrier 0.25 + block barriers 0.4 + dot 0.3 + epilogue 0.2) => ~50 us per
 // evaluation, with the 2.8 MB-per-CTA weight stream (at ~80 B/clk per SM: ~18 us) hidden underneath.
 //
 // Numerics: exact fp32, same formulas as conv_gemv.cu (two-pass GroupNorm statistics, mish_f, bias before statistics);
@@ -144,7 +149,7 @@ __device__ __forceinline__ void uc_dot(float (&acc)[2 * RT], const float* __rest
 template <int RT>
 __device__ __forceinline__ void uc_consume(float (&acc)[2 * RT], const UcProgram* pg, int nchunks, int& q, float* sm, const float* stream,
                                            unsigned long long* full, const int* t0, const int* t1, int C0, int C1, int ch0, int lane, int ks,
-                                           int ns, int tid) {
+                                           int ns, int tid, int dbg) {
   float* ring = sm + UC_O_RING;
   const int Cin = C0 + C1;
   const int sh = (Cin & (Cin - 1)) == 0 ? 31 - __clz(Cin) : -1;
@@ -152,19 +157,21 @@ __device__ __forceinline__ void uc_consume(float (&acc)[2 * RT], const UcProgram
   for (int c = 0; c < nchunks; ++c, ++q) {
     const UcChunk& ck = pg->chunks[q];
     const int stage = q % UC_NSTAGE;
-    uc_bar_wait(full + stage, (uint32_t)((q / UC_NSTAGE) & 1));
+    if (!(dbg & 8)) uc_bar_wait(full + stage, (uint32_t)((q / UC_NSTAGE) & 1));
     const float* wst = ring + stage * UC_STAGE_FLOATS + ch0 * ck.kstride;
-    if (vec) uc_dot<RT, true>(acc, wst, ck.kstride, ck.k0, ck.klen, sm, t0, t1, C0, Cin, sh, lane, ks, ns);
-    else uc_dot<RT, false>(acc, wst, ck.kstride, ck.k0, ck.klen, sm, t0, t1, C0, Cin, sh, lane, ks, ns);
+    if (!(dbg & 2)) {
+      if (vec) uc_dot<RT, true>(acc, wst, ck.kstride, ck.k0, ck.klen, sm, t0, t1, C0, Cin, sh, lane, ks, ns);
+      else uc_dot<RT, false>(acc, wst, ck.kstride, ck.k0, ck.klen, sm, t0, t1, C0, Cin, sh, lane, ks, ns);
+    }
     __syncthreads();                        // every warp is done with the stage
-    if (tid == 0) uc_issue(pg, q + UC_NSTAGE, stream, ring, full);
+    if (tid == 0 && !(dbg & 8)) uc_issue(pg, q + UC_NSTAGE, stream, ring, full);
   }
 }
 
 // dot-product phase of one op: conv chunks, then the residual 1x1 chunks, from the ring; K-slice partials to P / RP
 template <int RT>
 __device__ __forceinline__ void uc_layer_dot(const UcProgram* pg, const UcOp& o, float* sm, const float* stream, unsigned long long* full, int& q,
-                                             int tid) {
+                                             int tid, int dbg) {
   constexpr int NV = 2 * RT;
   const int warp = tid >> 5, lane = tid & 31;
   const int ng = o.nc >> 1;                 // channel pairs owned by this CTA (power of two, <= 16)
@@ -182,13 +189,13 @@ __device__ __forceinline__ void uc_layer_dot(const UcProgram* pg, const UcOp& o,
   float acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-  uc_consume<RT>(acc, pg, o.nchunks, q, sm, stream, full, t0, t1, o.C0, o.C1, ch0, lane, ks, ns, tid);
+  uc_consume<RT>(acc, pg, o.nchunks, q, sm, stream, full, t0, t1, o.C0, o.C1, ch0, lane, ks, ns, tid, dbg);
   uc_reduce<NV>(acc, lane, 16);
   if (writer) sm[UC_O_P + (ks * o.Lout + myrow) * o.nc + ch] = acc[0];
   if (o.rnchunks > 0) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-    uc_consume<RT>(acc, pg, o.rnchunks, q, sm, stream, full, i0, i1, o.RC0, o.RC1, ch0, lane, ks, ns, tid);
+    uc_consume<RT>(acc, pg, o.rnchunks, q, sm, stream, full, i0, i1, o.RC0, o.RC1, ch0, lane, ks, ns, tid, dbg);
     uc_reduce<NV>(acc, lane, 16);
     if (writer) sm[UC_O_RP + (ks * o.Lout + myrow) * o.nc + ch] = acc[0];
   }
@@ -200,6 +207,7 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
   const int tid = threadIdx.x;
   const int rank = blockIdx.x;              // grid = (UC_CL, B), cluster = (UC_CL, 1, 1): rank in the cluster == blockIdx.x
   const int b = blockIdx.y;
+  const int dbg = a.dbg;                    // developer timing bisect (results are wrong when any of bits 2/4/8 is set)
   UcProgram* pg = reinterpret_cast<UcProgram*>(sm + UC_O_PROG);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(pg) + ((sizeof(UcProgram) + 15) & ~(size_t)15));
 
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
   }
   __syncthreads();
   const float* stream = a.stream + (size_t)rank * pg->stream_floats_per_cta;
-  if (tid == 0)
+  if (tid == 0 && !(dbg & 8))
     for (int s = 0; s < UC_NSTAGE; ++s) uc_issue(pg, s, stream, sm + UC_O_RING, full);
   for (int i = tid; i < pg->head_dim * 64; i += UC_NT) sm[UC_O_HEAD + i] = __ldg(a.pack + pg->headWk + i);
   if (tid < pg->head_dim) sm[UC_O_HEAD + 448 + tid] = __ldg(a.pack + pg->headB + tid);
@@ -278,10 +286,10 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
 
     // (c) dot products over this CTA's weight slice
     switch (o.Lout) {
-      case 2: uc_layer_dot<2>(pg, o, sm, stream, full, q, tid); break;
-      case 4: uc_layer_dot<4>(pg, o, sm, stream, full, q, tid); break;
-      case 8: uc_layer_dot<8>(pg, o, sm, stream, full, q, tid); break;
-      default: uc_layer_dot<16>(pg, o, sm, stream, full, q, tid); break;
+      case 2: uc_layer_dot<2>(pg, o, sm, stream, full, q, tid, dbg); break;
+      case 4: uc_layer_dot<4>(pg, o, sm, stream, full, q, tid, dbg); break;
+      case 8: uc_layer_dot<8>(pg, o, sm, stream, full, q, tid, dbg); break;
+      default: uc_layer_dot<16>(pg, o, sm, stream, full, q, tid, dbg); break;
     }
     __syncthreads();
 
@@ -300,15 +308,19 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
     __syncthreads();
 
     // (e) push this CTA's outputs into the raw buffer of every CTA of the cluster (itself included)
-    for (int idx = tid; idx < n_items * UC_CL; idx += UC_NT) {
-      const int peer = idx / n_items, it = idx - peer * n_items;
-      const int r = it / o.nc, cl = it - r * o.nc;
-      const int e = r * o.Cout + rank * o.nc + cl;
-      uc_st_remote(raw + e, (uint32_t)peer, sm[UC_O_O + it]);
-      if (has_res) uc_st_remote(rraw + e, (uint32_t)peer, sm[UC_O_O + 64 + it]);
+    if (!(dbg & 4)) {
+      for (int idx = tid; idx < n_items * UC_CL; idx += UC_NT) {
+        const int peer = idx / n_items, it = idx - peer * n_items;
+        const int r = it / o.nc, cl = it - r * o.nc;
+        const int e = r * o.Cout + rank * o.nc + cl;
+        uc_st_remote(raw + e, (uint32_t)peer, sm[UC_O_O + it]);
+        if (has_res) uc_st_remote(rraw + e, (uint32_t)peer, sm[UC_O_O + 64 + it]);
+      }
+      // (f) one cluster barrier per layer: all parts of the layer output have landed everywhere
+      uc_cluster_sync();
+    } else {
+      __syncthreads();
     }
-    // (f) one cluster barrier per layer: all parts of the layer output have landed everywhere
-    uc_cluster_sync();
 
     // (g) GroupNorm statistics of the whole tensor, redundantly in every CTA: warp g owns group g
     if (o.gn) {

@@ -35,7 +35,7 @@ def latency(pl):
     for _ in range(3):
         pl.plan(x, f)
     ts = []
-    for _ in range(20):
+    for _ in range(12):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         pl.plan(x, f)
@@ -43,6 +43,12 @@ def latency(pl):
         ts.append((time.perf_counter() - t0) * 1e3)
     return sorted(ts)[len(ts) // 2]
 
+
+if "--bisect-only" in sys.argv:   # timing bisect alone (results are wrong in these modes), one JSON line per mode
+    for mode in [a for a in sys.argv[3:] if a.isdigit()]:
+        _, pm = make(mode)
+        print(json.dumps({"mode": int(mode), "T": T, "B": B, "plan_p50_ms": latency(pm)}), flush=True)
+    sys.exit(0)
 
 m0, p0 = make("0")
 y0 = m0(x, f, t)
@@ -60,6 +66,9 @@ try:
     torch.cuda.synchronize()
     out["plan_max_abs_diff"] = float((plan1 - plan0).abs().max())
     out["cluster_plan_p50_ms"] = latency(p1)
+    for mode in [a for a in sys.argv[3:] if a.isdigit()]:   # timing bisect (results are wrong in these modes): 3 no dot, 5 no exchange, 9 no weight stream, 15 skeleton
+        _, pm = make(mode)
+        out[f"bisect_{mode}_plan_p50_ms"] = latency(pm)
 except Exception as exc:  # report, do not hide
     out["error"] = repr(exc)
 print(json.dumps(out), flush=True)
