@@ -45,6 +45,16 @@ constexpr int UC_O_PROG = UC_O_SRC + 192;                            // UcProgra
 static_assert(sizeof(UcProgram) % 16 == 0, "UcProgram is copied in 16-byte units");
 constexpr size_t UC_SMEM_BYTES = (size_t)UC_O_PROG * 4 + ((sizeof(UcProgram) + 15) & ~(size_t)15) + 64;   // + mbarriers
 
+#ifdef B2P_TC_TRACE   // developer tracing (trace build, scripts/cluster_trace.py): stage clocks of CTA 0 of trajectory 0, per layer
+__device__ unsigned long long uc_trace[(UC_MAXOPS + 1) * 8];
+#define UC_T(op, k)                                                                  \
+  do {                                                                               \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) uc_trace[(op) * 8 + (k)] = clock64(); \
+  } while (0)
+#else
+#define UC_T(op, k)
+#endif
+
 __device__ __forceinline__ uint32_t uc_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void uc_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -204,6 +214,7 @@ __device__ __forceinline__ void uc_layer_dot(const UcProgram* pg, const UcOp& o,
 __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
   extern __shared__ __align__(128) float sm[];
   pdl_launch_dependents();
+  UC_T(UC_MAXOPS, 0);
   const int tid = threadIdx.x;
   const int rank = blockIdx.x;              // grid = (UC_CL, B), cluster = (UC_CL, 1, 1): rank in the cluster == blockIdx.x
   const int b = blockIdx.y;
@@ -234,8 +245,10 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
   for (int i = tid; i < a.H * a.D; i += UC_NT) sm[UC_O_SLOTS + pg->x_slot * UC_SLOT_FLOATS + i] = __ldg(a.x + (size_t)b * a.H * a.D + i);
   __syncthreads();
 
+  UC_T(UC_MAXOPS, 1);                       // prologue done (slot 0 of the last row = kernel start, below)
   int q = 0;                                // next chunk of the stream to consume
   for (int oi = 0; oi < pg->n_ops; ++oi) {
+    UC_T(oi, 0);
     const UcOp& o = pg->ops[oi];
     const int par = oi & 1;
     float* raw = sm + UC_O_RAW + par * 2 * UC_SLOT_FLOATS;
@@ -283,6 +296,7 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
       if (has_res && o.resB >= 0) p_rb = __ldg(a.pack + o.resB + ch);
     }
     __syncthreads();
+    UC_T(oi, 1);
 
     // (c) dot products over this CTA's weight slice
     switch (o.Lout) {
@@ -292,6 +306,7 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
       default: uc_layer_dot<16>(pg, o, sm, stream, full, q, tid, dbg); break;
     }
     __syncthreads();
+    UC_T(oi, 2);
 
     // (d) combine the K slices in a fixed order (+ bias)
     if (tid < n_items) {
@@ -306,6 +321,7 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
       }
     }
     __syncthreads();
+    UC_T(oi, 3);
 
     // (e) push this CTA's outputs into the raw buffer of every CTA of the cluster (itself included)
     if (!(dbg & 4)) {
@@ -321,6 +337,7 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
     } else {
       __syncthreads();
     }
+    UC_T(oi, 4);
 
     // (g) GroupNorm statistics of the whole tensor, redundantly in every CTA: warp g owns group g
     if (o.gn) {
@@ -349,6 +366,7 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
       }
       __syncthreads();
     }
+    UC_T(oi, 5);
 
     // (h) epilogue on the whole tensor: normalise, Mish, time term, residual -> this layer's output slot
     float* out = sm + UC_O_SLOTS + o.out * UC_SLOT_FLOATS;
@@ -368,6 +386,7 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
       }
     }
     __syncthreads();
+    UC_T(oi, 6);
 
     // (i) 1x1 head on the finished [L][64] tensor (final_conv.1): written once, by CTA 0
     if (o.head && rank == 0 && tid < o.Lout * pg->head_dim) {
@@ -408,3 +427,11 @@ int launch_unet_cluster(const UcLaunch& a, cudaStream_t s) {
 }
 
 }  // namespace b2p
+
+#ifdef B2P_TC_TRACE
+// rows 0..n_ops-1: clocks at {layer start, tables built, dot products done, K slices combined, exchange + cluster barrier done,
+// statistics done, epilogue done}; row UC_MAXOPS: {kernel start, prologue done}
+extern "C" __attribute__((visibility("default"))) int b2p_debug_uc_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, b2p::uc_trace, sizeof(unsigned long long) * (b2p::UC_MAXOPS + 1) * 8);
+}
+#endif
