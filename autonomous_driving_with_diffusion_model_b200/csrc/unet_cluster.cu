@@ -65,6 +65,15 @@ __device__ __forceinline__ void uc_st_remote(const float* local_dst, uint32_t pe
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(uc_saddr(local_dst)), "r"(peer));
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
+// 8-byte asynchronous store into CTA `peer` that also counts its bytes on THAT CTA's mbarrier (conv_gemv.cu's exchange): the
+// receiver waits for its byte count, no cluster-wide barrier or fence is involved
+__device__ __forceinline__ void uc_st_async(const float* local_dst, const unsigned long long* local_bar, uint32_t peer, float a, float b) {
+  uint32_t rd, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rd) : "r"(uc_saddr(local_dst)), "r"(peer));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(uc_saddr(local_bar)), "r"(peer));
+  const unsigned long long v = ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(a);
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(rd), "l"(v), "r"(rb) : "memory");
+}
 __device__ __forceinline__ void uc_bar_init(unsigned long long* bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uc_saddr(bar)) : "memory");
 }
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
   }
   for (int i = tid; i < UC_SLOT_FLOATS; i += UC_NT) sm[UC_O_ZERO + i] = 0.f;
   if (tid == 0) {
-    for (int s = 0; s < UC_NSTAGE; ++s) uc_bar_init(full + s);
+    for (int s = 0; s < UC_NSTAGE + 2; ++s) uc_bar_init(full + s);   // ring stages + the two receive barriers (raw buffer parity)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copies (async proxy) signal these barriers
   }
@@ -256,6 +265,14 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
     const int n_items = o.Lout * o.nc;      // outputs this CTA produces (<= 64)
     const int n_el = o.Lout * o.Cout;       // elements of the layer output (<= 1024)
     const bool has_res = o.rnchunks > 0;
+    // UNTESTED VARIANT (dbg bit 16, i.e. B2P_CLUSTER_EVAL=17): exchange by st.async + byte counting on the receiver's mbarrier
+    // instead of remote stores + a cluster barrier.  The phase of rx[par] used two layers ago has completed (every thread of
+    // this CTA waited on it), and no peer can send this layer's data before it has received this CTA's previous layer.
+    const bool xasync = (dbg & 16) && !(dbg & 4);
+    unsigned long long* rx = full + UC_NSTAGE;
+    if (xasync && tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(uc_saddr(rx + par)), "r"((uint32_t)(n_el * 4 * (has_res ? 2 : 1)))
+                   : "memory");
 
     // (a) input-row tables
     if (tid < 2 * 5 * UC_MAXL) {
@@ -324,7 +341,17 @@ __global__ void __launch_bounds__(UC_NT, 1) unet_cluster_kernel(UcLaunch a) {
     UC_T(oi, 3);
 
     // (e) push this CTA's outputs into the raw buffer of every CTA of the cluster (itself included)
-    if (!(dbg & 4)) {
+    if (xasync) {
+      const int n_pairs = n_items >> 1;       // nc is even: items (it, it + 1) are adjacent channels of one row
+      for (int idx = tid; idx < n_pairs * UC_CL; idx += UC_NT) {
+        const int peer = idx / n_pairs, it = (idx - peer * n_pairs) * 2;
+        const int r = it / o.nc, cl = it - r * o.nc;
+        const int e = r * o.Cout + rank * o.nc + cl;
+        uc_st_async(raw + e, rx + par, (uint32_t)peer, sm[UC_O_O + it], sm[UC_O_O + it + 1]);
+        if (has_res) uc_st_async(rraw + e, rx + par, (uint32_t)peer, sm[UC_O_O + 64 + it], sm[UC_O_O + 64 + it + 1]);
+      }
+      uc_bar_wait(rx + par, (uint32_t)((oi >> 1) & 1));   // all 16 parts of this layer have landed here
+    } else if (!(dbg & 4)) {
       for (int idx = tid; idx < n_items * UC_CL; idx += UC_NT) {
         const int peer = idx / n_items, it = idx - peer * n_items;
         const int r = it / o.nc, cl = it - r * o.nc;

@@ -60,7 +60,7 @@ struct UcLaunch {
   const float* temb2;              // per-step term [temb_total] or null
   float* head_out;                 // [B][H][head_dim]
   int B, H, D;
-  int dbg;                         // developer timing bisect: 2 skip the dot products, 4 skip the exchange, 8 skip the weight stream
+  int dbg;                         // developer timing bisect: 2 skip the dot products, 4 skip the exchange, 8 skip the weight stream; 16: UNTESTED st.async exchange variant
 };
 
 size_t uc_smem_bytes();

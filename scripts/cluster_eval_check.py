@@ -12,6 +12,7 @@ import torch  # noqa: E402
 import autonomous_driving_with_diffusion_model_b200 as P  # noqa: E402
 from oracle import weights as W  # noqa: E402
 
+MODE = os.environ.get("B2P_CLUSTER_CHECK_MODE", "1")   # "17": the (untested) st.async exchange variant
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 dev = torch.device("cuda:0")
@@ -57,7 +58,7 @@ torch.cuda.synchronize()
 out["default_launches_per_eval"] = m0.last_launch_count()
 out["default_plan_p50_ms"] = latency(p0)
 try:
-    m1, p1 = make("1")
+    m1, p1 = make(MODE)
     y1 = m1(x, f, t)
     torch.cuda.synchronize()
     out["cluster_launches_per_eval"] = m1.last_launch_count()
