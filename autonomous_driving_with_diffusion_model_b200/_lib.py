@@ -40,7 +40,7 @@ class PlanConfig(C.Structure):
                 ("classifier_scale", C.c_float), ("magic_num", C.c_float), ("postprocess", C.c_int32), ("use_graph", C.c_int32)]
 
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 SCHED_KINDS = {"guidance_ddim": 0, "guidance_ddpm": 1, "inpainting_ddim": 2, "inpainting_ddpm": 3}
 PRED_TYPES = {"epsilon": 0, "sample": 1, "v_prediction": 2}
 BETA_SCHEDULES = {"squaredcos_cap_v2": 0, "linear": 1, "scaled_linear": 2}
@@ -74,6 +74,12 @@ SYMBOLS = {
                                  C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, _VP]),
     "b2p_plan": (C.c_int, [_VP, C.POINTER(PlanConfig), _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "b2p_plan_host": (C.c_int, [_VP, C.POINTER(PlanConfig), _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32]),
+    "b2p_plan_host_async": (C.c_int, [_VP, C.POINTER(PlanConfig), _VP, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, C.c_int32]),
+    "b2p_sync": (C.c_int, [_VP]),
+    "b2p_plan_sharded_host": (C.c_int, [C.POINTER(_VP), C.c_int32, C.POINTER(PlanConfig), _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32]),
+    "b2p_set_noise_seed": (C.c_int, [_VP, C.c_uint64]),
+    "b2p_last_noise_key": (C.c_uint64, [_VP]),
+    "b2p_philox_normal": (C.c_int, [C.c_uint64, C.c_int32, C.c_int64, _VP, _VP]),
     "b2p_last_launch_count": (C.c_int64, [_VP]),
     "b2p_unet_flops_per_sample": (C.c_int64, [_VP]),
     "b2p_weight_bytes": (C.c_int64, [_VP]),

@@ -20,7 +20,10 @@ def copy_parameters(from_parameters: Iterable[torch.Tensor], to_parameters: Iter
             if tuple(s.shape) != tuple(p.shape):
                 raise ValueError(f"EMA shadow parameter {i} has shape {tuple(s.shape)}, the model expects {tuple(p.shape)}: "
                                  "the checkpoint was trained with a different configuration")
-            p.data.copy_(s.to(p.device).data)
+            p.copy_(s.detach().to(p.device))    # NOT p.data.copy_: a write through .data does not bump the version counter
+    owners = {id(o): o for o in (getattr(p, "_b2p_owner", lambda: None)() for p in dst) if o is not None}
+    for o in owners.values():                   # packed device copies / folded encoder weights are rebuilt on the next call
+        o.invalidate_weights()
 
 
 def load_checkpoint(model: torch.nn.Module, checkpoint: Union[str, Mapping], use_ema: bool = True, map_location="cpu") -> dict:

@@ -11,7 +11,6 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
-#include "unet_cluster.cuh"
 
 namespace b2p {
 int upload_freq_table(const float* f, int n);
@@ -47,7 +46,7 @@ struct LayerOp {
 struct Buf { int L, C; size_t off; };  // per-sample floats = L*C; off = prefix sum of per-sample floats
 
 struct GraphKey {
-  int B, T, kind, has_target, has_noise, has_traj, has_mask;
+  int B, T, kind, has_target, has_noise, has_traj, has_mask, dev_noise;
   b2p_plan_config pc;
   bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
@@ -97,13 +96,13 @@ struct b2p_handle_s {
   float *p_x = nullptr, *p_feat = nullptr, *p_target = nullptr, *p_cond = nullptr, *p_noise = nullptr, *p_traj = nullptr,
         *p_mask = nullptr, *p_mo = nullptr, *p_action = nullptr, *p_out = nullptr, *p_ttab = nullptr, *p_itab = nullptr, *p_tetab = nullptr;
   int64_t* p_tsteps = nullptr;
+  unsigned long long* p_seed = nullptr;   // Philox key of the current plan (device; read by the scheduler kernels at run time)
+  float* p_thr = nullptr;                 // dynamic-threshold scratch [B]
+  unsigned long long noise_seed = 0x5eed5eed5eedULL, noise_calls = 0, last_noise_key = 0;
+  int ts_ntrain = -1, ts_T = -1;       // which timestep table p_tsteps currently holds (the captured kernels read it at replay time)
   std::vector<GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;
   int small_batch_max = B2P_SMALL_BATCH_DEFAULT;   // largest evaluation batch that takes the GEMV kernels
-  // EXPERIMENTAL one-cluster-per-trajectory evaluation (unet_cluster.cu), only with B2P_CLUSTER_EVAL=1 in the environment
-  int cluster_eval = 0;
-  UcProgram* d_cprog = nullptr;
-  float* d_cstream = nullptr;
 
   int fail(int code, const std::string& m) { err = m; return code; }
 };
@@ -524,122 +523,6 @@ inline const float* buf_ptr(b2p_handle_s* h, int id, const float* x) {
   return h->d_act + h->bufs[id].off * (size_t)h->cap;
 }
 
-// ---- EXPERIMENTAL: program + per-CTA weight streams of the one-cluster-per-trajectory kernel (unet_cluster.cu) ----
-int pad4i(int n) { return (n + 3) & ~3; }
-
-// host part: the program table and the 16 per-CTA weight streams (pure host code: also driven by tests/native/uc_emulate.cu)
-int build_cluster_program_host(b2p_handle_s* h, UcProgram& pg, std::vector<float>& stream) {
-  if (h->cfg.guidance != B2P_NO_GUIDANCE || h->H > UC_MAXL || (int)h->ops.size() > UC_MAXOPS) return B2P_ERR_INVALID_ARG;
-  memset(&pg, 0, sizeof(pg));
-  const int nops = (int)h->ops.size();
-  auto bid = [](int id) { return id == BUF_X ? 0 : id + 1; };   // buffer index: 0 = input trajectory, i + 1 = bufs[i]
-  const int nb = (int)h->bufs.size() + 1;
-  std::vector<int> last(nb, -1), slot_of(nb, -1);
-  for (int i = 0; i < nops; ++i) {
-    const LayerOp& op = h->ops[i];
-    const int ids[5] = {op.in0, op.in1, op.res_id, op.resW != NPOS ? op.rin0 : BUF_NONE, op.resW != NPOS ? op.rin1 : BUF_NONE};
-    for (int id : ids) if (id != BUF_NONE) last[bid(id)] = i;
-  }
-  int owner[UC_NSLOT];
-  for (int s = 0; s < UC_NSLOT; ++s) owner[s] = -1;
-  slot_of[0] = 0; owner[0] = 0; pg.x_slot = 0;
-  auto slot = [&](int id) { return id == BUF_NONE ? -1 : slot_of[bid(id)]; };
-  struct ChunkSrc { int op, is_res, k0, klen, kstride; };
-  std::vector<ChunkSrc> csrc;
-  int off = 0;
-  for (int i = 0; i < nops; ++i) {
-    const LayerOp& op = h->ops[i];
-    for (int s = 0; s < UC_NSLOT; ++s) if (owner[s] >= 0 && last[owner[s]] < i) owner[s] = -1;   // no longer read by op i or later
-    int os = -1;
-    for (int s = 0; s < UC_NSLOT; ++s) if (owner[s] < 0) { os = s; break; }
-    if (os < 0 || op.out == BUF_NONE) return B2P_ERR_INVALID_ARG;
-    owner[os] = bid(op.out); slot_of[bid(op.out)] = os;
-    UcOp& u = pg.ops[i];
-    u.in0 = slot(op.in0); u.in1 = slot(op.in1); u.C0 = op.C0; u.C1 = op.C1;
-    u.Lin = op.Lin; u.Lout = op.Lout; u.Cout = op.Cout; u.nc = op.Cout / UC_CL;
-    int jmin = 0, jmax = op.taps - 1;
-    if (!op.transposed && op.stride == 1) {
-      jmin = op.pad - (op.Lout - 1) > 0 ? op.pad - (op.Lout - 1) : 0;
-      jmax = op.pad + op.Lin - 1 < op.taps - 1 ? op.pad + op.Lin - 1 : op.taps - 1;
-    }
-    u.ntaps = jmax - jmin + 1; u.jmin = jmin; u.stride = op.stride; u.pad = op.pad; u.transposed = op.transposed;
-    u.gn = op.gamma != NPOS; u.temb_off = op.temb_off;
-    u.res_id = slot(op.res_id);
-    const bool rc = op.resW != NPOS;
-    u.rin0 = rc ? slot(op.rin0) : -1; u.rin1 = rc ? slot(op.rin1) : -1; u.RC0 = rc ? op.RC0 : 0; u.RC1 = rc ? op.RC1 : 0;
-    u.out = os;
-    u.bias = op.bias != NPOS ? (int)op.bias : -1; u.gamma = u.gn ? (int)op.gamma : -1; u.beta = u.gn ? (int)op.beta : -1;
-    u.resB = rc ? (int)op.resB : -1;
-    u.head = op.headW != NPOS;
-    // shapes the kernel is written for
-    const bool pow2 = (op.Cout & (op.Cout - 1)) == 0;
-    if (!pow2 || op.Cout % (2 * UC_CL) != 0 || u.nc > 32 || op.Lout * u.nc > 64 || op.Lout * op.Cout > UC_SLOT_FLOATS ||
-        op.Lin * (op.C0 > op.C1 ? op.C0 : op.C1) > UC_SLOT_FLOATS || u.ntaps > 5 || u.in0 < 0 ||
-        (op.Lout != 2 && op.Lout != 4 && op.Lout != 8 && op.Lout != 16) || (u.head && op.Cout != 64) || (rc && op.resWk == NPOS) ||
-        op.Wk == NPOS)
-      return B2P_ERR_INVALID_ARG;
-    // chunks: [nc][kstride] blocks of at most one ring stage
-    const int kc_max = (UC_STAGE_FLOATS / u.nc) & ~3;
-    auto add_chunks = [&](int K, int is_res) {
-      int n = 0;
-      for (int k0 = 0; k0 < K; k0 += kc_max, ++n) {
-        const int klen = K - k0 < kc_max ? K - k0 : kc_max;
-        csrc.push_back(ChunkSrc{i, is_res, k0, klen, pad4i(klen)});
-      }
-      return n;
-    };
-    u.chunk0 = (int)csrc.size();
-    u.nchunks = add_chunks(u.ntaps * (op.C0 + op.C1), 0);
-    u.rnchunks = rc ? add_chunks(op.RC0 + op.RC1, 1) : 0;
-    if (u.head) { pg.head_dim = op.head_dim; pg.headWk = (int)op.headWk; pg.headB = (int)op.headB; }
-  }
-  if ((int)csrc.size() > UC_MAXCHUNKS || pg.head_dim <= 0 || pg.head_dim * 64 > 448) return B2P_ERR_INVALID_ARG;
-  pg.n_ops = nops; pg.n_chunks = (int)csrc.size();
-  for (size_t q = 0; q < csrc.size(); ++q) {
-    const ChunkSrc& c = csrc[q];
-    const int nc = pg.ops[c.op].nc;
-    UcChunk& k = pg.chunks[q];
-    k.k0 = c.k0; k.klen = c.klen; k.kstride = c.kstride; k.off = off; k.bytes = nc * c.kstride * 4;
-    off += nc * c.kstride;
-  }
-  pg.stream_floats_per_cta = off;
-  stream.assign((size_t)off * UC_CL, 0.f);
-  const float* P = h->pack_host.data();
-  for (int r = 0; r < UC_CL; ++r)
-    for (size_t q = 0; q < csrc.size(); ++q) {
-      const ChunkSrc& c = csrc[q];
-      const LayerOp& op = h->ops[c.op];
-      const UcOp& u = pg.ops[c.op];
-      float* dst = stream.data() + (size_t)r * off + pg.chunks[q].off;
-      for (int cl = 0; cl < u.nc; ++cl) {
-        const int ch = r * u.nc + cl;
-        // K-major sources: conv [Cout][taps][Cin] (row of channel ch starts at tap jmin), residual [Cout][RCin]
-        const float* src = c.is_res ? P + op.resWk + (size_t)ch * (op.RC0 + op.RC1)
-                                    : P + op.Wk + ((size_t)ch * op.taps + u.jmin) * (op.C0 + op.C1);
-        memcpy(dst + (size_t)cl * c.kstride, src + c.k0, sizeof(float) * c.klen);
-      }
-    }
-  return B2P_OK;
-}
-
-int ensure_cluster_program(b2p_handle_s* h) {
-  if (h->d_cprog) return B2P_OK;
-  std::vector<UcProgram> pg(1);
-  std::vector<float> stream;
-  int rc = build_cluster_program_host(h, pg[0], stream);
-  if (rc) return rc;
-  B2P_CUDA_TRY(cudaMalloc((void**)&h->d_cstream, stream.size() * sizeof(float)));
-  B2P_CUDA_TRY(cudaMemcpy(h->d_cstream, stream.data(), stream.size() * sizeof(float), cudaMemcpyHostToDevice));
-  B2P_CUDA_TRY(cudaMalloc((void**)&h->d_cprog, sizeof(UcProgram)));
-  B2P_CUDA_TRY(cudaMemcpy(h->d_cprog, pg.data(), sizeof(UcProgram), cudaMemcpyHostToDevice));
-  return B2P_OK;
-}
-
-void drop_cluster_program(b2p_handle_s* h) {
-  if (h->d_cprog) { cudaFree(h->d_cprog); h->d_cprog = nullptr; }
-  if (h->d_cstream) { cudaFree(h->d_cstream); h->d_cstream = nullptr; }
-}
-
 // the denoiser on `rows` batch rows; x rows may repeat with period x_period (CFG feeds [x; x]).
 // itab/ttab_row != null: "table mode" (inside a plan, no CFG): the per-block time-MLP outputs were precomputed as an
 // image term itab[rows, temb_total] (step-invariant) and a time vector ttab_row[temb_total] for this step, so the
@@ -670,16 +553,6 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
     if ((rc = launch_conv_ffma(a, s))) return rc;
     ++*launches;
     temb_rows = h->d_temb;
-  }
-  // EXPERIMENTAL (B2P_CLUSTER_EVAL=1): one launch per evaluation, one 16-CTA cluster per trajectory (unet_cluster.cu)
-  if ((h->cluster_eval & 1) && rows <= 8 && h->cfg.guidance == B2P_NO_GUIDANCE && x_period == 0 && head_out) {
-    if ((rc = ensure_cluster_program(h))) return h->fail(rc, "cluster evaluation: unsupported architecture");
-    UcLaunch u{};
-    u.prog = h->d_cprog; u.stream = h->d_cstream; u.pack = P; u.x = x; u.temb = temb_rows; u.temb_stride = h->temb_total;
-    u.temb2 = ttab_row; u.head_out = head_out; u.B = rows; u.H = h->H; u.D = h->D; u.dbg = h->cluster_eval & ~1;
-    if ((rc = launch_unet_cluster(u, s))) return h->fail(rc, "cluster evaluation launch failed");
-    ++*launches;
-    return B2P_OK;
   }
   // Small batches take the exact-fp32 GEMV program whatever the precision mode: with a handful of trajectories a layer is
   // pure weight streaming, the GEMV kernels prefetch weights layers ahead, and no bf16 splitting is needed.
@@ -769,7 +642,7 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
       if (op.temb_off >= 0) { t.temb = temb_rows + op.temb_off; t.temb_stride = h->temb_total; t.temb2 = ttab_row ? ttab_row + op.temb_off : nullptr; }
       if (op.headW != NPOS) { t.headW = P + op.headW; t.headB = P + op.headB; t.head_dim = op.head_dim; t.head_out = head_out; }
       if (op.headW == NPOS) { t.out_hi = hi_ptr(op.out); t.out_lo = lo_ptr(op.out); }   // the head layer's own output is not materialised
-      if ((rc = launch_conv_tc(m, t, nsplit, s))) return h->fail(rc, "tcgen05 conv launch failed");
+      if ((rc = launch_conv_tc(m, t, nsplit, s))) return h->fail(rc, std::string("tcgen05 conv launch failed: ") + tc_last_error());
       ++*launches;
       continue;
     }
@@ -898,7 +771,6 @@ int b2p_create(const b2p_model_config* cfg, int device, b2p_handle* out) {
     if (rc) { delete h; return rc; }
   }
   cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
-  { const char* e = getenv("B2P_CLUSTER_EVAL"); h->cluster_eval = e ? atoi(e) : 0; }
   *out = h;
   return B2P_OK;
 }
@@ -911,7 +783,6 @@ int b2p_destroy(b2p_handle h) {
   if (h->d_pack16) cudaFree(h->d_pack16);
   if (h->d_ws) cudaFree(h->d_ws);
   if (h->p_x) cudaFree(h->p_x);
-  drop_cluster_program(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
   return B2P_OK;
@@ -951,7 +822,6 @@ int b2p_finalize_weights(b2p_handle h) {
     build_trajpred(h, pk, tp_offs);
   }
   drop_graphs(h);
-  drop_cluster_program(h);         // rebuilt lazily from the new weights
   if (h->d_pack) { B2P_CUDA_TRY(cudaFree(h->d_pack)); h->d_pack = nullptr; }
   B2P_CUDA_TRY(cudaMalloc((void**)&h->d_pack, h->pack_host.size() * sizeof(float)));
   B2P_CUDA_TRY(cudaMemcpy(h->d_pack, h->pack_host.data(), h->pack_host.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -962,9 +832,6 @@ int b2p_finalize_weights(b2p_handle h) {
   // workspace offsets depend on the buffer table: force re-allocation
   if (h->d_ws) { B2P_CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; h->cap = 0; }
   h->finalized = true;
-  // experimental cluster evaluation: its program and weight streams are device allocations, which must exist before a plan is
-  // captured into a CUDA graph (an unsupported architecture is reported by the first evaluation instead)
-  if ((h->cluster_eval & 1) && h->cfg.guidance == B2P_NO_GUIDANCE) (void)ensure_cluster_program(h);
   return B2P_OK;
 }
 
@@ -981,6 +848,14 @@ int b2p_set_small_batch_max(b2p_handle h, int max_samples) {
   drop_graphs(h);
   return B2P_OK;
 }
+
+int b2p_set_noise_seed(b2p_handle h, uint64_t seed) {
+  if (!h) return B2P_ERR_INVALID_ARG;
+  h->noise_seed = seed; h->noise_calls = 0;
+  return B2P_OK;
+}
+
+uint64_t b2p_last_noise_key(b2p_handle h) { return h ? h->last_noise_key : 0; }
 
 int64_t b2p_last_launch_count(b2p_handle h) { return h ? h->last_launches : 0; }
 int64_t b2p_unet_flops_per_sample(b2p_handle h) { return h ? h->flops_per_sample : 0; }
@@ -1049,7 +924,8 @@ static int ensure_plan_buffers(b2p_handle h, int B, int T) {
   if (h->p_x) { B2P_CUDA_TRY(cudaFree(h->p_x)); h->p_x = nullptr; }
   int cb = B > h->plan_capB ? B : h->plan_capB, ct = T > h->plan_capT ? T : h->plan_capT;
   size_t hd = (size_t)h->H * h->D;
-  size_t floats = (size_t)cb * (hd * 6 + h->dim + 2 + 4 + (size_t)h->H * 3 + h->temb_total) + (size_t)ct * (cb * hd + h->temb_total + h->dim) + 64 * 20;
+  size_t floats = (size_t)cb * (hd * 6 + h->dim + 2 + 4 + 1 + (size_t)h->H * 3 + h->temb_total) + (size_t)ct * (cb * hd + h->temb_total + h->dim) + 64 * 20;
+  floats = (floats + 3) & ~(size_t)3;   // the int64 timestep table and the Philox key follow the floats
   B2P_CUDA_TRY(cudaMalloc((void**)&h->p_x, floats * sizeof(float) + sizeof(int64_t) * (ct + 8)));
   float* p = h->p_x;
   auto take = [&](size_t n) { float* r = p; p += (n + 63) & ~(size_t)63; return r; };
@@ -1065,8 +941,11 @@ static int ensure_plan_buffers(b2p_handle h, int B, int T) {
   h->p_itab = take((size_t)cb * h->temb_total);
   h->p_ttab = take((size_t)ct * h->temb_total);
   h->p_tetab = take((size_t)ct * h->dim);
+  h->p_thr = take((size_t)cb);
   h->p_noise = take((size_t)ct * cb * hd);
   h->p_tsteps = reinterpret_cast<int64_t*>(h->p_x + floats);
+  h->p_seed = reinterpret_cast<unsigned long long*>(h->p_tsteps + ct + 1);
+  h->ts_ntrain = h->ts_T = -1;
   h->plan_capB = cb; h->plan_capT = ct;
   return B2P_OK;
 }
@@ -1135,7 +1014,8 @@ static int enqueue_plan(b2p_handle h, const b2p_plan_config& pc, const GraphKey&
     if (last && pc.postprocess) flags |= B2P_STEP_FINAL_POSTPROCESS;
     SchedLaunch L{pc.sched, kc, mo, mo_u, pc.free_scale, h->p_x, k.has_noise ? h->p_noise + (size_t)i * B * hd : nullptr,
                   (inpaint && k.has_traj) ? h->p_traj : nullptr, (inpaint && k.has_mask) ? h->p_mask : nullptr,
-                  last ? h->p_out : h->p_x, nullptr, B, h->H, h->D, pc.eta, pc.magic_num, flags};
+                  last ? h->p_out : h->p_x, nullptr, B, h->H, h->D, pc.eta, pc.magic_num, flags,
+                  k.dev_noise ? h->p_seed : nullptr, (unsigned)i, h->p_thr};
     if ((rc = launch_sched_step(L, s))) return rc;
     ++*launches;
   }
@@ -1147,18 +1027,33 @@ __global__ void zero_first_waypoint_kernel(float* x, int B, int HD) {
   if (i < B * 3) x[(size_t)(i / 3) * HD + (i % 3)] = 0.f;
 }
 
+// The denoiser kernels of a plan (captured or eager) read their timesteps from h->p_tsteps when they RUN, so the table must
+// hold this plan's schedule before every launch — a cached graph of another (num_train_timesteps, T) may have run in between.
+static int ensure_timesteps(b2p_handle h, int ntrain, int T, cudaStream_t s) {
+  if (h->ts_ntrain == ntrain && h->ts_T == T) return B2P_OK;
+  std::vector<int64_t> ts(T);
+  b2p_timesteps(ntrain, T, ts.data());
+  B2P_CUDA_TRY(cudaMemcpyAsync(h->p_tsteps, ts.data(), sizeof(int64_t) * T, cudaMemcpyHostToDevice, s));
+  B2P_CUDA_TRY(cudaStreamSynchronize(s));   // ts is a stack vector
+  h->ts_ntrain = ntrain; h->ts_T = T;
+  return B2P_OK;
+}
+
+// host: the tensor arguments are HOST pointers (H2D / D2H copies on s).  sync: synchronise s before returning (a host caller
+// without a stream of its own).  noise_batch: batch extent of the caller's noise tensor [T, noise_batch, H, D] when this call
+// plans a contiguous slice [b0, b0 + B) of a larger batch (the caller passes noise + b0*H*D); 0 or B = dense.
 static int plan_impl(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const float* feat, const float* target,
-                     const float* noise, const float* traj, const float* mask, float* out, int B, cudaStream_t s, bool host) {
+                     const float* noise, const float* traj, const float* mask, float* out, int B, cudaStream_t s, bool host,
+                     bool sync, int noise_batch = 0) {
   if (!h || !pc || !x_init || !feat || !out || B <= 0) return B2P_ERR_INVALID_ARG;
   if (!h->finalized) return h->fail(B2P_ERR_NOT_FINALIZED, "weights not finalized");
   const int T = pc->num_inference_steps;
   if (T <= 0 || T > pc->sched.num_train_timesteps) return h->fail(B2P_ERR_INVALID_ARG, "bad num_inference_steps");
   const int g = h->cfg.guidance;
-  if (g == B2P_FREE_GUIDANCE && !target) return h->fail(B2P_ERR_INVALID_ARG, "FREE_GUIDANCE needs a target");
   const bool ddpm = pc->sched.kind == B2P_SCHED_GUIDANCE_DDPM || pc->sched.kind == B2P_SCHED_INPAINT_DDPM;
   const bool inpaint = pc->sched.kind == B2P_SCHED_INPAINT_DDIM || pc->sched.kind == B2P_SCHED_INPAINT_DDPM;
-  if ((ddpm || (inpaint && traj && mask) || pc->eta > 0.f) && !noise && T > 1)
-    return h->fail(B2P_ERR_INVALID_ARG, "this scheduler consumes noise: pass noise [T,B,H,D]");
+  // a scheduler that consumes noise and gets none draws it in the kernel (Philox keyed by b2p_set_noise_seed + a per-plan counter)
+  const bool dev_noise = (ddpm || (inpaint && traj && mask) || pc->eta > 0.f) && !noise;
   B2P_CUDA_TRY(cudaSetDevice(h->device));
   int rc;
   if ((rc = ensure_plan_buffers(h, B, T))) return rc;
@@ -1173,8 +1068,15 @@ static int plan_impl(b2p_handle h, const b2p_plan_config* pc, const float* x_ini
       B2P_CUDA_TRY(cudaMemcpyAsync(h->p_cond, target, sizeof(float) * B * 2, kind, s));
       B2P_CUDA_TRY(cudaMemsetAsync(h->p_cond + (size_t)B * 2, 0, sizeof(float) * B * 2, s));
     }
+  } else if (g == B2P_FREE_GUIDANCE) {   // generate_traj(image, None): cond = None == zeros for both halves (modeling/temporal.py:207)
+    B2P_CUDA_TRY(cudaMemsetAsync(h->p_cond, 0, sizeof(float) * B * 4, s));
   }
-  if (noise) B2P_CUDA_TRY(cudaMemcpyAsync(h->p_noise, noise, sizeof(float) * T * B * hd, kind, s));
+  if (noise) {
+    if (noise_batch > B)   // a batch slice of a larger [T, noise_batch, H, D] tensor: T strided rows
+      B2P_CUDA_TRY(cudaMemcpy2DAsync(h->p_noise, sizeof(float) * B * hd, noise, sizeof(float) * noise_batch * hd, sizeof(float) * B * hd, T, kind, s));
+    else
+      B2P_CUDA_TRY(cudaMemcpyAsync(h->p_noise, noise, sizeof(float) * T * B * hd, kind, s));
+  }
   if (traj) B2P_CUDA_TRY(cudaMemcpyAsync(h->p_traj, traj, sizeof(float) * B * hd, kind, s));
   if (mask) B2P_CUDA_TRY(cudaMemcpyAsync(h->p_mask, mask, sizeof(float) * B * hd, kind, s));
   zero_first_waypoint_kernel<<<(B * 3 + 127) / 128, 128, 0, s>>>(h->p_x, B, (int)hd);  // interact.py:129
@@ -1182,16 +1084,19 @@ static int plan_impl(b2p_handle h, const b2p_plan_config* pc, const float* x_ini
   GraphKey key;
   memset(&key, 0, sizeof(key));
   key.B = B; key.T = T; key.kind = pc->sched.kind; key.has_target = target != nullptr; key.has_noise = noise != nullptr;
-  key.has_traj = traj != nullptr; key.has_mask = mask != nullptr; key.pc = *pc;
+  key.has_traj = traj != nullptr; key.has_mask = mask != nullptr; key.dev_noise = dev_noise; key.pc = *pc;
+  if (dev_noise) {   // splitmix64 of (seed, plan counter): every plan of the handle gets its own stream of draws
+    unsigned long long z = h->noise_seed + 0x9E3779B97F4A7C15ULL * (++h->noise_calls);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; z ^= z >> 31;
+    h->last_noise_key = z;
+    B2P_CUDA_TRY(cudaMemcpyAsync(h->p_seed, &z, sizeof(z), cudaMemcpyHostToDevice, s));   // pageable source: staged before the call returns
+  }
   int64_t launches = 1;
+  if ((rc = ensure_timesteps(h, pc->sched.num_train_timesteps, T, s))) return rc;
   if (pc->use_graph) {
     GraphEntry* ge = nullptr;
     for (auto& e : h->graphs) if (e.key == key) { ge = &e; break; }
     if (!ge) {
-      std::vector<int64_t> ts(T);
-      b2p_timesteps(pc->sched.num_train_timesteps, T, ts.data());
-      B2P_CUDA_TRY(cudaMemcpyAsync(h->p_tsteps, ts.data(), sizeof(int64_t) * T, cudaMemcpyHostToDevice, s));
-      B2P_CUDA_TRY(cudaStreamSynchronize(s));
       cudaGraph_t graph;
       int64_t nl = 0;
       B2P_CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
@@ -1218,27 +1123,66 @@ static int plan_impl(b2p_handle h, const b2p_plan_config* pc, const float* x_ini
     B2P_CUDA_TRY(cudaGraphLaunch(ge->exec, s));
     launches += ge->launches;
   } else {
-    std::vector<int64_t> ts(T);
-    b2p_timesteps(pc->sched.num_train_timesteps, T, ts.data());
-    B2P_CUDA_TRY(cudaMemcpyAsync(h->p_tsteps, ts.data(), sizeof(int64_t) * T, cudaMemcpyHostToDevice, s));
-    B2P_CUDA_TRY(cudaStreamSynchronize(s));  // ts is a stack vector
     if ((rc = enqueue_plan(h, *pc, key, s, &launches))) return rc;
   }
   B2P_CUDA_TRY(cudaMemcpyAsync(out, h->p_out, sizeof(float) * B * hd, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
-  if (host) B2P_CUDA_TRY(cudaStreamSynchronize(s));
+  if (sync) B2P_CUDA_TRY(cudaStreamSynchronize(s));
   h->last_launches = launches;
   return B2P_OK;
 }
 
 int b2p_plan(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const float* feat, const float* target,
              const float* noise, const float* target_traj, const float* target_mask, float* out, int32_t B, void* stream) {
-  return plan_impl(h, pc, x_init, feat, target, noise, target_traj, target_mask, out, B, (cudaStream_t)stream, false);
+  return plan_impl(h, pc, x_init, feat, target, noise, target_traj, target_mask, out, B, (cudaStream_t)stream, false, false);
 }
 
 int b2p_plan_host(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const float* feat, const float* target,
                   const float* noise, const float* target_traj, const float* target_mask, float* out, int32_t B) {
   if (!h) return B2P_ERR_INVALID_ARG;
-  return plan_impl(h, pc, x_init, feat, target, noise, target_traj, target_mask, out, B, h->cap_stream, true);
+  return plan_impl(h, pc, x_init, feat, target, noise, target_traj, target_mask, out, B, h->cap_stream, true, true);
+}
+
+int b2p_plan_host_async(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const float* feat, const float* target,
+                        const float* noise, int32_t noise_batch, const float* target_traj, const float* target_mask, float* out,
+                        int32_t B) {
+  if (!h) return B2P_ERR_INVALID_ARG;
+  return plan_impl(h, pc, x_init, feat, target, noise, target_traj, target_mask, out, B, h->cap_stream, true, false, noise_batch);
+}
+
+int b2p_sync(b2p_handle h) {
+  if (!h) return B2P_ERR_INVALID_ARG;
+  B2P_CUDA_TRY(cudaSetDevice(h->device));
+  B2P_CUDA_TRY(cudaStreamSynchronize(h->cap_stream));
+  return B2P_OK;
+}
+
+// Independent planning requests sharded by batch over the GPUs of one box (the reference has a single caller
+// with a single batch, interact.py:115-168): contiguous split, the first B % n shards take one extra trajectory; every
+// handle's private stream gets its H2D copies, its captured loop and its D2H copy enqueued back to back, then all are
+// joined.  No collective, no peer access: the only inter-device traffic is host staging.
+int b2p_plan_sharded_host(const b2p_handle* handles, int32_t n_handles, const b2p_plan_config* pc, const float* x_init,
+                          const float* feat, const float* target, const float* noise, const float* target_traj,
+                          const float* target_mask, float* out, int32_t B) {
+  if (!handles || n_handles <= 0 || !pc || !x_init || !feat || !out || B <= 0) return B2P_ERR_INVALID_ARG;
+  for (int i = 0; i < n_handles; ++i) if (!handles[i]) return B2P_ERR_INVALID_ARG;
+  const int q = B / n_handles, r = B % n_handles;
+  int rc = B2P_OK, lo = 0;
+  for (int i = 0; i < n_handles && !rc; ++i) {
+    const int nb = q + (i < r ? 1 : 0);
+    if (nb == 0) continue;
+    b2p_handle h = handles[i];
+    const size_t hd = (size_t)h->H * h->D;
+    rc = plan_impl(h, pc, x_init + lo * hd, feat + (size_t)lo * h->dim, target ? target + (size_t)lo * 2 : nullptr,
+                   noise ? noise + lo * hd : nullptr, target_traj ? target_traj + lo * hd : nullptr,
+                   target_mask ? target_mask + lo * hd : nullptr, out + lo * hd, nb, h->cap_stream, true, false, B);
+    lo += nb;
+  }
+  for (int i = 0; i < n_handles; ++i) {   // join every device even after an error so no copy is left in flight on caller memory
+    cudaSetDevice(handles[i]->device);
+    cudaError_t e = cudaStreamSynchronize(handles[i]->cap_stream);
+    if (!rc && e != cudaSuccess) rc = (int)e;
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -110,6 +110,11 @@ struct SchedLaunch {
   const float* mo; const float* mo_u; float cfg_scale;
   const float* sample; const float* noise; const float* traj; const float* mask;
   float* prev; float* x0; int B, H, D; float eta, magic; int flags;
+  // in-kernel noise (K8 in SURVEY.md Appendix C): when `noise` is null and the step consumes noise, every thread draws its four
+  // N(0,1) values from Philox4x32-10 keyed by *seed (read at run time: a captured graph sees each plan's seed) with the
+  // counter (element group, noise_step)
+  const unsigned long long* seed; unsigned noise_step;
+  float* thr_scratch;   // [B] floats for the dynamic-threshold quantile (sample_max_value > 1); null => stream-ordered allocation
 };
 int launch_sched_step(const SchedLaunch& a, cudaStream_t s);
 

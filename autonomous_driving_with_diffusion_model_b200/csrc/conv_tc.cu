@@ -809,6 +809,16 @@ int tc_configure(TcArgs& a) {
   return (ntiles % a.cluster_l) ? B2P_ERR_INVALID_ARG : B2P_OK;
 }
 
+// Argument errors are reported through the handle (b2p_last_error), never on stderr: the message is kept per thread until the
+// caller (api.cu) attaches it to its handle.
+static thread_local char tc_err[256] = "";
+const char* tc_last_error() { return tc_err; }
+static int tc_fail(int line, const TcArgs& a, const char* what) {
+  snprintf(tc_err, sizeof(tc_err), "%s (conv_tc.cu:%d: T=%d TN=%d Cout=%d cg=%d L=%d n_out=%d cluster=%d/%d)", what, line, a.T, a.tile_n, a.Cout, a.cg,
+           a.Lrows, a.n_out, a.cluster_n, a.cluster_l);
+  return B2P_ERR_INVALID_ARG;
+}
+
 int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStream_t s) {
   TcArgs a = a_in;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("B2P_TC_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
@@ -816,16 +826,16 @@ int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStrea
   a.dbg |= (tc_trace_launch++ & 8191) << 8;
 #endif
   const int TN = a.tile_n;
-  if (TN != 64 && TN != 32 && TN != 16) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  if (a.T < 1 || a.T > 5 || a.n_out < 1 || a.n_out > 2 || (a.out_ldiv != 1 && a.out_ldiv != 2)) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  if (nsplit * (A_BYTES + a.T * TN * TC_K * 2) * 2 > (TN == 64 ? SmemPlan<64>::ring : (TN == 32 ? SmemPlan<32>::ring : SmemPlan<16>::ring))) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  if (a.Cout % TN || a.C[0] % TC_K || a.C[1] % TC_K || a.RC[0] % TC_K || a.RC[1] % TC_K || a.nrows <= 0) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  if (a.Lrows > 32 || (a.Lrows & (a.Lrows - 1)) || TC_M % a.Lrows) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  if (a.headW && (a.Cout != 64 || TN != 64 || a.head_dim > 8)) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  if (a.n_out == 2 && a.gn_gamma) { fprintf(stderr, "launch_conv_tc: GroupNorm with two outputs per row is not supported (single-use exchange barrier)\n"); return B2P_ERR_INVALID_ARG; }
-  if (a.n_out == 2 && (a.RC[0] || a.RC[1])) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
-  if (a.cluster_n < 1 || a.cluster_l < a.cluster_n || a.cluster_l % a.cluster_n || (a.cluster_n & (a.cluster_n - 1)) || (a.cluster_l & (a.cluster_l - 1))) { fprintf(stderr, "launch_conv_tc: tc_configure() was not applied\n"); return B2P_ERR_INVALID_ARG; }
-  if ((a.Cout / TN) % a.cluster_l) { fprintf(stderr, "launch_conv_tc: invalid argument (conv_tc.cu:%d) T=%d TN=%d Cout=%d cg=%d L=%d\n", __LINE__, a.T, a.tile_n, a.Cout, a.cg, a.Lrows); return B2P_ERR_INVALID_ARG; }
+  if (TN != 64 && TN != 32 && TN != 16) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (a.T < 1 || a.T > 5 || a.n_out < 1 || a.n_out > 2 || (a.out_ldiv != 1 && a.out_ldiv != 2)) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (nsplit * (A_BYTES + a.T * TN * TC_K * 2) * 2 > (TN == 64 ? SmemPlan<64>::ring : (TN == 32 ? SmemPlan<32>::ring : SmemPlan<16>::ring))) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (a.Cout % TN || a.C[0] % TC_K || a.C[1] % TC_K || a.RC[0] % TC_K || a.RC[1] % TC_K || a.nrows <= 0) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (a.Lrows > 32 || (a.Lrows & (a.Lrows - 1)) || TC_M % a.Lrows) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (a.headW && (a.Cout != 64 || TN != 64 || a.head_dim > 8)) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (a.n_out == 2 && a.gn_gamma) return tc_fail(__LINE__, a, "GroupNorm with two outputs per row is not supported (single-use exchange barrier)");
+  if (a.n_out == 2 && (a.RC[0] || a.RC[1])) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (a.cluster_n < 1 || a.cluster_l < a.cluster_n || a.cluster_l % a.cluster_n || (a.cluster_n & (a.cluster_n - 1)) || (a.cluster_l & (a.cluster_l - 1))) return tc_fail(__LINE__, a, "tc_configure() was not applied");
+  if ((a.Cout / TN) % a.cluster_l) return tc_fail(__LINE__, a, "invalid layer shape");
   dim3 grid((a.nrows + TC_M - 1) / TC_M, a.Cout / TN, 1);
   if (nsplit == 2) {
     if (TN == 64) return launch_t<2, 64>(maps, a, grid, s);

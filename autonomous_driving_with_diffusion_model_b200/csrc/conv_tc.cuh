@@ -52,5 +52,6 @@ int tc_make_weight_map(CUtensorMap* m, const void* base, int taps, int Cout, int
 int tc_pick_tile_n(int nrows, int Cout, bool has_head);
 int tc_configure(TcArgs& a);
 int launch_conv_tc(const TcMaps& maps, const TcArgs& a, int nsplit, cudaStream_t s);
+const char* tc_last_error();   // detail of the last B2P_ERR_INVALID_ARG returned by launch_conv_tc on this thread
 
 }  // namespace b2p

@@ -28,8 +28,33 @@ struct SchedK {
   int noise_on;       // t > 0
   int use_clipped;
   float eta, magic; int flags;
+  const unsigned long long* seed; unsigned noise_step;
   b2p_step_coeffs k;
 };
+
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so a thread's draw depends only on (seed, element group, step)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// four independent standard normals (Box-Muller on 24-bit uniforms; u1 in (0,1] so the log is finite)
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned group, unsigned step) {
+  const uint4 r = philox4x32_10(make_uint4(group, step, 0x6e6f6973u, 0x65u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  const float s24 = 1.0f / 16777216.0f;
+  const float u0 = (float)((r.x >> 8) + 1u) * s24, u1 = (float)(r.y >> 8) * s24;
+  const float u2 = (float)((r.z >> 8) + 1u) * s24, u3 = (float)(r.w >> 8) * s24;
+  const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+  float sa, ca, sb, cb;
+  sincospif(2.0f * u1, &sa, &ca);
+  sincospif(2.0f * u3, &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
 
 __device__ __forceinline__ float x0_of(const SchedK& a, float m, float x) {
   if (a.pred == B2P_PRED_SAMPLE) return m;
@@ -89,6 +114,7 @@ __global__ void __launch_bounds__(256) sched_step_kernel(SchedK a) {
   float4 mu = a.mo_u ? __ldg(reinterpret_cast<const float4*>(a.mo_u) + i4) : z;
   float4 x = __ldg(reinterpret_cast<const float4*>(a.sample) + i4);
   float4 nz = a.noise ? __ldg(reinterpret_cast<const float4*>(a.noise) + i4) : z;
+  if (!a.noise && a.seed) nz = philox_normal4(*a.seed, (unsigned)i4, a.noise_step);
   float4 tj = a.traj ? __ldg(reinterpret_cast<const float4*>(a.traj) + i4) : z;
   float4 mk = a.mask ? __ldg(reinterpret_cast<const float4*>(a.mask) + i4) : z;
   float4 o, x0;
@@ -138,6 +164,13 @@ __global__ void __launch_bounds__(128) threshold_s_kernel(SchedK a, float ratio,
   }
 }
 
+// the noise tensor [steps, n] a plan with noise == NULL consumes (same counters as sched_step_kernel: group = element / 4, step)
+__global__ void __launch_bounds__(256) philox_fill_kernel(unsigned long long seed, int groups_per_step, int steps, float* out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x, st = blockIdx.y;
+  if (g >= groups_per_step || st >= steps) return;
+  reinterpret_cast<float4*>(out)[(size_t)st * groups_per_step + g] = philox_normal4(seed, (unsigned)g, (unsigned)st);
+}
+
 int launch_sched_step(const SchedLaunch& L, cudaStream_t s) {
   if (!L.mo || !L.sample || !L.prev || L.B <= 0) return B2P_ERR_INVALID_ARG;
   int n = L.B * L.H * L.D;
@@ -155,12 +188,17 @@ int launch_sched_step(const SchedLaunch& L, cudaStream_t s) {
   a.use_clipped = (L.flags & B2P_STEP_USE_CLIPPED_OUTPUT) ? 1 : 0;
   a.eta = L.eta; a.magic = L.magic; a.flags = L.flags; a.k = L.k;
   bool needs_noise = (a.ddpm && a.noise_on) || (a.inpaint && a.traj && a.mask && a.noise_on) || (!a.ddpm && a.eta > 0.f);
-  if (needs_noise && !L.noise) return B2P_ERR_INVALID_ARG;
+  if (needs_noise && !L.noise && !L.seed) return B2P_ERR_INVALID_ARG;
+  a.seed = (needs_noise && !L.noise) ? L.seed : nullptr;
+  a.noise_step = L.noise_step;
   float* thr = nullptr;
   if (a.clip_mode == 3) {
-    B2P_CUDA_TRY(cudaMallocAsync((void**)&thr, sizeof(float) * L.B, s));
-    threshold_s_kernel<<<L.B, 128, sizeof(float) * a.HD, s>>>(a, L.sc.dynamic_thresholding_ratio, L.sc.sample_max_value, thr);
-    a.thr_s = thr;
+    // inside a plan the handle lends a scratch vector (no allocation node in the captured graph); the stand-alone step entry
+    // has no handle and takes a stream-ordered allocation
+    float* ts = L.thr_scratch;
+    if (!ts) { B2P_CUDA_TRY(cudaMallocAsync((void**)&thr, sizeof(float) * L.B, s)); ts = thr; }
+    threshold_s_kernel<<<L.B, 128, sizeof(float) * a.HD, s>>>(a, L.sc.dynamic_thresholding_ratio, L.sc.sample_max_value, ts);
+    a.thr_s = ts;
   }
   int n4 = n / 4;
   cudaError_t le = launch_pdl(sched_step_kernel, dim3((n4 + 255) / 256), dim3(256), 0, s, a);
@@ -242,12 +280,19 @@ extern "C" int b2p_step_coeffs_compute(const b2p_sched_config* sc, const float* 
   return B2P_OK;
 }
 
+extern "C" int b2p_philox_normal(uint64_t key, int32_t steps, int64_t n_per_step, float* out, void* stream) {
+  if (!out || steps <= 0 || n_per_step <= 0 || n_per_step % 4 != 0 || n_per_step / 4 > 0x7fffffff) return B2P_ERR_INVALID_ARG;
+  const int groups = (int)(n_per_step / 4);
+  b2p::philox_fill_kernel<<<dim3((groups + 255) / 256, steps), 256, 0, (cudaStream_t)stream>>>(key, groups, steps, out);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int b2p_sched_step(const b2p_sched_config* sc, const b2p_step_coeffs* k, const float* model_output,
                               const float* model_output_uncond, float cfg_scale, const float* sample, const float* noise,
                               const float* target_traj, const float* target_mask, float* prev_out, float* x0_out,
                               int32_t B, int32_t H, int32_t D, float eta, float magic_num, int32_t flags, void* stream) {
   if (!sc || !k) return B2P_ERR_INVALID_ARG;
   b2p::SchedLaunch L{*sc, *k, model_output, model_output_uncond, cfg_scale, sample, noise, target_traj, target_mask,
-                     prev_out, x0_out, B, H, D, eta, magic_num, flags};
+                     prev_out, x0_out, B, H, D, eta, magic_num, flags, nullptr, 0u, nullptr};
   return b2p::launch_sched_step(L, (cudaStream_t)stream);
 }

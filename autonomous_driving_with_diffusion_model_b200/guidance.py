@@ -1,19 +1,17 @@
 """Classifier guidance behind the reference's ``GuidanceLoss`` surface (control/guidance.py:18-59).
 
-Fast path: when the guided tensor was assembled the way interact.py:154-160 does (``cat[cat[0, state_pred(action[:, :-1],
-time_embed)], action]``) the whole update — TargetGuidance index rule, analytic gradient through TrajPredict, scaled
-update, clip — is ONE kernel (``b2p_classifier_guidance``).  Otherwise the generic path below reproduces the reference
-with torch.autograd (our ``state_pred`` is autograd-aware through its VJP kernel).
+This module is the drop-in for the UNMODIFIED loop (interact.py:154-163): the same statements as the reference, with
+torch.autograd running through our ``state_pred`` (its backward is the hand-written VJP kernel ``b2p_state_pred_vjp``).
+The fully fused form — TargetGuidance index rule, analytic gradient through TrajPredict, scaled update and clip in ONE
+kernel — is what ``DiffusionPlanner.plan`` / ``b2p_plan`` run inside the captured loop, and is exported for non-Python
+hosts as ``b2p_classifier_guidance``.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Union
 
 import torch
 import torch.nn as nn
-
-from . import _lib
 
 
 def convert(loss_config):
@@ -52,27 +50,8 @@ class GuidanceLoss(nn.Module):
             total = total + loss(x, target)
         return total
 
-    def _fused_context(self, x_guidance, action):
-        """Returns (model, time_embed) if ``x_guidance`` carries the provenance the planner / model attach, else None."""
-        ctx = getattr(x_guidance, "_b2p_guidance_ctx", None)
-        if ctx is None or self.guidance_step != 1 or len(self.loss_list) != 1 or not isinstance(self.loss_list[0], TargetGuidance):
-            return None
-        return ctx
-
     def forward(self, x_guidance: torch.Tensor, action: torch.Tensor, target: torch.Tensor,
                 grad_scale: Union[float, torch.Tensor] = None) -> torch.Tensor:
-        ctx = self._fused_context(x_guidance, action)
-        if ctx is not None:
-            model, time_embed = ctx
-            x = x_guidance.detach().contiguous().float()
-            B = x.shape[0]
-            tg = target.detach().to(x.device, torch.float32).reshape(-1, 2).expand(B, 2).contiguous()
-            gs = 1.0 if grad_scale is None else float(grad_scale)
-            h = model._handle_for(x.device)
-            rc = _lib.load().b2p_classifier_guidance(h, _lib.ptr(x), _lib.ptr(time_embed), _lib.ptr(tg), gs, float(self.scale), B,
-                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
-            _lib.check(rc, h, "b2p_classifier_guidance")
-            return x
         # generic path: same statements as the reference, autograd through our VJP-backed state_pred
         for _ in range(self.guidance_step):
             with torch.enable_grad():

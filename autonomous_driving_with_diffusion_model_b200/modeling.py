@@ -192,6 +192,18 @@ class ImageEncoder(_Tree):
         object.__setattr__(self, "_tlist", None)
         return super()._apply(fn, *args, **kwargs)
 
+    def invalidate(self):
+        """Drop the folded weights and the captured graphs (needed after a write the version counters cannot see, e.g.
+        through ``param.data``)."""
+        object.__setattr__(self, "_tlist", None)
+        object.__setattr__(self, "_fold_cache", None)
+        object.__setattr__(self, "_graphs", {})
+        object.__setattr__(self, "_gen", getattr(self, "_gen", 0) + 1)
+
+    def weights_key(self) -> tuple:
+        """Identifies the current encoder weights: (generation, sum of version counters)."""
+        return (getattr(self, "_gen", 0), sum([t._version for t in self._tensors()]))
+
     def _folded(self):
         key = tuple([(t.data_ptr(), t._version) for t in self._tensors()])
         cache = getattr(self, "_fold_cache", None)
@@ -324,6 +336,10 @@ class TemporalMapUnet(nn.Module):
         self._feat_cache: Optional[tuple] = None
         self._tensor_list: Optional[list] = None
         self._tensor_gen = 0
+        import weakref
+        me = weakref.ref(self)
+        for p in self.parameters():             # lets checkpoint.copy_parameters find the model that owns a parameter
+            object.__setattr__(p, "_b2p_owner", me)
 
     # ---- C handle management --------------------------------------------------------------------------
     def _unet_items(self) -> Iterable[Tuple[str, torch.Tensor]]:
@@ -346,12 +362,27 @@ class TemporalMapUnet(nn.Module):
         return (self._tensor_gen, sum([t._version for t in ts]))
 
     def _apply(self, fn, *args, **kwargs):
-        self._tensor_list, self._tensor_gen = None, getattr(self, "_tensor_gen", 0) + 1
-        return super()._apply(fn, *args, **kwargs)
+        self._tensor_list, self._tensor_gen, self._feat_cache = None, getattr(self, "_tensor_gen", 0) + 1, None
+        out = super()._apply(fn, *args, **kwargs)
+        import weakref
+        me = weakref.ref(self)
+        for p in self.parameters():             # .to()/.half() may replace Parameter objects
+            object.__setattr__(p, "_b2p_owner", me)
+        return out
 
     def load_state_dict(self, *args, **kwargs):
-        self._tensor_list, self._tensor_gen = None, getattr(self, "_tensor_gen", 0) + 1
+        self._tensor_list, self._tensor_gen, self._feat_cache = None, getattr(self, "_tensor_gen", 0) + 1, None
         return super().load_state_dict(*args, **kwargs)
+
+    def invalidate_weights(self) -> "TemporalMapUnet":
+        """Force the packed device weights, the folded encoder weights, the encoder graphs and the cached image feature to
+        be rebuilt on the next call.  In-place updates (``p.copy_()``, optimizers, ``load_state_dict``, ``.to()``) are
+        detected automatically through the tensors' version counters; a write through ``param.data`` (the idiom of the
+        reference's misc/load_param.copy_parameters and of EMA ``copy_to``) does NOT bump them, so call this afterwards —
+        ``checkpoint.copy_parameters`` does."""
+        self._tensor_list, self._tensor_gen, self._feat_cache = None, self._tensor_gen + 1, None
+        self.perception.invalidate()
+        return self
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -412,13 +443,16 @@ class TemporalMapUnet(nn.Module):
             pass
 
     # ---- conditioning feature -------------------------------------------------------------------------
-    def encode(self, img: torch.Tensor) -> torch.Tensor:
+    def encode(self, img: torch.Tensor, use_cache: bool = True) -> torch.Tensor:
         """perception(img) with a one-entry cache: the reference re-runs the encoder inside every denoising step
-        (modeling/temporal.py:203); in eval mode the feature is step-invariant, so it is computed once per image tensor."""
+        (modeling/temporal.py:203); in eval mode the feature is step-invariant, so it is computed once per image tensor.
+        The cache key covers the image tensor (address, version, geometry) AND the encoder weights (generation + version
+        counters).  Pass ``use_cache=False`` for a frame buffer that an external producer (DLPack, cupy, ``.data``) refills
+        in place without bumping its version counter."""
         if img.dim() == 2:
             return img
-        key = (img.data_ptr(), img._version, tuple(img.shape), tuple(img.stride()), img.device)
-        if self._feat_cache is not None and self._feat_cache[0] == key:
+        key = (img.data_ptr(), img._version, tuple(img.shape), tuple(img.stride()), img.device, self._tensor_gen, self.perception.weights_key())
+        if use_cache and self._feat_cache is not None and self._feat_cache[0] == key:
             return self._feat_cache[1]
         with torch.no_grad():
             feat = self.perception(img).float().contiguous()

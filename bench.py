@@ -9,10 +9,15 @@ final clamp/scale for a batch of B trajectories per GPU.  Default workload = BAS
 configs/default.yaml (NO_GUIDANCE), GuidanceDDIMScheduler, EVAL.SAMPLE_STEPS = 100, B = 256 per GPU, precomputed
 image feature [B,64] (the encoder is hoisted out of the loop, SURVEY.md §8d "loop-only").  Weak scaling: every rank
 plans its own 256 trajectories, no collective on the data path; torch.distributed is only used for the timing barrier
-and the max-over-ranks reduction.
+and the max-over-ranks reduction.  The same line also carries strong-scaling figures (fixed global batch 4096, configs 2
+and 3) and, at N > 1, the one-process multi-GPU entry (DiffusionPlanner.plan_sharded) driven from rank 0.
 
 `--impl reference` times the reference's algorithm on the host CPU cores (oracle port of the reference PyTorch code:
-/root/reference does not exist on the GPU box and diffusers is not installed) on the same config.
+/root/reference does not exist on the GPU box and diffusers is not installed): every step is ONE WHOLE
+plan of the same workload (B trajectories, T iterations) — nothing is extrapolated.
+
+CPU legs (cpu_baseline, the BASELINE.md §3 matrix, the per-mode report) run at N = 1 only: under torchrun the other
+ranks would sit in a barrier for minutes and torchrun pins OMP_NUM_THREADS=1.
 """
 from __future__ import annotations
 
@@ -28,10 +33,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank and MKL / oneDNN read it when torch is imported, which
+    # torch.set_num_threads cannot undo: the reference arm (rank 0 only) must see all host cores
+    os.environ.pop("OMP_NUM_THREADS", None)
+    os.environ.pop("MKL_NUM_THREADS", None)
+
 import torch  # noqa: E402
 
 FLOPS_PER_EVAL = {"NO_GUIDANCE": 78_874_624, "FREE_GUIDANCE": 78_883_072, "CLASSIFIER_GUIDANCE": 80_845_952}
 SCHED = {"ddim": "guidance_ddim", "ddpm": "guidance_ddpm", "inpainting_ddim": "inpainting_ddim", "inpainting_ddpm": "inpainting_ddpm"}
+STRONG_GLOBAL_BATCH = 4096
 
 
 def parse():
@@ -47,9 +59,11 @@ def parse():
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
                     help="bf16x3 = tcgen05 with bf16 hi/lo split operands (3 MMAs, fp32 accumulate): meets the fp32 parity bound (<=1e-3)")
     ap.add_argument("--no-other-precisions", action="store_true")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip cpu_baseline and the BASELINE.md §3 CPU matrix")
     ap.add_argument("--no-modes", action="store_true", help="skip the per-mode report (SURVEY.md 8d configs 1, 3, 4) and the encoder figure")
-    ap.add_argument("--cpu-sample-iters", type=int, default=5, help="denoising iterations per timed CPU sample")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling / one-process multi-GPU figures")
+    ap.add_argument("--cpu-budget-s", type=float, default=10.0, help="CPU seconds spent on the in-line cpu_baseline sample (whole plans)")
+    ap.add_argument("--cpu-sample-iters", type=int, default=0, help="(ignored; kept for old command lines — CPU legs time whole plans)")
     return ap.parse_args()
 
 
@@ -68,8 +82,7 @@ def b1_roofline(p50_ms: float, nfe: int, weight_bytes: int, pk: dict) -> dict:
     return {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
             "algorithmic_bytes_per_evaluation": weight_bytes, "evaluations_per_plan": nfe, "peak_source": pk["source"] + ", copy bandwidth",
             "note": "weights (fp32, K-major) are L2-resident across the iterations, so the HBM copy peak is the conservative denominator; "
-                    "the plan is a chain of ~43 dependent launches per iteration at ~3.9 us each (profiles/r01_gemv_stage_trace_b1.txt), "
-                    "latency-bound, not bandwidth-bound"}
+                    "the plan is a chain of dependent launches per iteration, latency-bound, not bandwidth-bound"}
 
 
 def workload_name(a):
@@ -77,79 +90,158 @@ def workload_name(a):
 
 
 # --------------------------------------------------------------------------------------------------------------
-# CPU side (oracle port of the reference): used for cpu_baseline and for --impl reference
+# CPU side (oracle port of the reference): cpu_baseline, the BASELINE.md §3 matrix and --impl reference
 # --------------------------------------------------------------------------------------------------------------
-def cpu_iterations(a, n_iters: int, B: int):
-    """Time n_iters denoising iterations of the reference algorithm on the host cores; returns seconds per iteration."""
-    from oracle import schedulers as S
-    from oracle import unet as U
-    from oracle import weights as W
+_CPU_SD = {}
 
-    if not hasattr(cpu_iterations, "_state"):
-        sd = W.make_state_dict(a.mode, seed=0, with_perception=False)
-        inp = W.synth_inputs(B, a.timesteps if a.sched != "ddim" else 0, seed=1)
-        cpu_iterations._state = (sd, inp, S.alphas_cumprod(100), S.SchedCfg(num_inference_steps=a.timesteps))
-    sd, inp, ac, cfg = cpu_iterations._state
-    x = inp["x"].clone()
-    ts = S.leading_timesteps(100, a.timesteps)[:n_iters]
+
+def _cpu_state(mode: str, with_perception: bool = False):
+    from autonomous_driving_with_diffusion_model_b200 import synthetic as W
+
+    key = (mode, with_perception)
+    if key not in _CPU_SD:
+        _CPU_SD[key] = W.make_state_dict(mode, seed=0, with_perception=with_perception)
+    return _CPU_SD[key]
+
+
+def cpu_plan(mode: str, kind: str, T: int, B: int, inp=None, seed: int = 1):
+    """ONE whole plan of the reference algorithm on the host cores (oracle/plan.py restates interact.py:115-168); returns seconds."""
+    from autonomous_driving_with_diffusion_model_b200 import synthetic as W
+    from oracle import plan as OP
+
+    sd = _cpu_state(mode)
+    if inp is None:
+        inp = W.synth_inputs(B, T if kind != "guidance_ddim" else 0, seed=seed)
+    inpaint = kind.startswith("inpainting")
+    kw = dict(target=inp["target"] if mode != "NO_GUIDANCE" and not inpaint else None, noise=inp["noise"],
+              target_traj=inp["target_traj"] if inpaint else None, target_mask=inp["mask"] if inpaint else None)
+    if mode == "FREE_GUIDANCE" and kw["target"] is None:
+        kw["target"] = inp["target"]
     t0 = time.perf_counter()
-    with torch.no_grad():
-        for i, t in enumerate(ts):
-            t = int(t)
-            tt = torch.full((B,), t, dtype=torch.long)
-            if a.mode == "FREE_GUIDANCE":
-                cond = torch.cat([inp["target"], torch.zeros_like(inp["target"])], 0)
-                c, u = U.unet_forward(sd, torch.cat([x, x], 0), inp["feat"], torch.tensor([t]), cond, a.mode).chunk(2, 0)
-                mo = u + 7.5 * (c - u)
-            else:
-                mo = U.unet_forward(sd, x, inp["feat"], tt, None, a.mode)
-            if a.sched.endswith("ddim"):
-                x, _ = S.ddim_step(cfg, ac, mo, t, x, inpainting=a.sched.startswith("inpainting"))
-            else:
-                x, _ = S.ddpm_step(cfg, ac, mo, t, x, variance_noise=inp["noise"][i], inpainting=a.sched.startswith("inpainting"))
-            x[:, 0, :3] = 0.0
-    return (time.perf_counter() - t0) / len(ts)
+    OP.plan(sd, mode, kind, inp["x"], inp["feat"], T, **kw)
+    return time.perf_counter() - t0
+
+
+def cpu_whole_plans(mode: str, kind: str, T: int, B: int, min_reps: int = 2, budget_s: float = 10.0, max_reps: int = 8, warm: bool = True):
+    """Bounded sample: whole plans until `budget_s` seconds are spent (at least min_reps, at most max_reps)."""
+    from autonomous_driving_with_diffusion_model_b200 import synthetic as W
+
+    inp = W.synth_inputs(B, T if kind != "guidance_ddim" else 0, seed=1)
+    if warm:
+        cpu_plan(mode, kind, min(T, 2), B)     # thread pool / oneDNN primitive warm-up (not a timed step)
+    ts, t_begin = [], time.perf_counter()
+    while len(ts) < min_reps or (time.perf_counter() - t_begin < budget_s and len(ts) < max_reps):
+        ts.append(cpu_plan(mode, kind, T, B, inp))
+    return ts
 
 
 def cpu_config0(reps: int = 3):
     """BASELINE.json configs[0]: default.yaml, no guidance, DDPM, T=100, batch 1, on the host cores (whole plans, loop only:
     the image feature is precomputed as on the GPU arm)."""
-    from oracle import plan as OP
-    from oracle import weights as W
-
-    sd = W.make_state_dict("NO_GUIDANCE", seed=0, with_perception=False)
-    inp = W.synth_inputs(1, 100, seed=1)
-    run = lambda: OP.plan(sd, "NO_GUIDANCE", "guidance_ddpm", inp["x"], inp["feat"], 100, noise=inp["noise"])  # noqa: E731
-    run()
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        run()
-        ts.append(time.perf_counter() - t0)
+    ts = cpu_whole_plans("NO_GUIDANCE", "guidance_ddpm", 100, 1, min_reps=reps, budget_s=0.0, max_reps=reps, warm=True)
     ms = statistics.median(ts) * 1e3
     return {"ms_per_plan_p50": ms, "traj_per_s": 1e3 / ms, "batch": 1, "T": 100, "sched": "guidance_ddpm", "cores": torch.get_num_threads(),
             "sample": f"{reps} whole plans (oracle port, fp32, precomputed feature)"}
+
+
+def cpu_matrix(batch: int = 256):
+    """the reference's CPU path for configs 1-4 at B in {1, batch}, hoisted (loop only, the like-for-like
+    counterpart of the GPU numbers) and as-is (ResNet-34 re-run inside every denoising step, modeling/temporal.py:203).
+    Whole plans, median; the as-is figures run the encoder on a bounded number of frames and say so."""
+    from autonomous_driving_with_diffusion_model_b200 import synthetic as W
+    from oracle import unet as U
+
+    out = {"cores": torch.get_num_threads(), "precision": "fp32", "kind": "port"}
+    cases = {"config1_noguidance_ddpm100": ("NO_GUIDANCE", "guidance_ddpm", 100, 2, 2),
+             "config2_noguidance_ddim100": ("NO_GUIDANCE", "guidance_ddim", 100, 2, 0),
+             "config3_cfg_ddim10_scale7.5": ("FREE_GUIDANCE", "guidance_ddim", 10, 3, 2),
+             "config4a_classifier_ddim2_scale15": ("CLASSIFIER_GUIDANCE", "guidance_ddim", 2, 3, 2),
+             "config4b_classifier_inpainting_ddim2": ("CLASSIFIER_GUIDANCE", "inpainting_ddim", 2, 3, 2)}
+    for name, (mode, kind, T, reps1, repsB) in cases.items():
+        row = {}
+        for B, reps in ((1, reps1), (batch, repsB)):
+            if reps == 0:
+                continue        # config 2 at B=batch is the cpu_baseline value itself
+            ts = cpu_whole_plans(mode, kind, T, B, min_reps=reps, budget_s=0.0, max_reps=reps)
+            s = statistics.median(ts)
+            row[f"b{B}"] = {"s_per_plan": s, "traj_per_s": B / s, "whole_plans": reps}
+        out[name] = row
+    # as-is: the encoder runs inside every step (temporal.py:203).  One ResNet-34 pass per frame is timed on a bounded number
+    # of frames (1 and 8); a plan of T steps on B frames = hoisted plan + T x B x (per-frame encoder time).
+    try:
+        sdp = _cpu_state("NO_GUIDANCE", with_perception=True)
+        enc = {}
+        for S in (1, 8):
+            img = W.synth_image(S, seed=2)
+            with torch.no_grad():
+                U.resnet34_feature(sdp, img)
+                ts = []
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    U.resnet34_feature(sdp, img)
+                    ts.append(time.perf_counter() - t0)
+            enc[S] = min(ts) / S
+        out["encoder_s_per_frame"] = {"batch1": enc[1], "batch8": enc[8], "frames_timed": "1 and 8 frames, 3x256x900 fp32, best of 2"}
+        t0 = time.perf_counter()
+        _cpu_as_is_plan(sdp, T=10)
+        as_is_10 = time.perf_counter() - t0
+        h1 = out["config1_noguidance_ddpm100"]["b1"]["s_per_plan"]
+        out["config1_as_is_b1"] = {"measured_s_per_plan_T10": as_is_10, "s_per_plan_T100": h1 + 100 * enc[1], "traj_per_s": 1.0 / (h1 + 100 * enc[1]),
+                                   "how": "DDPM-10 as-is plan measured whole (encoder inside each of the 10 steps); the T=100 figure = measured hoisted "
+                                          "DDPM-100 plan + 100 x measured per-frame encoder time"}
+        hb = out["config1_noguidance_ddpm100"][f"b{batch}"]["s_per_plan"]
+        out[f"config1_as_is_b{batch}"] = {"s_per_plan_T100": hb + 100 * batch * enc[8], "traj_per_s": batch / (hb + 100 * batch * enc[8]),
+                                          "how": f"measured hoisted DDPM-100 plan at B={batch} + 100 steps x {batch} frames x measured per-frame encoder time "
+                                                 "(8-frame batches); running 25,600 ResNet-34 passes on the host would take ~half an hour"}
+    except Exception as exc:  # report-only
+        out["as_is_error"] = repr(exc)[:200]
+    return out
+
+
+def _cpu_as_is_plan(sdp, T: int = 10):
+    """The reference loop as shipped at B=1: perception(img) inside every step (modeling/temporal.py:203, interact.py:132-164)."""
+    from autonomous_driving_with_diffusion_model_b200 import synthetic as W
+    from oracle import schedulers as S
+    from oracle import unet as U
+
+    inp = W.synth_inputs(1, T, seed=1)
+    img = W.synth_image(1, seed=2)
+    ac, cfg = S.alphas_cumprod(100), S.SchedCfg(num_inference_steps=T)
+    x = inp["x"].clone()
+    with torch.no_grad():
+        for i, t in enumerate(S.leading_timesteps(100, T)):
+            feat = U.resnet34_feature(sdp, img)
+            mo = U.unet_forward(sdp, x, feat, torch.tensor([int(t)]), None, "NO_GUIDANCE")
+            x, _ = S.ddpm_step(cfg, ac, mo, int(t), x, variance_noise=inp["noise"][i])
+            x[:, 0, :3] = 0.0
+    return x
 
 
 def run_reference_arm(a, rank: int):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    B, T, n = a.batch, a.timesteps, max(1, min(a.cpu_sample_iters, a.timesteps))
+    B, T, kind = a.batch, a.timesteps, SCHED[a.sched]
+    from autonomous_driving_with_diffusion_model_b200 import synthetic as W
+
+    inp = W.synth_inputs(B, T if kind != "guidance_ddim" else 0, seed=1)
+    t_run = time.perf_counter()
     for _ in range(a.warmup):
-        cpu_iterations(a, 1, B)
-    per_iter = [cpu_iterations(a, n, B) for _ in range(a.steps)]
-    plan_s = statistics.mean(per_iter) * T
+        cpu_plan(a.mode, kind, T, B, inp)
+    steps = [cpu_plan(a.mode, kind, T, B, inp) for _ in range(a.steps)]
+    wall = time.perf_counter() - t_run
+    plan_s = statistics.mean(steps)
     value = B / plan_s
-    sample = (f"each step = {n} of the {T} denoising iterations at B={B} (every iteration runs the same denoiser + scheduler step), "
-              f"extrapolated x{T}/{n}; oracle port of the reference PyTorch code, fp32, torch CPU {torch.get_num_threads()} threads")
+    sample = (f"each step = one WHOLE plan (B={B} trajectories, all {T} denoising iterations, nothing extrapolated); oracle port of the reference "
+              f"PyTorch code, fp32, torch CPU {torch.get_num_threads()} threads; the sample is B={B} at every --gpus N (CPU throughput does not "
+              f"depend on how many GPUs the other arm uses)")
     line = {"impl": "reference", "metric": "trajectories_per_sec_full_sampling_loop", "value": value, "unit": "trajectories/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": plan_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "timed_region_s": sum(steps), "wall_s_incl_warmup": wall}
     print(json.dumps(line), flush=True)
 
 
@@ -196,6 +288,18 @@ class ClockSampler:
         return out
 
 
+def _cfg_for(P, mode, T, precision):
+    return P.load_cfg(TRAIN=dict(USE_COND=mode), EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION=precision),
+                      GUIDANCE=dict(USE_COND=mode, FREE_SCALE=7.5, CLASSIFIER_SCALE=15.0,
+                                    LOSS_LIST=[["TargetGuidance", []]] if mode == "CLASSIFIER_GUIDANCE" else None))
+
+
+def _sched_for(P, kind, cfg):
+    cls = {"guidance_ddim": P.GuidanceDDIMScheduler, "guidance_ddpm": P.GuidanceDDPMScheduler,
+           "inpainting_ddim": P.InpaintingDDIMScheduler, "inpainting_ddpm": P.InpaintingDDPMScheduler}[kind]
+    return cls(cfg=cfg, **P.scheduler_kwargs(cfg)) if kind.startswith("guidance") else cls(**P.scheduler_kwargs(cfg))
+
+
 def mode_report(P, W, dev, B: int, precision: str):
     """throughput at B trajectories and batch-1 p50 plan latency for the other BASELINE.json configs, plus the
     end-to-end figure with the image encoder in front of the loop (rank 0 only, a few plans each; report-only numbers)."""
@@ -206,19 +310,14 @@ def mode_report(P, W, dev, B: int, precision: str):
         "config4a_classifier_ddim2_scale15": ("CLASSIFIER_GUIDANCE", "guidance_ddim", 2),
         "config4b_classifier_inpainting_ddim2": ("CLASSIFIER_GUIDANCE", "inpainting_ddim", 2),
     }
-    classes = {"guidance_ddim": P.GuidanceDDIMScheduler, "guidance_ddpm": P.GuidanceDDPMScheduler,
-               "inpainting_ddim": P.InpaintingDDIMScheduler, "inpainting_ddpm": P.InpaintingDDPMScheduler}
     models, out = {}, {}
     for name, (mode, kind, T) in cases.items():
-        cfg = P.load_cfg(TRAIN=dict(USE_COND=mode), EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION=precision),
-                         GUIDANCE=dict(USE_COND=mode, FREE_SCALE=7.5, CLASSIFIER_SCALE=15.0,
-                                       LOSS_LIST=[["TargetGuidance", []]] if mode == "CLASSIFIER_GUIDANCE" else None))
+        cfg = _cfg_for(P, mode, T, precision)
         if mode not in models:
             m = P.build_model(cfg)
             m.load_state_dict(W.make_state_dict(mode, seed=0))
             models[mode] = m.to(dev).eval()
-        sched = classes[kind](cfg=cfg, **P.scheduler_kwargs(cfg)) if kind.startswith("guidance") else classes[kind](**P.scheduler_kwargs(cfg))
-        planner = P.DiffusionPlanner(models[mode], sched, cfg)
+        planner = P.DiffusionPlanner(models[mode], _sched_for(P, kind, cfg), cfg)
         inp = W.synth_inputs(B, T, seed=2)
         needs_noise, inpaint = kind != "guidance_ddim", kind.startswith("inpainting")
         dd = dict(target=inp["target"].to(dev) if mode != "NO_GUIDANCE" and not inpaint else None,
@@ -248,11 +347,21 @@ def mode_report(P, W, dev, B: int, precision: str):
             lat.append((time.perf_counter() - t0) * 1e3)
         out[name] = {"traj_per_s": B / (ms * 1e-3), "ms_per_plan": ms, "batch": B, "latency_b1_p50_ms": statistics.median(lat),
                      "launches_per_plan": planner.last_launch_count()}
+        if kind == "guidance_ddpm":     # the same plan with the noise drawn inside the scheduler kernel (no [T,B,H,D] tensor)
+            for _ in range(2):
+                planner.plan(x, f)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                planner.plan(x, f)
+            e1.record()
+            torch.cuda.synchronize()
+            out[name]["traj_per_s_in_kernel_noise"] = B * reps / (e0.elapsed_time(e1) * 1e-3)
     # large-batch regime: the same kernels when a layer has hundreds of row tiles instead of 4..32
     try:
         mode, kind, T, BL = "NO_GUIDANCE", "guidance_ddim", 10, 4096
-        cfg = P.load_cfg(EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION=precision))
-        planner = P.DiffusionPlanner(models[mode], P.GuidanceDDIMScheduler(cfg=cfg, **P.scheduler_kwargs(cfg)), cfg)
+        cfg = _cfg_for(P, mode, T, precision)
+        planner = P.DiffusionPlanner(models[mode], _sched_for(P, kind, cfg), cfg)
         g = torch.Generator(device=dev).manual_seed(5)
         x, f = torch.randn(BL, 16, 7, device=dev, generator=g), torch.randn(BL, 64, device=dev, generator=g)
         for _ in range(2):
@@ -274,11 +383,11 @@ def mode_report(P, W, dev, B: int, precision: str):
     # end to end with the image encoder: one ResNet-34 pass per distinct scene (hoisted out of the loop), then the DDIM-100 loop
     try:
         mode, kind, T = "NO_GUIDANCE", "guidance_ddim", 100
-        cfg = P.load_cfg(EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION=precision))
+        cfg = _cfg_for(P, mode, T, precision)
         m = P.build_model(cfg)
         m.load_state_dict(W.make_state_dict(mode, seed=0, with_perception=True))
         m = m.to(dev).eval()
-        planner = P.DiffusionPlanner(m, P.GuidanceDDIMScheduler(cfg=cfg, **P.scheduler_kwargs(cfg)), cfg)
+        planner = P.DiffusionPlanner(m, _sched_for(P, kind, cfg), cfg)
         for scenes in sorted({min(16, B), B}):
             img = torch.randn(scenes, 3, 256, 900, device=dev, generator=torch.Generator(device=dev).manual_seed(2))   # ImageNet-normalised frames
             x = W.synth_inputs(B, 0, seed=2)["x"].to(dev)
@@ -307,15 +416,14 @@ def mode_report(P, W, dev, B: int, precision: str):
             torch.cuda.synchronize()
             out[f"with_encoder_{scenes}_scenes"] = {"traj_per_s": B / (e1.elapsed_time(e2) / 3 * 1e-3), "ms_per_plan": e1.elapsed_time(e2) / 3,
                                                     "encoder_ms": e0.elapsed_time(e1) / 3, "batch": B, "image": "3x256x900 fp32 per scene",
-                                                    "encoder": "ResNet-34 on torch/cuDNN (library code, SURVEY 8f rank 1), one pass per scene, hoisted"}
+                                                    "encoder": f"ResNet-34 on torch/cuDNN ({getattr(m.perception, 'compute_dtype', 'fp32')}, channels-last, folded BN; "
+                                                               "library code, SURVEY 8f rank 1), one pass per scene, hoisted"}
             del img
         # closed-loop tick at batch 1: a NEW camera frame every tick (interact.py:170-176 -> generate_traj), encoder included
         frames = [torch.randn(1, 3, 256, 900, device=dev) for _ in range(4)]
         for name, (mode, kind, T) in (("tick_noguidance_ddim100", ("NO_GUIDANCE", "guidance_ddim", 100)), ("tick_cfg_ddim10", cases["config3_cfg_ddim10_scale7.5"]),
                                       ("tick_classifier_ddim2", cases["config4a_classifier_ddim2_scale15"])):
-            cfg = P.load_cfg(TRAIN=dict(USE_COND=mode), EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION=precision),
-                             GUIDANCE=dict(USE_COND=mode, FREE_SCALE=7.5, CLASSIFIER_SCALE=15.0,
-                                           LOSS_LIST=[["TargetGuidance", []]] if mode == "CLASSIFIER_GUIDANCE" else None))
+            cfg = _cfg_for(P, mode, T, precision)
             mm = P.build_model(cfg)
             mm.load_state_dict(W.make_state_dict(mode, seed=0, with_perception=True))
             mm = mm.to(dev).eval()
@@ -337,34 +445,93 @@ def mode_report(P, W, dev, B: int, precision: str):
     return out
 
 
+def strong_scaling(P, W, dev, rank: int, world: int, precision: str, barrier, reduce_max):
+    """Fixed GLOBAL batch (strong scaling, SURVEY.md 8d config 5 / BASELINE.json configs[2]): 4096 trajectories split
+    contiguously over the ranks, DDIM-10 without guidance (config 2) and with classifier-free guidance (config 3,
+    free_guidance.yaml:7-9: scale 7.5, doubled denoiser batch).  Device-resident inputs, CUDA events, max over ranks."""
+    out = {"global_batch": STRONG_GLOBAL_BATCH, "T": 10, "n_gpus": world, "timing": "CUDA events on the launching stream, 5 plans after 2 warm-up plans, "
+           "barrier + synchronize on both sides, max over ranks", "sharding": f"contiguous batch/{world}, no collective on the data path"}
+    inp = W.synth_inputs(STRONG_GLOBAL_BATCH, 0, seed=11)
+    for name, mode in (("config2_noguidance_ddim10", "NO_GUIDANCE"), ("config3_cfg_ddim10_scale7.5", "FREE_GUIDANCE")):
+        cfg = _cfg_for(P, mode, 10, precision)
+        m = P.build_model(cfg)
+        m.load_state_dict(W.make_state_dict(mode, seed=0, with_perception=False), strict=False)
+        m = m.to(dev).eval()
+        planner = P.DiffusionPlanner(m, _sched_for(P, "guidance_ddim", cfg), cfg)
+        x, f, tg = (P.shard(inp[k], rank, world).contiguous().to(dev) for k in ("x", "feat", "target"))
+        tg = tg if mode == "FREE_GUIDANCE" else None
+        for _ in range(2):
+            planner.plan(x, f, target=tg)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            planner.plan(x, f, target=tg)
+        e1.record()
+        barrier()
+        ms = reduce_max(e0.elapsed_time(e1)) / reps
+        rows = STRONG_GLOBAL_BATCH * (2 if mode == "FREE_GUIDANCE" else 1)
+        tf = FLOPS_PER_EVAL[mode] * rows * 10 / (ms * 1e-3) / 1e12
+        out[name] = {"traj_per_s": STRONG_GLOBAL_BATCH / (ms * 1e-3), "ms_per_plan": ms, "per_gpu_batch": int(x.shape[0]),
+                     "nominal_tflops_all_gpus": tf, "frac_of_bf16_sustained_peak": tf / (peaks()["tensor"] * world)}
+        del m, planner
+    return out
+
+
+def one_process_sharded(P, W, precision: str, n_dev: int):
+    """The product-side multi-GPU entry: ONE process, ONE host batch -> DiffusionPlanner.plan_sharded (pinned staging, one handle +
+    stream + graph per device, concurrent replay, host concat).  Wall clock incl. H2D and D2H, host tensors in and out."""
+    out = {"entry": "DiffusionPlanner.plan_sharded -> b2p_plan_sharded_host", "devices": n_dev, "timing": "host wall clock incl. H2D/D2H, 5 calls after 2 warm-ups"}
+    for name, mode, B, T in (("config2_noguidance_ddim10_B4096", "NO_GUIDANCE", STRONG_GLOBAL_BATCH, 10),
+                             ("config3_cfg_ddim10_B4096", "FREE_GUIDANCE", STRONG_GLOBAL_BATCH, 10),
+                             ("headline_ddim100_B256_per_gpu", "NO_GUIDANCE", 256 * n_dev, 100)):
+        cfg = _cfg_for(P, mode, T, precision)
+        m = P.build_model(cfg)
+        m.load_state_dict(W.make_state_dict(mode, seed=0, with_perception=False), strict=False)
+        m.eval()
+        planner = P.DiffusionPlanner(m, _sched_for(P, "guidance_ddim", cfg), cfg)
+        inp = W.synth_inputs(B, 0, seed=12)
+        x, f, tg = inp["x"].pin_memory(), inp["feat"].pin_memory(), (inp["target"].pin_memory() if mode == "FREE_GUIDANCE" else None)
+        res = torch.empty_like(x).pin_memory()
+        devs = list(range(n_dev))
+        for _ in range(2):
+            planner.plan_sharded(x, f, target=tg, devices=devs, out=res)
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            planner.plan_sharded(x, f, target=tg, devices=devs, out=res)
+        s = (time.perf_counter() - t0) / reps
+        out[name] = {"traj_per_s": B / s, "ms_per_plan": s * 1e3, "global_batch": B, "T": T,
+                     "h2d_bytes": int(x.numel() + f.numel() + (tg.numel() if tg is not None else 0)) * 4, "d2h_bytes": int(res.numel()) * 4}
+        del m, planner
+    return out
+
+
 def run_b200_arm(a, rank: int, world: int, local_rank: int):
     import autonomous_driving_with_diffusion_model_b200 as P
-    from oracle import weights as W  # deterministic synthetic weights/inputs only (not the checker, not timed)
+    from autonomous_driving_with_diffusion_model_b200 import synthetic as W  # deterministic synthetic weights / inputs (not the oracle)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: the product path has no CPU fallback")
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
-    dist = None
+    dist, host_group = None, None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")   # host-side waits (a NCCL barrier spins on the GPU)
 
     B, T = a.batch, a.timesteps
     mode = a.mode
-    cfg = P.load_cfg(TRAIN=dict(USE_COND=mode), EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION=a.precision),
-                     GUIDANCE=dict(USE_COND=mode, FREE_SCALE=7.5, CLASSIFIER_SCALE=15.0,
-                                   LOSS_LIST=[["TargetGuidance", []]] if mode == "CLASSIFIER_GUIDANCE" else None))
+    cfg = _cfg_for(P, mode, T, a.precision)
     model = P.build_model(cfg)
     sd = W.make_state_dict(mode, seed=0)
     weight_bytes = 4 * sum(int(v.numel()) for k, v in sd.items() if not k.startswith("perception.") and "num_batches_tracked" not in k)
     model.load_state_dict(sd)
     model = model.to(dev).eval()
     kind = SCHED[a.sched]
-    cls = {"guidance_ddim": P.GuidanceDDIMScheduler, "guidance_ddpm": P.GuidanceDDPMScheduler,
-           "inpainting_ddim": P.InpaintingDDIMScheduler, "inpainting_ddpm": P.InpaintingDDPMScheduler}[kind]
-    sched = cls(cfg=cfg, **P.scheduler_kwargs(cfg)) if kind.startswith("guidance") else cls(**P.scheduler_kwargs(cfg))
-    planner = P.DiffusionPlanner(model, sched, cfg)
+    planner = P.DiffusionPlanner(model, _sched_for(P, kind, cfg), cfg)
 
     # global synthetic batch, sharded by rank (weak scaling: B per GPU)
     inp = W.synth_inputs(B * world, T if kind != "guidance_ddim" else 0, seed=1)
@@ -384,6 +551,13 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_max(v: float) -> float:
+        if dist is None:
+            return float(v)
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
     for _ in range(max(a.warmup, 3)):
         out = call()
@@ -419,8 +593,9 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
     assert torch.equal(e2e_out, out.cpu()), "host-entry result differs from the device-entry result"
     h2d = sum(v.numel() * 4 for v in host.values() if v is not None)
     d2h = e2e_out.numel() * 4
+    total_ms, e2e_s = reduce_max(total_ms), reduce_max(e2e_s)
 
-    # dominant kernel (fused conv block) timed live: one eager denoiser evaluation = its 41 conv launches + 2 small ones
+    # dominant kernel family timed live: one eager denoiser evaluation (its fused conv launches + 2 small ones)
     tt = torch.full((B,), 50, dtype=torch.long, device=dev)
     n_eval = 20
     xin = d["x"] if mode != "FREE_GUIDANCE" else torch.cat([d["x"], d["x"]], 0)
@@ -453,7 +628,7 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
 
     # the other arithmetic modes on the same workload (3 plans each, device-resident inputs), for the report only
     others = {}
-    if not a.no_other_precisions:
+    if not a.no_other_precisions and world == 1:
         for prec in ("fp32", "bf16x3", "bf16"):
             if prec == a.precision:
                 continue
@@ -467,42 +642,54 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
                 call()
             o1.record(stream)
             torch.cuda.synchronize()
-            others[prec] = B * world * 3 / (o0.elapsed_time(o1) * 1e-3)
+            others[prec] = B * 3 / (o0.elapsed_time(o1) * 1e-3)
         model.set_precision(a.precision)
 
+    strong = None
+    if not a.no_strong:
+        try:
+            strong = strong_scaling(P, W, dev, rank, world, a.precision, barrier, reduce_max)
+        except Exception as exc:  # report-only
+            strong = {"error": repr(exc)[:200]}
+
+    # one process feeding every GPU of the box: rank 0 alone drives all devices while the other ranks wait on the HOST (gloo)
+    sharded = None
+    if not a.no_strong:
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(group=host_group)
+        if rank == 0:
+            try:
+                sharded = one_process_sharded(P, W, a.precision, world)
+            except Exception as exc:  # report-only
+                sharded = {"error": repr(exc)[:200]}
+        if dist is not None:
+            dist.barrier(group=host_group)
+
     modes = None
-    if rank == 0 and not a.no_modes:
+    if rank == 0 and world == 1 and not a.no_modes:
         modes = mode_report(P, W, dev, B, a.precision)
 
-    # max over ranks
-    tot = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s = float(tot[0]), float(tot[1])
-
     cpu = None
-    if rank == 0 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        n = max(1, min(a.cpu_sample_iters, T))
-        cpu_iterations(a, 1, B)
-        reps, t_begin, per = 0, time.perf_counter(), []
-        while reps < 3 or (time.perf_counter() - t_begin < 12 and reps < 40):
-            per.append(cpu_iterations(a, n, B))
-            reps += 1
-        cpu = {"value": B / (statistics.mean(per) * T), "unit": "trajectories/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{reps} x {n} of the {T} denoising iterations at B={B} (oracle port of the reference PyTorch code, fp32), extrapolated x{T}/{n}"}
+        ts = cpu_whole_plans(mode, kind, T, B, min_reps=2, budget_s=a.cpu_budget_s, max_reps=8)
+        cpu = {"value": B / statistics.mean(ts), "unit": "trajectories/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{len(ts)} WHOLE plans of the same workload (B={B}, T={T}, all iterations; oracle port of the reference PyTorch code, fp32), "
+                         f"{sum(ts):.1f} s of CPU work, nothing extrapolated"}
         try:
             cpu["config0_b1_ddpm100"] = cpu_config0()
-        except Exception as exc:  # report-only figure: never lose the bench line over it
-            cpu["config0_b1_ddpm100"] = {"error": repr(exc)}
+            cpu["matrix"] = cpu_matrix(B)
+        except Exception as exc:  # report-only figures: never lose the bench line over them
+            cpu["matrix_error"] = repr(exc)[:200]
 
     if rank == 0:
         pk = peaks()
         nfe = T * (2 if mode == "FREE_GUIDANCE" else 1)
         rows = B * (2 if mode == "FREE_GUIDANCE" else 1)
         flops_eval = FLOPS_PER_EVAL[mode] * rows
-        # dominant kernel = the fused conv layer kernel (>95 % of the step, profiles/r01_launches_*): its algorithmic FLOPs over the
-        # timed region divided by the timed region itself (conservative: the scheduler launches are inside the denominator)
+        # dominant kernel family = the fused conv layer kernels (>95 % of the step): their algorithmic FLOPs over the timed region
+        # divided by the timed region itself (conservative: the scheduler launches are inside the denominator)
         achieved = flops_eval * T / (total_ms / a.steps * 1e-3) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -522,24 +709,31 @@ def run_b200_arm(a, rank: int, world: int, local_rank: int):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
                          "traffic": traffic, "peak_source": pk["source"] + ", bf16 sustained",
-                         "kernel": "fused conv block (conv_ffma_kernel, CUDA cores)" if a.precision == "fp32" else "fused conv block (conv_tc_kernel: TMA + tcgen05.mma + TMEM epilogue)",
-                         "note": "B=256/GPU: ~40 dependent layer launches per denoising iteration, each <=128 CTAs of 128 rows x 16 channels; per layer ~1.15 us dependency release + 0.8 us first-operand latency + a main loop of narrow (N<=80) MMAs paced by shared-memory operand reads + a TMEM-read-bound epilogue (profiles/r01_tc_stage_trace_b256.txt); see scripts/sweep.py for the large-batch regime",
+                         "kernel": "fused conv block (conv_ffma_kernel, CUDA cores)" if a.precision == "fp32" else
+                                   "fused conv kernels (conv_tc_kernel / chain kernel: TMA + tcgen05.mma + TMEM epilogue)",
+                         "note": "B=256/GPU: a chain of dependent layer launches per denoising iteration; see DESIGN.md §4/§5 for the stage clocks",
                          "how": f"algorithmic FLOPs ({FLOPS_PER_EVAL[mode]} nominal 2*MAC x {rows} rows x {T} evaluations per plan) / CUDA-event time of the plan "
                                 f"(timed region, CUDA graph replay)",
+                         "launches_per_plan": int(launches_per_step),
                          "eager_eval": {"tflops": flops_eval / (eval_ms * 1e-3) / 1e12, "us": eval_ms * 1e3, "launches": eval_launches,
                                         "note": "one denoiser evaluation launched eagerly (no graph), CUDA events, avg of %d" % n_eval}},
             "latency_b1": {"p50_ms": statistics.median(lat), "p95_ms": sorted(lat)[int(0.95 * len(lat)) - 1], "T": T, "sched": kind,
                            "roofline": b1_roofline(statistics.median(lat), nfe, weight_bytes, pk)},
             "precision": {"mode": a.precision, "parity_bound_max_abs": {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 0.3}[a.precision],
-                          "other_modes_traj_per_s_rank0_x_world": others},
+                          "other_modes_traj_per_s": others},
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if sharded is not None:
+            line["one_process_multi_gpu"] = sharded
         if modes is not None:
             line["modes"] = modes
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
         dist.destroy_process_group()
 
 

@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define B2P_ABI_VERSION 5
+#define B2P_ABI_VERSION 6
 
 typedef enum {
   B2P_OK = 0,
@@ -197,8 +197,11 @@ typedef struct {
   int32_t use_graph;            /* 1: capture/replay a CUDA graph                     */
 } b2p_plan_config;
 
-/* device-pointer variant.  x_init [B,H,D]; feat [B,dim]; target [B,2] or NULL; noise [T,B,H,D] or NULL (required
- * by DDPM / inpainting steps); target_traj/target_mask [B,H,D] or NULL; out [B,H,D].                               */
+/* device-pointer variant.  x_init [B,H,D]; feat [B,dim]; target [B,2] or NULL; noise [T,B,H,D] or NULL;
+ * target_traj/target_mask [B,H,D] or NULL; out [B,H,D].  A scheduler that consumes noise (DDPM, inpainting blend, eta > 0)
+ * and gets noise == NULL draws it inside the scheduler kernel (Philox4x32-10; replaces randn_tensor at
+ * guidance_ddpm_scheduler.py:154-157), keyed by b2p_set_noise_seed and a per-plan counter: statistically equivalent, not
+ * the same stream as torch's generator — parity runs inject `noise`.                                              */
 int b2p_plan(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const float* feat, const float* target,
              const float* noise, const float* target_traj, const float* target_mask, float* out, int32_t B,
              void* stream);
@@ -206,6 +209,29 @@ int b2p_plan(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const
  * stream synchronise before returning.  This is the end-to-end entry a non-PyTorch caller uses.                   */
 int b2p_plan_host(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const float* feat, const float* target,
                   const float* noise, const float* target_traj, const float* target_mask, float* out, int32_t B);
+
+/* the same without the final synchronise: H2D copies, the loop and the D2H copy are enqueued on the handle's private stream
+ * and the call returns; b2p_sync(h) joins.  `noise_batch` is the batch extent of the caller's noise tensor
+ * [T, noise_batch, H, D] when this call plans the slice starting at `noise` (0 or B = dense).  Host buffers should be
+ * pinned (pageable memory makes the copies synchronous) and must stay valid until b2p_sync returns.                */
+int b2p_plan_host_async(b2p_handle h, const b2p_plan_config* pc, const float* x_init, const float* feat, const float* target,
+                        const float* noise, int32_t noise_batch, const float* target_traj, const float* target_mask, float* out,
+                        int32_t B);
+int b2p_sync(b2p_handle h);
+/* multi-GPU entry (north_star "independent planning requests are sharded by batch across the 8 GPUs of one
+ * box with no NCCL on the sampling path"): one handle per device (same weights loaded into each), contiguous batch split
+ * (the first B % n shards take one extra trajectory), all shards enqueued, then joined.  Host tensors as b2p_plan_host.
+ * Replaces the single caller / single batch of interact.py:115-168 for a fleet-sized batch.                          */
+int b2p_plan_sharded_host(const b2p_handle* handles, int32_t n_handles, const b2p_plan_config* pc, const float* x_init,
+                          const float* feat, const float* target, const float* noise, const float* target_traj,
+                          const float* target_mask, float* out, int32_t B);
+
+/* seed of the in-kernel noise (resets the per-plan counter): the same seed and call sequence reproduce the same plans */
+int b2p_set_noise_seed(b2p_handle h, uint64_t seed);
+/* Philox key the last plan with in-kernel noise used, and the noise tensor that key stands for: out [steps, n_per_step]
+ * (n_per_step = B*H*D, device fp32, 16-byte aligned) — injecting it as `noise` reproduces the plan bit for bit.     */
+uint64_t b2p_last_noise_key(b2p_handle h);
+int b2p_philox_normal(uint64_t key, int32_t steps, int64_t n_per_step, float* out, void* stream);
 
 /* ---- introspection for tests / bench ---------------------------------------------------------------------- */
 /* number of kernel launches the last b2p_unet_forward / b2p_plan call enqueued (graph replay counts its nodes) */

@@ -19,9 +19,10 @@ MAGIC_NUM = 23.315  # modeling/temporal.py:195
 def plan(sd, mode: str, scheduler: str, x_init: torch.Tensor, feat: torch.Tensor, num_inference_steps: int,
          target: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None, free_scale: float = 7.5,
          classifier_scale: float = 15.0, target_traj: Optional[torch.Tensor] = None, target_mask: Optional[torch.Tensor] = None,
-         num_train_timesteps: int = 100, postprocess: bool = True, trace: Optional[list] = None) -> torch.Tensor:
+         num_train_timesteps: int = 100, postprocess: bool = True, trace: Optional[list] = None,
+         sched_overrides: Optional[dict] = None) -> torch.Tensor:
     """scheduler in {guidance_ddim, guidance_ddpm, inpainting_ddim, inpainting_ddpm}; returns trajectories [B,H,D]."""
-    cfg = S.SchedCfg(num_train_timesteps=num_train_timesteps, num_inference_steps=num_inference_steps)
+    cfg = S.SchedCfg(num_train_timesteps=num_train_timesteps, num_inference_steps=num_inference_steps, **(sched_overrides or {}))
     ac = S.alphas_cumprod(num_train_timesteps)
     B = x_init.shape[0]
     trajs = x_init.clone()

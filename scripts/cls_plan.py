@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import autonomous_driving_with_diffusion_model_b200 as P
-from oracle import weights as W
+from autonomous_driving_with_diffusion_model_b200 import synthetic as W
 B = int(sys.argv[1]); prec = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
 dev = "cuda:0"; mode = "CLASSIFIER_GUIDANCE"
 cfg = P.load_cfg(TRAIN=dict(USE_COND=mode), EVAL=dict(SAMPLE_STEPS=2), B200=dict(PRECISION=prec),

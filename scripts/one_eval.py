@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import autonomous_driving_with_diffusion_model_b200 as P
-from oracle import weights as W
+from autonomous_driving_with_diffusion_model_b200 import synthetic as W
 B = int(sys.argv[1]); prec = sys.argv[2]; n = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = "cuda:0"
 cfg = P.load_cfg(B200=dict(PRECISION=prec))

@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import autonomous_driving_with_diffusion_model_b200 as P
-from oracle import weights as W
+from autonomous_driving_with_diffusion_model_b200 import synthetic as W
 dev = "cuda:0"
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 for mode, prec, B, T in (("CLASSIFIER_GUIDANCE", "bf16x3", 1, 1), ("CLASSIFIER_GUIDANCE", "bf16x3", 5, 1), ("FREE_GUIDANCE", "fp32", 3, 1), ("NO_GUIDANCE", "bf16", 130, 1)):

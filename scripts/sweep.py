@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import autonomous_driving_with_diffusion_model_b200 as P  # noqa: E402
-from oracle import weights as W  # noqa: E402  (deterministic synthetic weights / inputs only)
+from autonomous_driving_with_diffusion_model_b200 import synthetic as W  # noqa: E402  (deterministic synthetic weights / inputs only)
 
 FLOPS_PER_EVAL = 78_874_624  # SURVEY.md 8d, nominal 2*MAC per trajectory per denoiser evaluation (NO_GUIDANCE)
 

@@ -2,7 +2,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import autonomous_driving_with_diffusion_model_b200 as P
-from oracle import weights as W
+from autonomous_driving_with_diffusion_model_b200 import synthetic as W
 dev="cuda:0"; prec=sys.argv[1] if len(sys.argv)>1 else "bf16x3"; B=int(sys.argv[2]) if len(sys.argv)>2 else 256
 mode="NO_GUIDANCE"
 cfg=P.load_cfg(B200=dict(PRECISION=prec), EVAL=dict(SAMPLE_STEPS=100))

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import autonomous_driving_with_diffusion_model_b200 as P
 from autonomous_driving_with_diffusion_model_b200 import _lib
-from oracle import weights as W
+from autonomous_driving_with_diffusion_model_b200 import synthetic as W
 
 dev = "cuda:0"; prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"; B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 T = 20

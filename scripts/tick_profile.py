@@ -2,7 +2,7 @@ import sys, os, time, cProfile, pstats
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import autonomous_driving_with_diffusion_model_b200 as P
-from oracle import weights as W
+from autonomous_driving_with_diffusion_model_b200 import synthetic as W
 dev = "cuda:0"; mode, T = "CLASSIFIER_GUIDANCE", 2
 cfg = P.load_cfg(TRAIN=dict(USE_COND=mode), EVAL=dict(SAMPLE_STEPS=T), B200=dict(PRECISION="bf16x3"),
                  GUIDANCE=dict(USE_COND=mode, CLASSIFIER_SCALE=15.0, LOSS_LIST=[["TargetGuidance", []]]))

@@ -23,7 +23,7 @@ def lib():
 
 def test_header_symbols_all_exported_and_bound(lib):
     hdr = open(os.path.join(ROOT, "include", "b200plan.h")).read()
-    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(b2p_[a-z0-9_]+)\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|uint64_t|const char\*)\s+(b2p_[a-z0-9_]+)\(", hdr, flags=re.M))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name)

@@ -667,3 +667,166 @@ def test_plan_graph_cache_is_bounded_and_reusable():
     ref = OP.plan(sd, "NO_GUIDANCE", "guidance_ddim", inp["x"][:5], inp["feat"][:5], 3)
     d = (first[5].cpu() - ref).abs()
     assert float(d[..., :2].max()) <= 1e-3 * MAGIC and float(d[..., 2:].max()) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------
+# round-2 regression tests
+# ------------------------------------------------------------------------------------------------------------
+def test_headline_config_b256_t100_bf16x3_vs_oracle():
+    """The exact bench configuration (BASELINE.json configs[1]: NO_GUIDANCE, GuidanceDDIM, T=100, B=256, bf16x3) against the
+    oracle on trajectories spread over the first / middle / last row tiles of every level (a 128-row tile holds 8 samples
+    at L=16 and 64 at L=2).  Bound: 1e-3 in normalised units (north_star)."""
+    model, sd = get_tc_model("NO_GUIDANCE", "bf16x3")
+    T, B = 100, 256
+    planner = P.DiffusionPlanner(model, make_sched("guidance_ddim"), _cfg("NO_GUIDANCE", T))
+    inp = W.synth_inputs(B, 0, 1)      # bench.py's seed
+    out = planner.plan(inp["x"].to(DEV), inp["feat"].to(DEV), postprocess=False).cpu()
+    rows = [0, 7, 8, 63, 64, 127, 128, 191, 192, 248, 255]
+    ref = OP.plan(sd, "NO_GUIDANCE", "guidance_ddim", inp["x"][rows], inp["feat"][rows], T, postprocess=False)
+    err = (out[rows] - ref).abs()
+    assert float(err.max()) <= 1e-3, [float(e.max()) for e in err]
+    assert float(out[:, 0, :3].abs().max()) == 0.0
+
+
+def test_cached_graphs_of_different_T_do_not_share_timesteps():
+    """a cached plan graph reads its timesteps from a handle-owned buffer at REPLAY time; alternating
+    T=100 / T=10 / T=100 on one handle (no buffer growth, no graph drop in between) must reproduce the first result."""
+    model, sd = get_model("NO_GUIDANCE")
+    sched = make_sched("guidance_ddim")
+    inp = W.synth_inputs(2, 0, 97)
+    x, f = inp["x"].to(DEV), inp["feat"].to(DEV)
+    p100 = P.DiffusionPlanner(model, sched, _cfg("NO_GUIDANCE", 100))
+    p10 = P.DiffusionPlanner(model, sched, _cfg("NO_GUIDANCE", 10))
+    a100 = p100.plan(x, f).clone()
+    a10 = p10.plan(x, f).clone()
+    b100 = p100.plan(x, f)                      # cache hit after another schedule ran
+    b10 = p10.plan(x, f)
+    assert torch.equal(a100, b100) and torch.equal(a10, b10)
+    eager = P.DiffusionPlanner(model, sched, _cfg("NO_GUIDANCE", 10), use_graph=False)
+    assert torch.equal(eager.plan(x, f), a10)
+    assert torch.equal(p100.plan(x, f), a100)   # and after an eager plan of another T
+    ref = OP.plan(sd, "NO_GUIDANCE", "guidance_ddim", inp["x"], inp["feat"], 100)
+    d = (a100.cpu() - ref).abs()
+    assert float(d[..., :2].max()) <= 1e-3 * MAGIC and float(d[..., 2:].max()) <= 1e-3
+
+
+def test_copy_parameters_and_data_writes_reach_the_device_copy():
+    """positional EMA copy (misc/load_param.py:4-8 idiom) after the weights were already packed."""
+    sd = W.make_state_dict("NO_GUIDANCE", seed=0, with_perception=False)
+    sd2 = W.make_state_dict("NO_GUIDANCE", seed=3, with_perception=False)
+    m = P.build_model(P.load_cfg())
+    m.load_state_dict(sd, strict=False)
+    m = m.to(DEV).eval()
+    inp = W.synth_inputs(2, 0, 71)
+    x, f, t = inp["x"].to(DEV), inp["feat"].to(DEV), torch.tensor([20, 60], device=DEV)
+    base = m(x, f, t).clone()                                   # packs the weights
+    m2 = P.build_model(P.load_cfg())
+    m2.load_state_dict(sd2, strict=False)
+    want = m2.to(DEV).eval()(x, f, t).clone()
+    assert not torch.equal(base, want)
+    P.copy_parameters([p.detach().cpu() for p in m2.parameters()], m.parameters())
+    assert torch.equal(m(x, f, t), want)
+    # the raw `.data` idiom needs the explicit invalidation (documented)
+    m.load_state_dict(sd, strict=False)
+    assert torch.equal(m(x, f, t), base)
+    with torch.no_grad():
+        for p, q in zip(m.parameters(), m2.parameters()):
+            p.data.copy_(q.data)
+    m.invalidate_weights()
+    assert torch.equal(m(x, f, t), want)
+
+
+def test_classifier_plan_follows_the_scheduler_guidance_switch_and_cfg_accepts_no_target():
+    """guidance is applied only when the scheduler was built with use_classifier_guidance
+    (guidance_ddim_scheduler.py:19-21); FREE_GUIDANCE with target None runs with a zero condition (temporal.py:207)."""
+    model, sd = get_model("CLASSIFIER_GUIDANCE")
+    inp = W.synth_inputs(3, 0, 21)
+    x, f, tg = inp["x"].to(DEV), inp["feat"].to(DEV), inp["target"].to(DEV)
+    guided = P.DiffusionPlanner(model, make_sched("guidance_ddim", "CLASSIFIER_GUIDANCE"), _cfg("CLASSIFIER_GUIDANCE", 2))
+    cfg_off = _cfg("CLASSIFIER_GUIDANCE", 2)
+    cfg_off.GUIDANCE.LOSS_LIST = None
+    kw = P.scheduler_kwargs(cfg_off)
+    plain = P.DiffusionPlanner(model, P.GuidanceDDIMScheduler(cfg=cfg_off, **kw), cfg_off)
+    a, b, c = guided.plan(x, f, target=tg), plain.plan(x, f, target=tg), guided.plan(x, f, target=None)
+    assert torch.equal(b, c) and not torch.equal(a, b)
+    ref = OP.plan(sd, "CLASSIFIER_GUIDANCE", "guidance_ddim", inp["x"], inp["feat"], 2, target=None)
+    d = (b.cpu() - ref).abs()
+    assert float(d[..., :2].max()) <= 1e-3 * MAGIC and float(d[..., 2:].max()) <= 1e-3
+    fmodel, fsd = get_model("FREE_GUIDANCE")
+    fp = P.DiffusionPlanner(fmodel, make_sched("guidance_ddim", "FREE_GUIDANCE"), _cfg("FREE_GUIDANCE", 4))
+    z = fp.plan(x, f, target=None)
+    assert torch.equal(z, fp.plan(x, f, target=torch.zeros_like(tg)))
+
+
+def test_in_kernel_noise_is_reproducible_injectable_and_standard_normal():
+    """VERDICT r01 missing #6 (Appendix C K8): DDPM / inpainting plans called without a noise tensor draw N(0,1) inside the
+    scheduler kernel (Philox4x32-10), inside the captured graph.  The stream is (a) a pure function of the seed and the call
+    sequence, (b) exportable: injecting b2p_philox_normal(key) as `noise` reproduces the plan bitwise, (c) standard normal."""
+    import ctypes as C
+    from autonomous_driving_with_diffusion_model_b200 import _lib
+    model, _ = get_model("NO_GUIDANCE")
+    T, B = 10, 37
+    planner = P.DiffusionPlanner(model, make_sched("guidance_ddpm"), _cfg("NO_GUIDANCE", T))
+    inp = W.synth_inputs(B, 0, 55)
+    x, f = inp["x"].to(DEV), inp["feat"].to(DEV)
+    planner.seed_noise(1234)
+    a1, a2 = planner.plan(x, f).clone(), planner.plan(x, f).clone()
+    planner.seed_noise(1234)
+    b1 = planner.plan(x, f).clone()
+    h = model._handle_for(torch.device(DEV))
+    key = _lib.load().b2p_last_noise_key(h)
+    b2 = planner.plan(x, f)
+    assert torch.equal(a1, b1) and torch.equal(a2, b2) and not torch.equal(a1, a2)       # seed + call counter
+    nz = torch.empty(T, B, 16, 7, device=DEV)
+    _lib.check(_lib.load().b2p_philox_normal(C.c_uint64(key), T, B * 112, _lib.ptr(nz), model._stream()), None, "b2p_philox_normal")
+    assert torch.equal(planner.plan(x, f, noise=nz), b1)                                 # the in-kernel draws ARE this tensor
+    big = torch.empty(64, 1 << 16, device=DEV)
+    _lib.check(_lib.load().b2p_philox_normal(C.c_uint64(99), 64, 1 << 16, _lib.ptr(big), model._stream()), None, "b2p_philox_normal")
+    z = big.double().flatten()
+    n = z.numel()
+    assert abs(float(z.mean())) < 5 / n ** 0.5 and abs(float(z.var()) - 1) < 5 * (2 / n) ** 0.5
+    assert abs(float((z ** 3).mean())) < 5 * (15 / n) ** 0.5 and abs(float((z ** 4).mean()) - 3) < 5 * (96 / n) ** 0.5
+    assert abs(float((big[0] * big[1]).mean())) < 5 / (1 << 8) and abs(float((big[:, :-1] * big[:, 1:]).mean())) < 5 / n ** 0.5
+    cdf = torch.distributions.Normal(0, 1).cdf(z.sort().values)
+    ks = float((cdf - torch.arange(1, n + 1, device=DEV, dtype=torch.double) / n).abs().max())
+    assert ks < 1.95 / n ** 0.5 + 2 ** -23, ks                                          # Kolmogorov-Smirnov at ~0.1 % (+ the 24-bit grid)
+
+
+def test_dynamic_threshold_inside_a_captured_plan():
+    """sample_max_value > 1 (real per-sample quantile, quirk 8) inside a graph-captured plan: the
+    quantile scratch comes from the handle, no allocation node in the graph."""
+    model, sd = get_model("NO_GUIDANCE")
+    inp = W.synth_inputs(5, 0, 77)
+    x = (2.5 * inp["x"]).clone()
+    x[:, 0, :3] = 0
+    outs = []
+    for use_graph in (True, False):
+        planner = P.DiffusionPlanner(model, make_sched("guidance_ddim", sample_max_value=1.5), _cfg("NO_GUIDANCE", 4), use_graph=use_graph)
+        outs.append(planner.plan(x.to(DEV), inp["feat"].to(DEV), postprocess=False))
+        outs.append(planner.plan(x.to(DEV), inp["feat"].to(DEV), postprocess=False))
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    ref = OP.plan(sd, "NO_GUIDANCE", "guidance_ddim", x, inp["feat"], 4, postprocess=False, sched_overrides=dict(sample_max_value=1.5))
+    assert float((outs[0].cpu() - ref).abs().max()) <= 1e-3
+
+
+def test_plan_sharded_one_process_matches_the_single_device_plan():
+    """VERDICT r01 missing #1: DiffusionPlanner.plan_sharded — one host batch, one process, one handle + stream + graph per
+    device, pinned staging, host concat.  Bitwise equal to the single-device plan (no operation crosses samples).  On a one-GPU
+    box the two shards share device 0 (same code path, serialised on the handle's stream); with >= 2 GPUs they run concurrently."""
+    ndev = torch.cuda.device_count()
+    for mode, kind, T in (("NO_GUIDANCE", "guidance_ddpm", 6), ("FREE_GUIDANCE", "guidance_ddim", 4), ("CLASSIFIER_GUIDANCE", "guidance_ddim", 2)):
+        model, _ = get_tc_model(mode, "bf16x3")
+        planner = P.DiffusionPlanner(model, make_sched(kind, mode), _cfg(mode, T))
+        B = 41
+        inp = W.synth_inputs(B, T, 91)
+        noise = inp["noise"] if kind.endswith("ddpm") else None
+        tg = inp["target"] if mode != "NO_GUIDANCE" else None
+        single = planner.plan(inp["x"].to(DEV), inp["feat"].to(DEV), target=None if tg is None else tg.to(DEV),
+                              noise=None if noise is None else noise.to(DEV)).cpu()
+        for devices in ([0, 0], [0, 0, 0, 0, 0], list(range(ndev)) if ndev > 1 else [0]):
+            out = planner.plan_sharded(inp["x"], inp["feat"], target=tg, noise=noise, devices=devices)
+            assert out.device.type == "cpu" and torch.equal(out, single), (mode, devices)
+    pinned = torch.empty(41, 16, 7).pin_memory()
+    assert planner.plan_sharded(inp["x"], inp["feat"], target=tg, devices=[0, 0], out=pinned) is pinned and torch.equal(pinned, single)
+    assert planner.plan_sharded(inp["x"][:0], inp["feat"][:0], devices=[0]).shape == (0, 16, 7)
+    assert planner.shard_sizes(41, [0, 0, 0]) == [14, 14, 13]
