@@ -40,6 +40,13 @@ class PlanConfig(C.Structure):
                 ("classifier_scale", C.c_float), ("magic_num", C.c_float), ("postprocess", C.c_int32), ("use_graph", C.c_int32)]
 
 
+class ControlConfig(C.Structure):
+    _fields_ = [("turn_kp", C.c_double), ("turn_ki", C.c_double), ("turn_kd", C.c_double), ("turn_n", C.c_int32),
+                ("speed_kp", C.c_double), ("speed_ki", C.c_double), ("speed_kd", C.c_double), ("speed_n", C.c_int32),
+                ("aim_dist", C.c_double), ("angle_thresh", C.c_double), ("dist_thresh", C.c_double), ("brake_speed", C.c_double),
+                ("brake_ratio", C.c_double), ("clip_delta", C.c_double), ("max_throttle", C.c_double)]
+
+
 ABI_VERSION = 6
 SCHED_KINDS = {"guidance_ddim": 0, "guidance_ddpm": 1, "inpainting_ddim": 2, "inpainting_ddpm": 3}
 PRED_TYPES = {"epsilon": 0, "sample": 1, "v_prediction": 2}
@@ -62,6 +69,7 @@ SYMBOLS = {
     "b2p_finalize_weights": (C.c_int, [_VP]),
     "b2p_set_precision": (C.c_int, [_VP, C.c_int]),
     "b2p_set_small_batch_max": (C.c_int, [_VP, C.c_int]),
+    "b2p_set_chain": (C.c_int, [_VP, C.c_int]),
     "b2p_preprocess_frames": (C.c_int, [_VP, _VP, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), _VP]),
     "b2p_unet_forward": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "b2p_state_pred": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int32, _VP]),
@@ -80,6 +88,10 @@ SYMBOLS = {
     "b2p_set_noise_seed": (C.c_int, [_VP, C.c_uint64]),
     "b2p_last_noise_key": (C.c_uint64, [_VP]),
     "b2p_philox_normal": (C.c_int, [C.c_uint64, C.c_int32, C.c_int64, _VP, _VP]),
+    "b2p_fleet_state_bytes": (C.c_int64, [C.POINTER(ControlConfig), C.c_int32]),
+    "b2p_fleet_reset": (C.c_int, [C.POINTER(ControlConfig), _VP, C.c_int32, _VP]),
+    "b2p_fleet_control_pid": (C.c_int, [C.POINTER(ControlConfig), _VP, _VP, C.c_int32, _VP, _VP, _VP, C.c_int32, _VP]),
+    "b2p_fleet_post_process": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "b2p_last_launch_count": (C.c_int64, [_VP]),
     "b2p_unet_flops_per_sample": (C.c_int64, [_VP]),
     "b2p_weight_bytes": (C.c_int64, [_VP]),

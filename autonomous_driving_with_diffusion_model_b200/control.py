@@ -1,4 +1,9 @@
-"""Plan post-processing -> vehicle control: host-side mirror of the reference's controller.
+"""Plan post-processing -> vehicle control.
+
+Two forms: the host-side mirror of the reference's per-vehicle controller (``Controller``, ``PIDController``,
+``post_process_control`` — numpy, pinned bit-for-bit against the reference's classes) and the FLEET form on the device
+(``FleetController``, ``post_process_control_batch`` — hand-written kernels in csrc/control.cu, one thread per vehicle, the
+per-vehicle PID windows resident in device memory) for many vehicles planned in one batch.
 
 ``post_process_control`` is what the shipped 7-dim configuration uses (interact.py:218-229, 296-297: the control triple is
 the last three columns of the first waypoint); ``Controller.control_pid`` is the waypoint-following PID used when the model
@@ -82,14 +87,78 @@ def post_process_control(throttle_res, steer_res, brake_res):
 
 
 def post_process_control_batch(trajs):
-    """Fleet form of interact.py:296-297 + 218-229: trajs [B,H,D>=5] (torch tensor, any device) -> [B,3] controls
-    (throttle, steer, brake) read from the first waypoint's last three columns, one row per vehicle."""
+    """Fleet form of interact.py:296-297 + 218-229: trajs [B,H,D>=5] (CUDA tensor) -> [B,3] controls (throttle, steer, brake)
+    read from the first waypoint's last three columns, one row per vehicle (``b2p_fleet_post_process``)."""
+    import ctypes as C
+
     import torch
 
-    c = trajs[:, 0, -3:].to(torch.float32)
-    throttle, steer, brake = c[:, 0], c[:, 1], c[:, 2]
-    brake = torch.where(brake < 0.05, torch.zeros_like(brake), brake)
-    brake = torch.where(throttle > brake, torch.zeros_like(brake), brake)
-    hard = brake > 0.5
-    one, zero = torch.ones_like(brake), torch.zeros_like(brake)
-    return torch.stack([torch.where(hard, zero, throttle), torch.where(hard, zero, steer), torch.where(hard, one, brake)], dim=-1)
+    from . import _lib
+    if trajs.device.type != "cuda":
+        raise RuntimeError("post_process_control_batch runs on CUDA tensors (use post_process_control per vehicle on the host)")
+    t = trajs.detach().to(torch.float32).contiguous()
+    B, H, D = t.shape
+    out = torch.empty((B, 3), device=t.device, dtype=torch.float32)
+    if B:
+        with torch.cuda.device(t.device):
+            rc = _lib.load().b2p_fleet_post_process(_lib.ptr(t), _lib.ptr(out), B, H, D, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, None, "b2p_fleet_post_process")
+    return out
+
+
+class FleetController:
+    """``Controller.control_pid`` (control/controller.py:29-76) for ``n_vehicles`` vehicles at once: one thread per vehicle,
+    float64 arithmetic, the two PID windows of every vehicle (the deques of control/pid.py:10) resident on the device and
+    advanced by every call.  Same constructor argument as ``Controller`` (a config tree with PID.* and CONTROL.*)."""
+
+    def __init__(self, cfg, n_vehicles: int, device="cuda"):
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+        p, c = cfg.PID, cfg.CONTROL
+        self._cfg = _lib.ControlConfig(p.TURN_KP, p.TURN_KI, p.TURN_KD, int(p.TURN_N), p.SPEED_KP, p.SPEED_KI, p.SPEED_KD, int(p.SPEED_N),
+                                       c.AIM_DIST, c.ANGLE_THRESH, c.DIST_THRESH, c.BRAKE_SPEED, c.BRAKE_RATIO, c.CLIP_DELTA, c.MAX_THROTTLE)
+        self.n_vehicles, self.device = int(n_vehicles), torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FleetController runs on CUDA (use Controller per vehicle on the host)")
+        nbytes = _lib.load().b2p_fleet_state_bytes(C.byref(self._cfg), self.n_vehicles)
+        if nbytes <= 0:
+            raise ValueError("invalid PID configuration (window lengths must be in 1..127) or fleet size")
+        self._state = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        self.reset()
+
+    def _stream(self):
+        import ctypes as C
+
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self) -> None:
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().b2p_fleet_reset(C.byref(self._cfg), _lib.ptr(self._state), self.n_vehicles, self._stream()), None, "b2p_fleet_reset")
+
+    def control_pid(self, waypoints, velocity, target):
+        """waypoints [V,N,2], velocity [V] or [V,1], target [V,2] (ego frame, metres) -> [V,3] = (throttle, steer, brake in {0,1})."""
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+        f = lambda t: t.detach().to(self.device, torch.float32).contiguous()  # noqa: E731
+        w, v, tg = f(waypoints), f(velocity).reshape(-1), f(target).reshape(-1, 2)
+        V, N = w.shape[0], w.shape[1]
+        if V != self.n_vehicles or v.numel() != V or tg.shape[0] != V or w.dim() != 3 or w.shape[2] != 2 or N < 2:
+            raise ValueError(f"expected waypoints [{self.n_vehicles},N>=2,2], velocity [{self.n_vehicles}], target [{self.n_vehicles},2]")
+        out = torch.empty((V, 3), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = _lib.load().b2p_fleet_control_pid(C.byref(self._cfg), _lib.ptr(self._state), _lib.ptr(w), N, _lib.ptr(v), _lib.ptr(tg),
+                                                   _lib.ptr(out), V, self._stream())
+        _lib.check(rc, None, "b2p_fleet_control_pid")
+        return out

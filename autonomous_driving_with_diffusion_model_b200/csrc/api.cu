@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "chain64.cuh"
 
 namespace b2p {
 int upload_freq_table(const float* f, int n);
@@ -84,6 +85,16 @@ struct b2p_handle_s {
   size_t o_w1t, o_b1, o_w3t, o_b3, o_wc0t, o_bc0, o_wc2t, o_bc2, o_tembW, o_tembB;
   TrajPredWeights tp{};
   bool has_tp = false;
+
+  // row-owned chain kernel (chain64.cu): the 64-channel layers at the full-resolution end of the U-Net
+  bool chain_ok = false;
+  bool chain_on = true;                // b2p_set_chain / B2P_CHAIN: off = every layer is its own launch
+  unsigned long long* d_chain_trace = nullptr;   // developer stage clocks (B2P_CHAIN_TRACE=1)
+  int chain_u0 = -1;                   // index of the last up level's first conv (runs per-layer, with the residual projection as a sixth tap)
+  std::vector<uint32_t> chain_woff;    // per op: byte offset of its pre-swizzled weight image in d_chain (0xffffffff: not a chain op)
+  std::vector<uint8_t> chain_host;
+  uint8_t* d_chain = nullptr;
+  size_t aux_hi = NPOS, aux_lo = NPOS; // 6-tap weights of op chain_u0 in the 16-bit pack: taps 0..4 = conv, tap 5 = residual_conv
 
   // workspace (activation buffers) for `cap` denoiser rows
   int cap = 0;
@@ -423,6 +434,80 @@ int build_program(b2p_handle_s* h) {
   return B2P_OK;
 }
 
+// ---- chain kernel: which ops it covers and their pre-swizzled weight images ----
+// image of one op: plane hi = [T*64 rows (column half, tap, 32 out channels)][64 k] bf16, K-major with the 128-byte swizzle applied (what TMA would
+// have produced in shared memory), followed by plane lo.  The kernel copies it with plain bulk copies, one per tap.
+uint32_t chain_add_image(b2p_handle_s* h, const float* w, int T, int cin, int ktaps, bool transposed, int im2col_D) {
+  const size_t plane = (size_t)T * 64 * 128;
+  const size_t off = (h->chain_host.size() + 1023) & ~(size_t)1023;
+  h->chain_host.resize(off + 2 * plane, 0);
+  uint8_t* base = h->chain_host.data() + off;
+  for (int t = 0; t < T; ++t)
+    for (int co = 0; co < 64; ++co)
+      for (int k = 0; k < 64; ++k) {
+        float v = 0.f;
+        if (im2col_D > 0) {            // first conv: k = j * D + c over the 5 taps of Conv1d [64][D][5]
+          const int j = k / im2col_D, c = k - j * im2col_D;
+          if (j < ktaps) v = w[((size_t)co * im2col_D + c) * ktaps + j];
+        } else if (k < cin) {
+          v = transposed ? w[((size_t)k * 64 + co) * ktaps + t] : w[((size_t)co * cin + k) * ktaps + t];
+        }
+        const int n = (co >> 5) * (T * 32) + t * 32 + (co & 31);   // [column half][tap][32 channels]: the taps of one half are one MMA operand
+        const size_t o = (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
+        const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+        memcpy(base + o, &hi, 2);
+        memcpy(base + plane + o, &lo, 2);
+      }
+  return (uint32_t)off;
+}
+
+void build_chain(b2p_handle_s* h) {
+  h->chain_ok = false; h->chain_u0 = -1; h->chain_host.clear(); h->aux_hi = h->aux_lo = NPOS;
+  h->chain_woff.assign(h->ops.size(), 0xffffffffu);
+  const int n = h->nlev, nops = (int)h->ops.size();
+  if (h->H != 16 || h->chans[1] != 64 || h->D > 8 || n < 2) return;
+  const int u0 = nops - 6;   // [.., ups.last.0.conv0, .conv1, ups.last.1.conv0, .conv1, Upsample1d, head]
+  if (u0 < 5) return;
+  auto is64 = [&](const LayerOp& op, int L, int taps) { return op.Cout == 64 && op.Lin == L && op.taps == taps; };
+  const LayerOp* o = h->ops.data();
+  if (!(is64(o[0], 16, 5) && o[0].C0 == h->D && is64(o[1], 16, 5) && o[1].resW != NPOS && o[1].RC0 == h->D && is64(o[2], 16, 5) && is64(o[3], 16, 5) &&
+        o[3].res_id == o[1].out && is64(o[4], 16, 3) && o[4].stride == 2)) return;
+  if (!(is64(o[u0], 8, 5) && o[u0].C1 > 0 && is64(o[u0 + 1], 8, 5) && o[u0 + 1].resW != NPOS && o[u0 + 1].tcRW_hi != NPOS && is64(o[u0 + 2], 8, 5) &&
+        is64(o[u0 + 3], 8, 5) && o[u0 + 3].res_id == o[u0 + 1].out && is64(o[u0 + 4], 8, 4) && o[u0 + 4].transposed && is64(o[u0 + 5], 16, 5) &&
+        o[u0 + 5].headW != NPOS)) return;
+  const std::string up = "ups." + std::to_string(n - 2), head = h->cfg.guidance == B2P_CLASSIFIER_GUIDANCE ? "act_conv" : "final_conv";
+  const char* keyA[5] = {"downs.0.0.blocks.0.block.0.weight", "downs.0.0.blocks.1.block.0.weight", "downs.0.1.blocks.0.block.0.weight",
+                         "downs.0.1.blocks.1.block.0.weight", "downs.0.3.conv.weight"};
+  h->chain_woff[0] = chain_add_image(h, W(h, keyA[0]), 1, h->D, 5, false, h->D);
+  for (int i = 1; i < 4; ++i) h->chain_woff[i] = chain_add_image(h, W(h, keyA[i]), 5, 64, 5, false, 0);
+  h->chain_woff[4] = chain_add_image(h, W(h, keyA[4]), 3, 64, 3, false, 0);
+  h->chain_woff[u0 + 1] = chain_add_image(h, W(h, up + ".0.blocks.1.block.0.weight"), 5, 64, 5, false, 0);
+  h->chain_woff[u0 + 2] = chain_add_image(h, W(h, up + ".1.blocks.0.block.0.weight"), 5, 64, 5, false, 0);
+  h->chain_woff[u0 + 3] = chain_add_image(h, W(h, up + ".1.blocks.1.block.0.weight"), 5, 64, 5, false, 0);
+  h->chain_woff[u0 + 4] = chain_add_image(h, W(h, up + ".3.conv.weight"), 4, 64, 4, true, 0);
+  h->chain_woff[u0 + 5] = chain_add_image(h, W(h, head + ".0.block.0.weight"), 5, 64, 5, false, 0);
+  {  // op u0 with the block's residual projection as a sixth tap: [6][64][Cin] hi / lo (K-major, read through TMA)
+    const int cin = o[u0].C0 + o[u0].C1;
+    const float* w = W(h, up + ".0.blocks.0.block.0.weight");
+    const float* rw = W(h, up + ".0.residual_conv.weight");
+    const size_t nel = (size_t)6 * 64 * cin;
+    h->aux_hi = alloc16(h->pack16_host, nel);
+    h->aux_lo = alloc16(h->pack16_host, nel);
+    uint16_t* ph = h->pack16_host.data() + h->aux_hi;
+    uint16_t* pl = h->pack16_host.data() + h->aux_lo;
+    for (int j = 0; j < 6; ++j)
+      for (int co = 0; co < 64; ++co)
+        for (int c = 0; c < cin; ++c) {
+          const float v = j < 5 ? w[((size_t)co * cin + c) * 5 + j] : rw[(size_t)co * cin + c];
+          const size_t q = ((size_t)j * 64 + co) * cin + c;
+          ph[q] = f2bf(v);
+          pl[q] = f2bf(v - bf2f(ph[q]));
+        }
+  }
+  h->chain_u0 = u0;
+  h->chain_ok = true;
+}
+
 void build_trajpred(b2p_handle_s* h, Packer& pk, std::vector<size_t>& offs) {
   // offsets recorded in order; resolved to device pointers after upload
   const int hd = 64, S = h->H - 1;
@@ -527,9 +612,23 @@ inline const float* buf_ptr(b2p_handle_s* h, int id, const float* x) {
 // itab/ttab_row != null: "table mode" (inside a plan, no CFG): the per-block time-MLP outputs were precomputed as an
 // image term itab[rows, temb_total] (step-invariant) and a time vector ttab_row[temb_total] for this step, so the
 // embedding kernels are skipped.
+// Seam of two evaluations inside a plan without guidance (chain64.cu): behind the tail chain of this evaluation run the scheduler
+// step and, unless this is the last step, the head chain of the NEXT evaluation (whose per-step time vector is next_ttab_row).
+struct ChainSeam {
+  SchedLaunch sched;            // mo / sample are taken from shared memory; prev = where x_{t-1} goes
+  bool next_head;
+  const float* next_ttab_row;
+};
+
+bool chain_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("B2P_CHAIN"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
+
 int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, int feat_rows, const int64_t* t, int t_count,
              const float* cond, float* head_out, float* time_embed_out, int rows, cudaStream_t s, int64_t* launches,
-             const float* itab = nullptr, const float* ttab_row = nullptr) {
+             const float* itab = nullptr, const float* ttab_row = nullptr, const ChainSeam* seam = nullptr, bool head_chain_done = false) {
   if (!h->finalized) return h->fail(B2P_ERR_NOT_FINALIZED, "weights not finalized");
   int rc = ensure_workspace(h, rows);
   if (rc) return rc;
@@ -567,8 +666,68 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
     return (id < 0 || nsplit != 2) ? nullptr : hi_ptr(id) + (size_t)h->bufs[id].L * h->bufs[id].C * h->cap;
   };
   bool proj_done = false;   // residual projection of the raw trajectory already produced by the first conv launch
+  // ---- row-owned chain kernel for the 64-channel layers (tensor-core precisions) ----
+  const bool chain = tc && h->chain_ok && h->chain_on;
+  const int u0 = h->chain_u0;
+  if (seam && !chain) return h->fail(B2P_ERR_STATE, "seam fusion needs the chain kernel");
+  auto launch_chain = [&](bool do_tail, bool do_head) -> int {
+    ChainArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    auto mk = [&](int oi2, int kind, int T, int pad, int L, int in_buf, int out_buf, int res_kind, int res_buf, int phase, int ksteps) {
+      const LayerOp& o = h->ops[oi2];
+      ChainOp& c = ca.ops[ca.n_ops++];
+      c.kind = kind; c.T = T; c.pad = pad; c.L = L; c.log2L = ilog2(L); c.in_buf = in_buf; c.out_buf = out_buf; c.res_kind = res_kind; c.res_buf = res_buf;
+      c.temb_off = o.temb_off; c.phase = phase; c.gn = o.gamma != NPOS; c.ksteps = ksteps; c.w_off = h->chain_woff[oi2];
+      c.bias = P + o.bias; c.gamma = o.gamma != NPOS ? P + o.gamma : nullptr; c.beta = o.gamma != NPOS ? P + o.beta : nullptr;
+    };
+    const int nops = (int)h->ops.size();
+    if (do_tail) {
+      mk(u0 + 1, CH_CONV, 5, 2, 8, 0, 1, CH_RES_F32, 0, 0, 4);
+      mk(u0 + 2, CH_CONV, 5, 2, 8, 1, 2, CH_RES_NONE, 0, 0, 4);
+      mk(u0 + 3, CH_CONV, 5, 2, 8, 2, 0, CH_RES_SMEM, 1, 0, 4);
+      mk(u0 + 4, CH_UP, 4, 1, 8, 0, 1, CH_RES_NONE, 0, 0, 4);
+      mk(u0 + 5, CH_CONV, 5, 2, 16, 1, CH_OUT_HEAD, CH_RES_NONE, 0, 0, 4);
+      const LayerOp& hd = h->ops[nops - 1];
+      ca.in_hi = hi_ptr(h->ops[u0].out); ca.in_lo = lo_ptr(h->ops[u0].out); ca.res_f32 = h->d_res0;
+      ca.headW = P + hd.headW; ca.headB = P + hd.headB; ca.head_dim = hd.head_dim; ca.head_out = seam ? nullptr : head_out;
+      if (seam) {
+        ca.do_sched = 1;
+        int rc2 = sched_make_args(seam->sched, &ca.sk);
+        if (rc2) return rc2;
+        ca.x_out = seam->sched.prev;
+      }
+    }
+    if (do_head) {
+      const int ph = do_tail ? 1 : 0;
+      mk(0, CH_CONV, 1, 0, 16, CH_IN_IM2COL, 1, CH_RES_NONE, 0, ph, (5 * h->D + 15) / 16);
+      mk(1, CH_CONV, 5, 2, 16, 1, 2, CH_RES_XPROJ, 0, ph, 4);
+      mk(2, CH_CONV, 5, 2, 16, 2, 1, CH_RES_NONE, 0, ph, 4);
+      mk(3, CH_CONV, 5, 2, 16, 1, 0, CH_RES_SMEM, 2, ph, 4);
+      mk(4, CH_DOWN, 3, 1, 16, 0, CH_OUT_GLOBAL, CH_RES_NONE, 0, ph, 4);
+      ca.xprojW = P + h->ops[1].resW; ca.xprojB = P + h->ops[1].resB;
+      ca.out_hi = hi_ptr(h->ops[4].out); ca.out_lo = lo_ptr(h->ops[4].out);
+    }
+    ca.B = rows; ca.H = h->H; ca.D = h->D; ca.wpack = h->d_chain;
+    ca.x = x; ca.x_period = x_period;
+    ca.temb_rows = temb_rows; ca.temb_stride = h->temb_total;
+    ca.temb2[0] = ttab_row; ca.temb2[1] = seam ? seam->next_ttab_row : nullptr;
+    ca.trace = (h->d_chain_trace && do_tail && do_head) ? h->d_chain_trace : nullptr;
+    int rc2 = launch_chain64(ca, nsplit, s);
+    if (rc2) return h->fail(rc2, "chain kernel launch failed");
+    ++*launches;
+    return B2P_OK;
+  };
   for (size_t oi = 0; oi < h->ops.size(); ++oi) {
     const LayerOp& op = h->ops[oi];
+    if (chain && oi == 0) {            // ops 0..4: the head chain (already run by the previous step's seam launch inside a plan)
+      if (!head_chain_done && (rc = launch_chain(false, true))) return rc;
+      oi = 4;
+      continue;
+    }
+    if (chain && (int)oi == u0 + 1) {  // ops u0+1 .. last: the tail chain (+ scheduler step + the next evaluation's head chain)
+      if ((rc = launch_chain(true, seam && seam->next_head))) return rc;
+      break;
+    }
     if (tc && op.tcW_hi != NPOS) {
       // ------------------------------ tcgen05 path ------------------------------
       TcArgs t;
@@ -593,6 +752,8 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
         t.nt[0] = 2; t.tap_blk[0][0] = 1; t.tap_shift[0][0] = 0; t.tap_blk[0][1] = 3; t.tap_shift[0][1] = -1;
         t.nt[1] = 2; t.tap_blk[1][0] = 0; t.tap_shift[1][0] = 1; t.tap_blk[1][1] = 2; t.tap_shift[1][1] = 0;
       }
+      const bool aux = chain && (int)oi == u0;   // the block's residual projection rides along as a sixth tap (consumed by the tail chain)
+      if (aux) { t.T = 6; t.aux_blk = 5; t.aux_out = h->d_res0; t.aux_bias = P + h->ops[u0 + 1].resB; }
       const int lstride = 1;
       t.Lrows = Lrows; t.log2L = ilog2(Lrows); t.samples_per_tile = 128 / Lrows; t.nrows = rows * Lrows;
       if (op.gamma != NPOS) { t.gn_gamma = P + op.gamma; t.gn_beta = P + op.beta; t.cg = op.Cout / 8; }
@@ -608,8 +769,8 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
         if (nsplit == 2 && (rc = tc_make_act_map(&m.a[sidx][1], lo_ptr(ins[sidx]), rows, op.Lin, cs[sidx], op.Lin, lstride, box_b))) return h->fail(rc, "tensor map (A lo)");
       }
       const __nv_bfloat16* P16 = reinterpret_cast<const __nv_bfloat16*>(h->d_pack16);
-      if ((rc = tc_make_weight_map(&m.w[0], P16 + op.tcW_hi, op.taps, op.Cout, op.C0 + op.C1, t.T, t.tile_n))) return h->fail(rc, "tensor map (W)");
-      if (nsplit == 2 && (rc = tc_make_weight_map(&m.w[1], P16 + op.tcW_lo, op.taps, op.Cout, op.C0 + op.C1, t.T, t.tile_n))) return h->fail(rc, "tensor map (W lo)");
+      if ((rc = tc_make_weight_map(&m.w[0], P16 + (aux ? h->aux_hi : op.tcW_hi), aux ? 6 : op.taps, op.Cout, op.C0 + op.C1, t.T, t.tile_n))) return h->fail(rc, "tensor map (W)");
+      if (nsplit == 2 && (rc = tc_make_weight_map(&m.w[1], P16 + (aux ? h->aux_lo : op.tcW_lo), aux ? 6 : op.taps, op.Cout, op.C0 + op.C1, t.T, t.tile_n))) return h->fail(rc, "tensor map (W lo)");
       if (op.resW != NPOS) {
         if (op.tcRW_hi != NPOS) {
           t.RC[0] = op.RC0; t.RC[1] = op.RC1; t.resB = P + op.resB;
@@ -771,6 +932,8 @@ int b2p_create(const b2p_model_config* cfg, int device, b2p_handle* out) {
     if (rc) { delete h; return rc; }
   }
   cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+  h->chain_on = chain_enabled();
+  if (getenv("B2P_CHAIN_TRACE")) { cudaMalloc((void**)&h->d_chain_trace, 8 * 16 * 16); cudaMemset(h->d_chain_trace, 0, 8 * 16 * 16); }
   *out = h;
   return B2P_OK;
 }
@@ -781,6 +944,7 @@ int b2p_destroy(b2p_handle h) {
   drop_graphs(h);
   if (h->d_pack) cudaFree(h->d_pack);
   if (h->d_pack16) cudaFree(h->d_pack16);
+  if (h->d_chain) cudaFree(h->d_chain);
   if (h->d_ws) cudaFree(h->d_ws);
   if (h->p_x) cudaFree(h->p_x);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -816,6 +980,7 @@ int b2p_finalize_weights(b2p_handle h) {
   B2P_CUDA_TRY(cudaSetDevice(h->device));
   int rc = build_program(h);
   if (rc) return h->fail(rc, "unsupported architecture");
+  build_chain(h);
   std::vector<size_t> tp_offs;
   if (h->cfg.guidance == B2P_CLASSIFIER_GUIDANCE) {
     Packer pk{h->pack_host};
@@ -825,6 +990,11 @@ int b2p_finalize_weights(b2p_handle h) {
   if (h->d_pack) { B2P_CUDA_TRY(cudaFree(h->d_pack)); h->d_pack = nullptr; }
   B2P_CUDA_TRY(cudaMalloc((void**)&h->d_pack, h->pack_host.size() * sizeof(float)));
   B2P_CUDA_TRY(cudaMemcpy(h->d_pack, h->pack_host.data(), h->pack_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (h->d_chain) { B2P_CUDA_TRY(cudaFree(h->d_chain)); h->d_chain = nullptr; }
+  if (h->chain_ok) {
+    B2P_CUDA_TRY(cudaMalloc((void**)&h->d_chain, h->chain_host.size() + 1024));
+    B2P_CUDA_TRY(cudaMemcpy(h->d_chain, h->chain_host.data(), h->chain_host.size(), cudaMemcpyHostToDevice));
+  }
   if (h->d_pack16) { B2P_CUDA_TRY(cudaFree(h->d_pack16)); h->d_pack16 = nullptr; }
   B2P_CUDA_TRY(cudaMalloc((void**)&h->d_pack16, h->pack16_host.size() * sizeof(uint16_t) + 256));
   B2P_CUDA_TRY(cudaMemcpy(h->d_pack16, h->pack16_host.data(), h->pack16_host.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
@@ -838,6 +1008,19 @@ int b2p_finalize_weights(b2p_handle h) {
 int b2p_set_precision(b2p_handle h, int precision) {
   if (!h || precision < 0 || precision > 2) return B2P_ERR_INVALID_ARG;
   h->cfg.precision = precision;
+  drop_graphs(h);
+  return B2P_OK;
+}
+
+// developer: stage clocks of CTA 0 of the last seam launch ([op][8] cycle counters; needs B2P_CHAIN_TRACE=1 at b2p_create)
+__attribute__((visibility("default"))) int b2p_debug_chain_trace(b2p_handle h, unsigned long long* out) {
+  if (!h || !out || !h->d_chain_trace) return B2P_ERR_STATE;
+  return (int)cudaMemcpy(out, h->d_chain_trace, 8 * 16 * 16, cudaMemcpyDeviceToHost);
+}
+
+int b2p_set_chain(b2p_handle h, int enabled) {
+  if (!h) return B2P_ERR_INVALID_ARG;
+  h->chain_on = enabled != 0;
   drop_graphs(h);
   return B2P_OK;
 }
@@ -983,6 +1166,10 @@ static int enqueue_plan(b2p_handle h, const b2p_plan_config& pc, const GraphKey&
     if ((rc = launch_conv_ffma(b, s))) return rc;
     *launches += 3;
   }
+  // Without guidance the tail chain of evaluation i, the scheduler step and the head chain of evaluation i+1 are ONE launch
+  // (chain64.cu): x_t stays in shared memory across the step boundary.
+  const bool seam_plan = g == B2P_NO_GUIDANCE && h->chain_ok && h->chain_on && h->cfg.precision != B2P_PREC_FP32 && B > h->small_batch_max &&
+                         !(pc.sched.thresholding && pc.sched.sample_max_value != 1.0f);
   for (int i = 0; i < T; ++i) {
     int t = (T - 1 - i) * (pc.sched.num_train_timesteps / T);
     b2p_step_coeffs kc;
@@ -990,6 +1177,15 @@ static int enqueue_plan(b2p_handle h, const b2p_plan_config& pc, const GraphKey&
     const int64_t* tp = h->p_tsteps + i;
     const float* mo = h->p_mo;
     const float* mo_u = nullptr;
+    int flags = B2P_STEP_ZERO_FIRST_WAYPOINT;
+    bool last = (i == T - 1);
+    if (last && pc.postprocess) flags |= B2P_STEP_FINAL_POSTPROCESS;
+    auto sched_launch = [&]() {
+      return SchedLaunch{pc.sched, kc, mo, mo_u, pc.free_scale, h->p_x, k.has_noise ? h->p_noise + (size_t)i * B * hd : nullptr,
+                         (inpaint && k.has_traj) ? h->p_traj : nullptr, (inpaint && k.has_mask) ? h->p_mask : nullptr,
+                         last ? h->p_out : h->p_x, nullptr, B, h->H, h->D, pc.eta, pc.magic_num, flags,
+                         k.dev_noise ? h->p_seed : nullptr, (unsigned)i, h->p_thr};
+    };
     if (g == B2P_FREE_GUIDANCE) {
       // rows [0,B) conditional, [B,2B) unconditional (interact.py:119-127, 134-141)
       if ((rc = run_unet(h, h->p_x, B, h->p_feat, B, tp, 1, h->p_cond, h->p_mo, nullptr, 2 * B, s, launches))) return rc;
@@ -1005,17 +1201,16 @@ static int enqueue_plan(b2p_handle h, const b2p_plan_config& pc, const GraphKey&
         if ((rc = launch_state_pred(h->tp, h->p_action, te_row, 0, h->p_mo, 1, B, h->H, h->D, s))) return rc;
       }
       ++*launches;
+    } else if (seam_plan) {
+      ChainSeam seam{sched_launch(), !last, last ? nullptr : h->p_ttab + (size_t)(i + 1) * h->temb_total};
+      if ((rc = run_unet(h, h->p_x, 0, h->p_feat, B, tp, 1, nullptr, h->p_mo, nullptr, B, s, launches, h->p_itab,
+                         h->p_ttab + (size_t)i * h->temb_total, &seam, i > 0))) return rc;
+      continue;                         // the scheduler step ran inside the seam launch
     } else {
       if ((rc = run_unet(h, h->p_x, 0, h->p_feat, B, tp, 1, nullptr, h->p_mo, nullptr, B, s, launches, h->p_itab,
                          h->p_ttab + (size_t)i * h->temb_total))) return rc;
     }
-    int flags = B2P_STEP_ZERO_FIRST_WAYPOINT;
-    bool last = (i == T - 1);
-    if (last && pc.postprocess) flags |= B2P_STEP_FINAL_POSTPROCESS;
-    SchedLaunch L{pc.sched, kc, mo, mo_u, pc.free_scale, h->p_x, k.has_noise ? h->p_noise + (size_t)i * B * hd : nullptr,
-                  (inpaint && k.has_traj) ? h->p_traj : nullptr, (inpaint && k.has_mask) ? h->p_mask : nullptr,
-                  last ? h->p_out : h->p_x, nullptr, B, h->H, h->D, pc.eta, pc.magic_num, flags,
-                  k.dev_noise ? h->p_seed : nullptr, (unsigned)i, h->p_thr};
+    SchedLaunch L = sched_launch();
     if ((rc = launch_sched_step(L, s))) return rc;
     ++*launches;
   }

@@ -1,0 +1,454 @@
+// Row-owned chain kernel for the 64-channel layers of the denoiser (K2 + K4 + K6 + K1 fused).
+//
+// At the full-resolution end of the U-Net every layer has 64 output channels, so ONE CTA can own a group of 8 trajectories
+// (8 x 16 positions = one 128-row tcgen05 tile, all 64 channels = one column tile) through a whole CHAIN of layers without
+// ever exchanging data with another CTA: activations stay in shared memory as the next layer's A operand (bf16 hi/lo,
+// K-major, 128-byte swizzle — written by the epilogue in exactly the layout TMA would produce), accumulators in TMEM, weights
+// stream in as pre-swizzled images (one bulk copy per tap, issued as soon as the previous layer's MMAs have retired).
+// No kernel boundary, no dependency release, no first-operand latency between the layers of a chain.
+//
+// Chains (modeling/temporal.py:197-245, interact.py:132-164):
+//   head of an evaluation  : downs.0 = im2col'd Conv1dBlock(7->64) [+temb], Conv1dBlock(64->64) [+1x1 projection of x],
+//                            second residual block, Downsample1d(64)                              (5 tensor-core layers)
+//   tail of an evaluation  : ups.<last> from its second conv on, Upsample1d(64), final_conv / act_conv with the fused 1x1 head
+//   seam (no guidance)     : tail of evaluation i + the scheduler step (bit-exact arithmetic of sched_math.cuh) + head of
+//                            evaluation i+1 in ONE launch: x_t never leaves shared memory between two denoiser evaluations.
+// Precision: NSPLIT = 2 -> bf16 hi/lo operands, hi*hi + lo*hi + hi*lo accumulated in fp32 (same "bf16x3" as conv_tc.cu);
+// NSPLIT = 1 -> single bf16 pass.  GroupNorm / Mish / residuals / scheduler arithmetic in fp32.
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <stddef.h>
+#include <string.h>
+
+#include "chain64.cuh"
+#include "tc_ptx.cuh"
+
+namespace b2p {
+
+constexpr int CH_THREADS = 512;                      // 16 warps: 4 per TMEM lane quadrant (1024 threads x 8 columns measured no faster: the epilogue is throughput-bound)
+constexpr int CH_EC = 8;                             // columns per epilogue thread and column half: one GroupNorm group, one 16-byte chunk
+constexpr int CH_SL = 4;                             // column slices per half (4 warps per TMEM lane quadrant)
+constexpr int CH_HCOLS = 160;                        // TMEM column stride between the two column halves (5 taps x 32 channels)
+constexpr int CH_HALF = 16 * 1024;                    // one bf16 plane of an activation buffer: [128 rows][64 ch]
+constexpr int CH_ACT_BYTES = 2 * CH_HALF;             // hi | lo
+constexpr int CH_TAP_BYTES = 64 * 64 * 2;             // one tap of one weight plane
+constexpr int CH_OFF_W = 3 * CH_ACT_BYTES;            // weight image of the current op (<= 5 taps x 8 KB x 2 planes)
+constexpr int CH_W_BYTES = 2 * 5 * CH_TAP_BYTES;
+constexpr int CH_OFF_HEADP = CH_OFF_W + CH_W_BYTES;   // head partial sums [slice][8][128 rows]
+constexpr int CH_OFF_MISC = CH_OFF_HEADP + CH_SL * 8 * 128 * 4;
+static_assert(CH_THREADS == 512, "the epilogue mapping assumes 16 warps: 4 lane quadrants x 4 column slices of 8 channels per half");
+constexpr int CH_MAX_HD = 16 * 8;                     // horizon 16 x transition dim <= 8 (im2col K = 5 * D <= 64; one scheduler element per thread)
+
+struct __align__(16) ChainShared {
+  uint64_t wbar;                 // weight image of the current op has landed
+  uint64_t mma_bar[2];           // MMAs of column half 0 / 1 of the current op have retired
+  uint32_t tmem_base;
+  uint32_t pad;                  // the float tables below are read as float4: keep them 16-byte aligned
+  float vec[2][3][64];           // bias / gamma / beta of the current op (double-buffered by op parity: the previous op's readers may still run)
+  float xs[CH_NS * CH_MAX_HD];   // x_t of the CTA's trajectories
+  float mo[CH_NS * CH_MAX_HD];   // model output of the CTA's trajectories (head result)
+  float xw[8 * 64 + 64];         // 1x1 projection of x: [D][64] + bias
+  float headw[8 * 64 + 8];       // head weights [d][64] + bias
+};
+
+static_assert(CH_OFF_MISC + sizeof(ChainShared) + 1024 <= 227 * 1024, "shared memory budget");
+static_assert(offsetof(ChainShared, xs) % 16 == 0 && offsetof(ChainShared, mo) % 16 == 0 && offsetof(ChainShared, headw) % 16 == 0, "float4 alignment");
+
+size_t chain64_smem_bytes() { return CH_OFF_MISC + sizeof(ChainShared) + 1024; }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// byte offset of the 16-byte chunk `c8` (8 channels) of row `r` inside a K-major, 128-byte-swizzled [128][64] bf16 plane
+__device__ __forceinline__ uint32_t swz(int r, int c8) { return (uint32_t)(r * 128 + ((c8 ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void split8(const float* v, uint4* hi, uint4* lo) {
+  __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(hi);
+  __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(lo);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    hp[i] = __float2bfloat16_rn(v[i]);
+    lp[i] = __float2bfloat16_rn(v[i] - __bfloat162float(hp[i]));
+  }
+}
+
+// The scheduler step runs once per launch: kept out of line so the hot per-op loop body stays small in the instruction cache.
+__device__ __noinline__ float sched_elem(const SchedK& k, int sample, int pos, int col, float m, float x, float nz, float tj, float mk, float* x0) {
+  return step_one(k, sample, pos, col, m, 0.f, x, nz, tj, mk, x0);
+}
+__device__ __noinline__ float4 philox_group(unsigned long long seed, unsigned group, unsigned step) { return philox_normal4(seed, group, step); }
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_constant__ ChainArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  ChainShared* sh = reinterpret_cast<ChainShared*>(smem + CH_OFF_MISC);
+  uint8_t* wbuf = smem + CH_OFF_W;
+  float (*headp)[8][TC_M] = reinterpret_cast<float (*)[8][TC_M]>(smem + CH_OFF_HEADP);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b0 = blockIdx.x * CH_NS;
+  const int nb = a.B - b0 < CH_NS ? a.B - b0 : CH_NS;
+  const int HD = a.H * a.D;
+
+  if (tid == 0) {
+    mbar_init(&sh->wbar, 1);
+    mbar_init(&sh->mma_bar[0], 1);
+    mbar_init(&sh->mma_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // weights-only tables: independent of the preceding kernels
+  if (a.xprojW)
+    for (int i = tid; i < a.D * 64 + 64; i += CH_THREADS) sh->xw[i] = i < a.D * 64 ? __ldg(a.xprojW + i) : __ldg(a.xprojB + i - a.D * 64);
+  if (a.headW) {   // [64][head_dim] -> [d][64]
+    const int hd = a.head_dim;
+    for (int i = tid; i < 64 * hd; i += CH_THREADS) { const int c = i / hd, d = i - c * hd; sh->headw[d * 64 + c] = __ldg(a.headW + i); }
+    if (tid < hd) sh->headw[8 * 64 + tid] = __ldg(a.headB + tid);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  auto issue_weights = [&](int oi) {   // one thread: pre-swizzled image, one bulk copy per tap and plane
+    const ChainOp& op = a.ops[oi];
+    const uint32_t plane = (uint32_t)op.T * CH_TAP_BYTES;
+    mbar_expect_tx(&sh->wbar, NSPLIT * plane);
+    const uint8_t* src = a.wpack + op.w_off;
+    for (int i = 0; i < NSPLIT * op.T; ++i) bulk_g2s(wbuf + (size_t)i * CH_TAP_BYTES, src + (size_t)i * CH_TAP_BYTES, CH_TAP_BYTES, &sh->wbar);
+  };
+  if (tid == 0) issue_weights(0);
+  griddep_launch_dependents();      // the next kernel may become resident and prefetch ITS weights
+  griddep_wait();                   // everything below reads what the preceding kernels wrote
+
+  // x_t of this CTA's trajectories
+  for (int i = tid; i < CH_NS * HD; i += CH_THREADS) {
+    const int s = i / HD;
+    float v = 0.f;
+    if (s < nb) {
+      const int bs = b0 + s;
+      const int row = a.x_period > 0 ? bs % a.x_period : bs;
+      v = a.x[(size_t)row * HD + (i - s * HD)];   // plain load: a seam launch rewrites x in place later on
+    }
+    sh->xs[i] = v;
+  }
+  if (a.ops[0].in_buf >= 0) {       // the chain starts from a tensor in global memory: stage it as the first A operand
+    const int L0 = a.ops[0].L;
+    uint8_t* dst = smem + a.ops[0].in_buf * CH_ACT_BYTES;
+    const int rows_ok = nb * L0;
+    for (int i = tid; i < NSPLIT * TC_M * 8; i += CH_THREADS) {
+      const int half = i >> 10, row = (i >> 3) & 127, c8 = i & 7;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row < rows_ok) v = __ldg(reinterpret_cast<const uint4*>((half ? a.in_lo : a.in_hi) + ((size_t)b0 * L0 + row) * 64 + c8 * 8));
+      *reinterpret_cast<uint4*>(dst + half * CH_HALF + swz(row, c8)) = v;
+    }
+  }
+
+  const int quad = warp & 3, slice = warp >> 2, col0 = slice * CH_EC;
+  const int r = quad * 32 + lane;                               // tile row == TMEM lane
+  const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + col0;
+  uint32_t wpar = 0, mpar = 0;
+
+#pragma unroll 1
+  for (int oi = 0; oi < a.n_ops; ++oi) {
+    const ChainOp& op = a.ops[oi];
+    const int L = op.L;
+    if (op.in_buf == CH_IN_IM2COL) {
+      // A[row (s, l)][k = j * D + c] = x[s, l + j - pad, c]  (zero outside the trajectory, zero for k >= T_im2col * D)
+      __syncthreads();                                           // xs may just have been rewritten by the scheduler step
+      const int D = a.D, KT = 5 * D;
+      for (int i = tid; i < TC_M * 8; i += CH_THREADS) {
+        const int row = i >> 3, c8 = i & 7;
+        const int s = row >> 4, l = row & 15;                    // H == 16
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = c8 * 8 + e;
+          const int j = k / D, c = k - j * D;
+          const int pos = l + j - 2;
+          v[e] = (k < KT && s < nb && pos >= 0 && pos < 16) ? sh->xs[s * HD + pos * D + c] : 0.f;
+        }
+        uint4 hi, lo;
+        split8(v, &hi, &lo);
+        *reinterpret_cast<uint4*>(smem + swz(row, c8)) = hi;
+        if (NSPLIT == 2) *reinterpret_cast<uint4*>(smem + CH_HALF + swz(row, c8)) = lo;
+      }
+    }
+    if (tid < 192) {
+      const int w = tid >> 6, c = tid & 63;
+      const float* p = w == 0 ? op.bias : (w == 1 ? op.gamma : op.beta);
+      sh->vec[oi & 1][w][c] = p ? __ldg(p + c) : (w == 1 ? 1.f : 0.f);
+    }
+    if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 0] = clock64();
+    fence_async_smem();              // the A operand was written with ordinary stores: make it visible to the tensor core
+    tc_fence_before();               // ... and the previous op's TMEM reads are complete
+    __syncthreads();
+    if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 1] = clock64();
+
+    if (tid == 32) {
+      // =============================== MMA issue (one thread) ===============================
+      mbar_wait(&sh->wbar, wpar);
+      tc_fence_after();
+      if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 2] = clock64();
+      const uint32_t sa = smem_u32(smem + (op.in_buf < 0 ? 0 : op.in_buf) * CH_ACT_BYTES);
+      const uint32_t sb = smem_u32(wbuf);
+      const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + CH_HALF);
+      // the weight image is ordered [column half][tap][32 channels]: the taps of one half are ONE instruction of N = 32 * T, and the
+      // epilogue of half 0 overlaps the MMAs of half 1
+      const uint32_t idn = umma_idesc_n(op.T * 32);
+      const uint32_t half_bytes = (uint32_t)op.T * (CH_TAP_BYTES / 2);
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        const uint64_t b_hi = umma_desc(sb + hf * half_bytes), b_lo = umma_desc(sb + op.T * CH_TAP_BYTES + hf * half_bytes);
+        const uint32_t dcol = tmem_base + hf * CH_HCOLS;
+#pragma unroll 1
+        for (int k = 0; k < op.ksteps; ++k) {
+          const uint64_t ko = (uint64_t)(k * TC_UMMA_K * 2 / 16);  // +32 B per K step, in 16-byte units
+          umma(dcol, a_hi + ko, b_hi + ko, idn, k == 0 ? 0u : 1u);
+          if (NSPLIT == 2) {
+            umma(dcol, a_lo + ko, b_hi + ko, idn, 1u);
+            umma(dcol, a_hi + ko, b_lo + ko, idn, 1u);
+          }
+        }
+        umma_commit(&sh->mma_bar[hf]);
+      }
+      if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 3] = clock64();
+    }
+    wpar ^= 1;
+    __syncwarp();
+
+    // ------------- everything added after GroupNorm / Mish is fetched while the tensor core works -------------
+    const int l = r & (L - 1), sidx = r >> op.log2L;
+    const bool row_ok = sidx < nb;
+    const int b = b0 + sidx;
+    float addv[2][CH_EC];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int ch0 = hf * 32 + col0;                 // first of this thread's 8 channels in column half hf
+#pragma unroll
+      for (int c = 0; c < CH_EC; ++c) addv[hf][c] = 0.f;
+      if (row_ok) {
+        if (op.temb_off >= 0) {
+          const float* tp = a.temb_rows + (size_t)b * a.temb_stride + op.temb_off + ch0;
+          const float* t2 = a.temb2[op.phase] ? a.temb2[op.phase] + op.temb_off + ch0 : nullptr;
+#pragma unroll
+          for (int c = 0; c < CH_EC; c += 4) {
+            float4 t4v = __ldg(reinterpret_cast<const float4*>(tp + c));
+            addv[hf][c] += t4v.x; addv[hf][c + 1] += t4v.y; addv[hf][c + 2] += t4v.z; addv[hf][c + 3] += t4v.w;
+            if (t2) { float4 u = __ldg(reinterpret_cast<const float4*>(t2 + c)); addv[hf][c] += u.x; addv[hf][c + 1] += u.y; addv[hf][c + 2] += u.z; addv[hf][c + 3] += u.w; }
+          }
+        }
+        if (op.res_kind == CH_RES_F32) {
+          const float* q = a.res_f32 + ((size_t)b * L + l) * 64 + ch0;
+#pragma unroll
+          for (int c = 0; c < CH_EC; c += 4) { float4 t4v = __ldg(reinterpret_cast<const float4*>(q + c)); addv[hf][c] += t4v.x; addv[hf][c + 1] += t4v.y; addv[hf][c + 2] += t4v.z; addv[hf][c + 3] += t4v.w; }
+        } else if (op.res_kind == CH_RES_XPROJ) {   // residual_conv(x) of the first block: 1x1 conv over the D raw channels, fp32 on CUDA cores
+          const float* xr = sh->xs + sidx * HD + l * a.D;
+#pragma unroll
+          for (int c = 0; c < CH_EC; ++c) addv[hf][c] = sh->xw[a.D * 64 + ch0 + c];
+#pragma unroll 1
+          for (int d = 0; d < a.D; ++d) {
+            const float xv = xr[d];
+#pragma unroll
+            for (int c = 0; c < CH_EC; ++c) addv[hf][c] = fmaf(xv, sh->xw[d * 64 + ch0 + c], addv[hf][c]);
+          }
+        }
+      }
+    }
+    if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 4] = clock64();
+
+    // =============================== epilogue (all 16 warps), one column half at a time ===============================
+    const int n_out = op.kind == CH_UP ? 2 : 1;
+    float hsum[8];                                      // fused head: partial dot products of this thread over both halves
+#pragma unroll
+    for (int d = 0; d < 8; ++d) hsum[d] = 0.f;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int ch0 = hf * 32 + col0, c8 = hf * 4 + slice;
+      mbar_wait_sleep(&sh->mma_bar[hf], mpar);
+      tc_fence_after();
+      if (hf == 0 && a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 5] = clock64();
+      if (hf == 1 && tid == 0 && oi + 1 < a.n_ops) issue_weights(oi + 1);   // the weight buffer is free: every MMA of this op has retired
+#pragma unroll 1
+      for (int o = 0; o < n_out; ++o) {
+        float v[CH_EC];
+#pragma unroll
+        for (int c = 0; c < CH_EC; ++c) v[c] = sh->vec[oi & 1][0][ch0 + c];
+        // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the trajectory) ----
+        // The TMEM load of tap i+1 is in flight while tap i is shifted and added (tcgen05.wait::ld waits for every outstanding load,
+        // so the next one is issued right after the wait).
+        const int nt = op.kind == CH_UP ? 2 : op.T;
+        const bool up = op.kind == CH_UP;
+        const uint32_t tbase = taddr + hf * CH_HCOLS;
+        auto tap_blk = [&](int i) { return up ? (o == 0 ? (i == 0 ? 1 : 3) : (i == 0 ? 0 : 2)) : i; };   // convT: out[2m] = Y1[m] + Y3[m-1]; out[2m+1] = Y0[m+1] + Y2[m]
+        auto tap_shift = [&](int i) { return up ? (o == 0 ? (i == 0 ? 0 : -1) : (i == 0 ? 1 : 0)) : i - op.pad; };
+        float y[2][CH_EC];
+        tmem_ld<CH_EC, false>(tbase + tap_blk(0) * 32, y[0]);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          if (i < nt) {
+            tmem_ld_wait();
+            if (i + 1 < nt) tmem_ld<CH_EC, false>(tbase + tap_blk(i + 1) * 32, y[(i + 1) & 1]);
+            const int d = tap_shift(i);
+            if (d == 0) {
+#pragma unroll
+              for (int c = 0; c < CH_EC; ++c) v[c] += y[i & 1][c];
+            } else {
+              const bool valid = (l + d >= 0) && (l + d < L);
+              const int src = (lane + d) & 31;
+#pragma unroll
+              for (int c = 0; c < CH_EC; ++c) { const float g = __shfl_sync(0xffffffffu, y[i & 1][c], src); v[c] += valid ? g : 0.f; }
+            }
+          }
+        }
+        if (op.gn) {   // GroupNorm(8): a group = the thread's 8 consecutive channels x the L rows (adjacent lanes) of a trajectory
+          const float inv_n = 1.0f / (float)(8 * L);
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) s += v[c];
+#pragma unroll 1
+          for (int of = 1; of < L; of <<= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
+          const float mean = s * inv_n;
+          float q = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { const float dd = v[c] - mean; q = fmaf(dd, dd, q); }
+#pragma unroll 1
+          for (int of = 1; of < L; of <<= 1) q += __shfl_xor_sync(0xffffffffu, q, of);
+          const float rs = rsqrtf(q * inv_n + 1e-5f);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = mish_fast((v[c] - mean) * rs * sh->vec[oi & 1][1][ch0 + c] + sh->vec[oi & 1][2][ch0 + c]);
+        }
+#pragma unroll
+        for (int c = 0; c < CH_EC; ++c) v[c] += addv[hf][c];
+        if (op.res_kind == CH_RES_SMEM) {     // identity residual: the block input, still resident (hi + lo)
+          const uint8_t* rb = smem + op.res_buf * CH_ACT_BYTES;
+          const uint4 hh = *reinterpret_cast<const uint4*>(rb + swz(r, c8));
+          const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hh);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += __bfloat162float(hp[i]);
+          if (NSPLIT == 2) {
+            const uint4 ll = *reinterpret_cast<const uint4*>(rb + CH_HALF + swz(r, c8));
+            const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&ll);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += __bfloat162float(lp[i]);
+          }
+        }
+        // ---- output ----
+        if (op.out_buf >= 0) {
+          // next op's A operand, written in the swizzled K-major layout; rows without a trajectory are zero
+          const int ro = op.kind == CH_UP ? sidx * 2 * L + 2 * l + o : r;
+          if (op.kind != CH_UP || r < 64) {
+            uint8_t* ob = smem + op.out_buf * CH_ACT_BYTES;
+            uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+            if (row_ok) split8(v, &hi, &lo);
+            *reinterpret_cast<uint4*>(ob + swz(ro, c8)) = hi;
+            if (NSPLIT == 2) *reinterpret_cast<uint4*>(ob + CH_HALF + swz(ro, c8)) = lo;
+          }
+        } else if (op.out_buf == CH_OUT_GLOBAL) {
+          const bool emit = row_ok && (op.kind != CH_DOWN || (l & 1) == 0);
+          if (emit) {
+            const size_t orow = op.kind == CH_DOWN ? (size_t)b * (L >> 1) + (l >> 1) : (op.kind == CH_UP ? (size_t)b * 2 * L + 2 * l + o : (size_t)b * L + l);
+            uint4 hi, lo;
+            split8(v, &hi, &lo);
+            *reinterpret_cast<uint4*>(a.out_hi + orow * 64 + ch0) = hi;
+            if (NSPLIT == 2) *reinterpret_cast<uint4*>(a.out_lo + orow * 64 + ch0) = lo;
+          }
+        } else {
+          // fused 1x1 head (final_conv.1 / act_conv.1): this thread's share of the dot products
+          const int hd = a.head_dim;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) {
+            if (d < hd) {
+              const float4 w0 = *reinterpret_cast<const float4*>(sh->headw + d * 64 + ch0), w1 = *reinterpret_cast<const float4*>(sh->headw + d * 64 + ch0 + 4);
+              float s = fmaf(v[0], w0.x, fmaf(v[1], w0.y, fmaf(v[2], w0.z, fmaf(v[3], w0.w, hsum[d]))));
+              hsum[d] = fmaf(v[4], w1.x, fmaf(v[5], w1.y, fmaf(v[6], w1.z, fmaf(v[7], w1.w, s))));
+            }
+          }
+        }
+      }
+    }
+    mpar ^= 1;
+    if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 8] = clock64();
+    if (op.out_buf == CH_OUT_HEAD) {
+      const int hd = a.head_dim;
+#pragma unroll
+      for (int d = 0; d < 8; ++d)
+        if (d < hd) headp[slice][d][r] = hsum[d];
+      __syncthreads();
+      if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 10] = clock64();
+      for (int idx = tid; idx < TC_M * hd; idx += CH_THREADS) {   // one (row, d) sum at a time
+        const int rr = idx / hd, d = idx - rr * hd;
+        const float m = sh->headw[8 * 64 + d] + headp[0][d][rr] + headp[1][d][rr] + headp[2][d][rr] + headp[3][d][rr];
+        sh->mo[idx] = m;                      // index rr * hd + d with rr == s * 16 + l: the [NS, H, head_dim] block of this CTA
+        const int s2 = rr >> 4;
+        if (a.head_out && s2 < nb) a.head_out[((size_t)(b0 + s2) * 16 + (rr & 15)) * hd + d] = m;
+      }
+      __syncthreads();
+      if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 11] = clock64();
+      if (a.do_sched)
+#pragma unroll 1
+        for (int e = tid; e < nb * HD; e += CH_THREADS) {
+          // ---- fused scheduler step, one element at a time per thread: the stand-alone kernel's arithmetic and noise counters (group = 4 elements) ----
+          const size_t ge = (size_t)b0 * HD + e;                // global element index
+          const SchedK& k = a.sk;
+          float nz = 0.f;
+          if (k.noise) nz = __ldg(k.noise + ge);
+          else if (k.seed) { const float4 n4 = philox_group(*k.seed, (unsigned)(ge >> 2), k.noise_step); nz = (ge & 3) == 0 ? n4.x : ((ge & 3) == 1 ? n4.y : ((ge & 3) == 2 ? n4.z : n4.w)); }
+          const float tj = k.traj ? __ldg(k.traj + ge) : 0.f;
+          const float mk = k.mask ? __ldg(k.mask + ge) : 0.f;
+          const int sample = e / HD, pos = e - sample * HD;
+          float x0;
+          const float out = sched_elem(k, sample, pos, pos % a.D, sh->mo[e], sh->xs[e], nz, tj, mk, &x0);
+          a.x_out[ge] = out;
+          sh->xs[e] = out;                                      // x_{t-1}: the next evaluation's input (im2col + projection)
+        }
+    }
+    if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 6] = clock64();
+  }
+
+  if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[a.n_ops * 16] = clock64();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+int launch_chain64(const ChainArgs& a, int nsplit, cudaStream_t s) {
+  if (a.n_ops < 1 || a.n_ops > CH_MAXOPS || a.B <= 0 || a.H != 16 || a.D < 1 || a.D > 8 || (a.H * a.D) % 4 != 0) return B2P_ERR_INVALID_ARG;
+  for (int i = 0; i < a.n_ops; ++i) {
+    const ChainOp& op = a.ops[i];
+    if (op.T < 1 || op.T > 5 || (op.L != 8 && op.L != 16) || op.in_buf > 2 || op.out_buf > 2 || op.ksteps < 1 || op.ksteps > 4) return B2P_ERR_INVALID_ARG;
+    if (op.out_buf >= 0 && (op.out_buf == op.in_buf || (op.res_kind == CH_RES_SMEM && op.out_buf == op.res_buf))) return B2P_ERR_INVALID_ARG;
+    if (op.kind == CH_UP && (op.L != 8 || op.T != 4)) return B2P_ERR_INVALID_ARG;
+    if (op.out_buf == CH_OUT_HEAD && (!a.headW || a.head_dim < 1 || a.head_dim > 8 || op.L != 16)) return B2P_ERR_INVALID_ARG;
+    if (op.in_buf == CH_IN_IM2COL && op.L != 16) return B2P_ERR_INVALID_ARG;
+  }
+  if (a.do_sched && (a.head_dim != a.D || !a.x_out || a.sk.mo_u || a.sk.clip_mode == 3)) return B2P_ERR_INVALID_ARG;
+  const size_t smem = chain64_smem_bytes();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((a.B + CH_NS - 1) / CH_NS); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (nsplit == 2) {
+    B2P_CUDA_TRY(cudaFuncSetAttribute(chain64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return (int)cudaLaunchKernelEx(&cfg, chain64_kernel<2>, a);
+  }
+  B2P_CUDA_TRY(cudaFuncSetAttribute(chain64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return (int)cudaLaunchKernelEx(&cfg, chain64_kernel<1>, a);
+}
+
+}  // namespace b2p

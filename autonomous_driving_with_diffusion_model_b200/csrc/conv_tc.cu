@@ -34,12 +34,10 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "tc_ptx.cuh"
 
 namespace b2p {
 
-constexpr int TC_M = 128;           // rows per tile
-constexpr int TC_K = 64;            // channels per pipeline stage (128 bytes of bf16: one swizzle atom row)
-constexpr int TC_UMMA_K = 16;
 constexpr int TC_THREADS = 512;
 constexpr int A_BYTES = TC_M * TC_K * 2;   // 16 KB
 
@@ -67,153 +65,6 @@ int tc_trace_launch = 0;
 #define TC_T(k)
 #define TC_TG(k, all)
 #endif
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// long wait (epilogue warps waiting for the accumulators): suspend in hardware instead of spinning so that the waiting
-// warps do not take issue slots from the single TMA / MMA issuing threads that share their schedulers
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAITS_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONES_%=;\n\t"
-      "bra WAITS_%=;\n\t"
-      "DONES_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-// multicast variant: the box lands at the same shared-memory offset in every CTA of `mask`, and each of their mbarriers
-// (same offset) receives the complete_tx for the bytes written into that CTA
-__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128B swizzle, 8-row groups 1024 B apart (sm100 descriptor version 1)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
-  d |= (uint64_t)0 << 16;                            // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
-  d |= (uint64_t)1 << 46;                            // version = 1 (Blackwell)
-  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-  return d;
-}
-// kind::f16: D fp32, A/B bf16, both K-major, M=128, N=n (multiple of 16, <= 256)
-__device__ __forceinline__ constexpr uint32_t umma_idesc_n(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-}
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far have retired
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-template <int EC, bool WAIT = true> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-template <bool WAIT> __device__ __forceinline__ void tmem_ld16_impl(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  if (WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-template <bool WAIT> __device__ __forceinline__ void tmem_ld8_impl(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-  if (WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-template <bool WAIT> __device__ __forceinline__ void tmem_ld4_impl(uint32_t taddr, float* v) {
-  uint32_t r[4];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
-  if (WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-template <> __device__ __forceinline__ void tmem_ld<16, true>(uint32_t t, float* v) { tmem_ld16_impl<true>(t, v); }
-template <> __device__ __forceinline__ void tmem_ld<16, false>(uint32_t t, float* v) { tmem_ld16_impl<false>(t, v); }
-template <> __device__ __forceinline__ void tmem_ld<8, true>(uint32_t t, float* v) { tmem_ld8_impl<true>(t, v); }
-template <> __device__ __forceinline__ void tmem_ld<8, false>(uint32_t t, float* v) { tmem_ld8_impl<false>(t, v); }
-template <> __device__ __forceinline__ void tmem_ld<4, true>(uint32_t t, float* v) { tmem_ld4_impl<true>(t, v); }
-template <> __device__ __forceinline__ void tmem_ld<4, false>(uint32_t t, float* v) { tmem_ld4_impl<false>(t, v); }
-
-// Mish with the SFU approximations (ex2.approx / rcp.approx): relative error ~1e-6, far below the bf16-split noise.
-__device__ __forceinline__ float mish_fast(float x) {
-  float e = __expf(x);
-  float n = e * (e + 2.f);
-  float m = x * __fdividef(n, n + 2.f);
-  return x > 20.f ? x : m;
-}
-
-// programmatic dependent launch: block until the preceding kernel in the stream has completed and flushed its writes /
-// allow the next kernel in the stream to be scheduled (its pre-wait prologue then overlaps the rest of this kernel)
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t local_saddr, uint32_t cta, float x) {
-  uint32_t ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(cta));
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(x) : "memory");
-}
-
-// 8-byte asynchronous store into CTA `cta` of the cluster that also signals the bytes on that CTA's mbarrier
-__device__ __forceinline__ void st_async_cluster_f32x2(uint32_t local_dst, uint32_t local_bar, uint32_t cta, float a, float b) {
-  uint32_t rd, rb;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rd) : "r"(local_dst), "r"(cta));
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(local_bar), "r"(cta));
-  const unsigned long long v = ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(a);
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(rd), "l"(v), "r"(rb) : "memory");
-}
 
 struct __align__(16) TcShared {
   uint64_t full[8];
@@ -427,7 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     // N = T*TN (<= 256; a fifth 64-wide tap takes a second instruction) covers them.  Descriptors are built once per
     // stage and advanced by adding to the address field.
     const int nA = (T * TN <= 256) ? T : 4;                              // taps covered by the first instruction
-    const uint32_t idescA = umma_idesc_n(nA * TN), idescB = umma_idesc_n(TN);
+    const uint32_t idescA = umma_idesc_n(nA * TN), idescB = umma_idesc_n(TN), idescR = umma_idesc_n((T - nA) * TN);   // idescR: the taps beyond the first instruction
     const bool concat = NSPLIT == 2 && a.concat;                         // W_hi and W_lo are adjacent in N: A_hi x [W_hi | W_lo] is one instruction
     const uint32_t idescC = umma_idesc_n(concat ? 2 * T * TN : TN);
     for (int it = 0, s = 0, par = 0; it < n_local; ++it, s = (s + 1 == stages ? 0 : s + 1), par ^= (s == 0)) {   // s = it % stages, par = (it / stages) & 1
@@ -459,10 +310,10 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
           }
           if (nA < T) {
             const uint64_t t4 = (uint64_t)(nA * BT_BYTES / 16);
-            umma(tmem_base + nA * TN, a_hi + ko, b_hi + t4 + ko, idescB, acc);
+            umma(tmem_base + nA * TN, a_hi + ko, b_hi + t4 + ko, idescR, acc);
             if (NSPLIT == 2) {
-              umma(tmem_base + nA * TN, a_lo + ko, b_hi + t4 + ko, idescB, 1u);
-              umma(tmem_base + nA * TN, a_hi + ko, b_lo + t4 + ko, idescB, 1u);
+              umma(tmem_base + nA * TN, a_lo + ko, b_hi + t4 + ko, idescR, 1u);
+              umma(tmem_base + nA * TN, a_hi + ko, b_lo + t4 + ko, idescR, 1u);
             }
           }
         }
@@ -648,6 +499,23 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
           }
         }
       }
+      if (a.aux_out && o == 0 && n_local > 0) {   // the extra tap block: a 1x1 conv of the same rows (residual projection), fp32 rows
+        float rv[EC];
+        tmem_ld<EC>(taddr + a.aux_blk * TN, rv);
+        if (NSPLIT == 2 && a.concat) {
+          float r2[EC];
+          tmem_ld<EC>(taddr + (T + a.aux_blk) * TN, r2);
+#pragma unroll
+          for (int c = 0; c < EC; ++c) rv[c] += r2[c];
+        }
+        if (row_ok) {
+          float* q = a.aux_out + (size_t)grow * a.Cout + gcol;
+#pragma unroll
+          for (int c = 0; c < EC; c += 4)
+            *reinterpret_cast<float4*>(q + c) = make_float4(rv[c] + __ldg(a.aux_bias + gcol + c), rv[c + 1] + __ldg(a.aux_bias + gcol + c + 1),
+                                                            rv[c + 2] + __ldg(a.aux_bias + gcol + c + 2), rv[c + 3] + __ldg(a.aux_bias + gcol + c + 3));
+        }
+      }
       if (a.headW) {   // fused 1x1 head (TN == Cout == 64): partial dot products per column slice, summed by slice 0
         // head weights as [d][64] (+ bias) in the idle operand ring (a TN == 64 launch has no peers writing into it); the
         // values were fetched before the accumulator wait, so no global latency is exposed here
@@ -753,6 +621,7 @@ static int launch_t(const TcMaps& maps, const TcArgs& a_in, dim3 grid, cudaStrea
   a.concat = (NSPLIT == 2 && concat && TN <= 32 && 2 * a.T * TN <= 256 && (concat > 1 || chunks * 256 > 10 * a.T * TN)) ? 1 : 0;
   a.ring = SmemPlan<TN>::ring;
   if (TN == 16 && bigring && (int)(grid.x * grid.y) <= 148) a.ring = SmemPlan<32>::ring;
+  if (TN == 16 && 2 * NSPLIT * (A_BYTES + a.T * TN * TC_K * 2) > a.ring) a.ring = SmemPlan<32>::ring;   // six tap blocks: two stages need the deep ring
   {
     const int stage_bytes = NSPLIT * (A_BYTES + a.T * TN * TC_K * 2);
     a.stages = a.ring / stage_bytes > 8 ? 8 : a.ring / stage_bytes;
@@ -791,6 +660,7 @@ int tc_pick_tile_n(int nrows, int Cout, bool has_head) {
 // activation tensor maps are encoded (their box covers samples_per_tile / cluster_l samples).
 int tc_configure(TcArgs& a) {
   a.tile_n = tc_pick_tile_n(a.nrows, a.Cout, a.headW != nullptr);
+  if (a.T == 6 && a.tile_n == 64) a.tile_n = 32;   // six tap blocks of 64 columns would leave a single ring stage
   const int TN = a.tile_n;
   if (a.Cout % TN) return B2P_ERR_INVALID_ARG;
   a.cluster_n = 1;
@@ -827,8 +697,8 @@ int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStrea
 #endif
   const int TN = a.tile_n;
   if (TN != 64 && TN != 32 && TN != 16) return tc_fail(__LINE__, a, "invalid layer shape");
-  if (a.T < 1 || a.T > 5 || a.n_out < 1 || a.n_out > 2 || (a.out_ldiv != 1 && a.out_ldiv != 2)) return tc_fail(__LINE__, a, "invalid layer shape");
-  if (nsplit * (A_BYTES + a.T * TN * TC_K * 2) * 2 > (TN == 64 ? SmemPlan<64>::ring : (TN == 32 ? SmemPlan<32>::ring : SmemPlan<16>::ring))) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (a.T < 1 || a.T > 6 || a.n_out < 1 || a.n_out > 2 || (a.out_ldiv != 1 && a.out_ldiv != 2)) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (nsplit * (A_BYTES + a.T * TN * TC_K * 2) * 2 > (TN == 64 ? SmemPlan<64>::ring : SmemPlan<32>::ring)) return tc_fail(__LINE__, a, "invalid layer shape");
   if (a.Cout % TN || a.C[0] % TC_K || a.C[1] % TC_K || a.RC[0] % TC_K || a.RC[1] % TC_K || a.nrows <= 0) return tc_fail(__LINE__, a, "invalid layer shape");
   if (a.Lrows > 32 || (a.Lrows & (a.Lrows - 1)) || TC_M % a.Lrows) return tc_fail(__LINE__, a, "invalid layer shape");
   if (a.headW && (a.Cout != 64 || TN != 64 || a.head_dim > 8)) return tc_fail(__LINE__, a, "invalid layer shape");

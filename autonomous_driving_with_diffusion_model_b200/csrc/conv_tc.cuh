@@ -38,6 +38,9 @@ struct TcArgs {
   const __nv_bfloat16* res_hi; const __nv_bfloat16* res_lo;   // identity residual, bf16 hi/lo
   const float* headW; const float* headB; int head_dim; float* head_out;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  // auxiliary output: tap block `aux_blk` (>= 0) is NOT part of the conv sum; it is a 1x1 conv of the same input rows (the block's
+  // residual projection packed as one more "tap"), written as fp32 rows  aux_out[row, Cout] = Y_aux + aux_bias  for the chain kernel
+  float* aux_out; const float* aux_bias; int aux_blk;
   int tile_n;             // column-tile width: 64, 32 or 16 (tc_pick_tile_n)
   int cluster_n;          // set by launch_conv_tc: CTAs along N sharing one GroupNorm group
   int cluster_l;          // set by launch_conv_tc: cluster size along N (activation-tile multicast), multiple of cluster_n

@@ -156,6 +156,16 @@ class ImageEncoder(_Tree):
     conv+bias(+residual)+ReLU, and the whole network replayed as one CUDA graph per input shape (36 launches instead of
     ~110 eager ones).  TF32 follows ``torch.backends.cudnn.allow_tf32`` as for any torch convolution."""
 
+    compute_dtype = "fp32"   # "fp32" (TF32 follows torch.backends.cudnn.allow_tf32) or "bf16" (SURVEY.md 8f rank 1: bf16 channels-last;
+    #                           feature error <= 3e-2 of its max-abs vs the fp32 golden, tests/test_gpu_parity.py) — set_precision()
+
+    def set_precision(self, precision: str) -> "ImageEncoder":
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("encoder precision must be 'fp32' or 'bf16'")
+        object.__setattr__(self, "compute_dtype", precision)
+        self.invalidate()
+        return self
+
     def _bn(self, x, m):
         return F.batch_norm(x, m.running_mean, m.running_var, m.weight, m.bias, False, 0.0, 1e-5)
 
@@ -177,11 +187,11 @@ class ImageEncoder(_Tree):
         return F.linear(F.adaptive_avg_pool2d(x, 1).flatten(1), self.fc.weight, self.fc.bias)
 
     # ---- folded / fused / graphed inference path --------------------------------------------------------
-    @staticmethod
-    def _fold(conv_w, bn):
+    def _fold(self, conv_w, bn):
+        dt = torch.bfloat16 if self.compute_dtype == "bf16" else torch.float32
         scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + 1e-5)
-        w = (conv_w.detach().float() * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
-        return w, (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
+        w = (conv_w.detach().float() * scale.view(-1, 1, 1, 1)).to(dt).contiguous(memory_format=torch.channels_last)
+        return w, (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).to(dt).contiguous()
 
     def _tensors(self):
         if getattr(self, "_tlist", None) is None:
@@ -205,7 +215,7 @@ class ImageEncoder(_Tree):
         return (getattr(self, "_gen", 0), sum([t._version for t in self._tensors()]))
 
     def _folded(self):
-        key = tuple([(t.data_ptr(), t._version) for t in self._tensors()])
+        key = (self.compute_dtype,) + tuple([(t.data_ptr(), t._version) for t in self._tensors()])
         cache = getattr(self, "_fold_cache", None)
         if cache is None or cache[0] != key:
             stem = self._fold(self.conv1.weight, self.bn1)
@@ -224,18 +234,18 @@ class ImageEncoder(_Tree):
     def _forward_fused(self, img: torch.Tensor) -> torch.Tensor:
         _, (w, b), blocks = self._folded()
         one, zero = [1, 1], [0, 0]
-        x = torch.cudnn_convolution_relu(img.contiguous(memory_format=torch.channels_last), w, b, [2, 2], [3, 3], one, 1)
+        x = torch.cudnn_convolution_relu(img.to(w.dtype).contiguous(memory_format=torch.channels_last), w, b, [2, 2], [3, 3], one, 1)
         x = F.max_pool2d(x, 3, 2, 1)
         for stride, (w1, b1), (w2, b2), ds in blocks:
             y = torch.cudnn_convolution_relu(x, w1, b1, [stride, stride], one, one, 1)
             if ds is not None:
                 x = F.conv2d(x, ds[0], ds[1], stride, 0)
             x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, one, one, one, 1)
-        return F.linear(x.mean((2, 3)), self.fc.weight, self.fc.bias)
+        return F.linear(x.float().mean((2, 3)), self.fc.weight.float(), self.fc.bias.float())   # pooling and fc in fp32
 
     def _forward_graphed(self, img: torch.Tensor) -> torch.Tensor:
         self._folded()   # (re)builds the folded weights and drops stale graphs when a parameter changed
-        key = (tuple(img.shape), img.device, torch.backends.cudnn.allow_tf32)
+        key = (tuple(img.shape), img.device, torch.backends.cudnn.allow_tf32, self.compute_dtype)
         g = self._graphs.get(key)
         if g is None:
             static_in = torch.empty_like(img, memory_format=torch.channels_last)
@@ -402,6 +412,8 @@ class TemporalMapUnet(nn.Module):
             h = C.c_void_p()
             _lib.check(lib.b2p_create(C.byref(cfg), idx, C.byref(h)), None, "b2p_create")
             _lib.check(lib.b2p_set_small_batch_max(h, self.small_batch_max), h, "b2p_set_small_batch_max")
+            if getattr(self, "_chain", None) is not None:
+                _lib.check(lib.b2p_set_chain(h, int(self._chain)), h, "b2p_set_chain")
             self._handles[idx] = h
         h = self._handles[idx]
         key = self._version_key()
@@ -432,6 +444,15 @@ class TemporalMapUnet(nn.Module):
         lib = _lib.load()
         for h in self._handles.values():
             _lib.check(lib.b2p_set_small_batch_max(h, self.small_batch_max), h, "b2p_set_small_batch_max")
+        return self
+
+    def set_chain(self, enabled: bool) -> "TemporalMapUnet":
+        """Developer switch: False runs every layer of the tensor-core precisions as its own launch instead of the row-owned
+        chain kernels (csrc/chain64.cu).  Same results up to fp32 summation order."""
+        self._chain = bool(enabled)
+        lib = _lib.load()
+        for h in self._handles.values():
+            _lib.check(lib.b2p_set_chain(h, int(self._chain)), h, "b2p_set_chain")
         return self
 
     def __del__(self):

@@ -123,6 +123,11 @@ int b2p_set_precision(b2p_handle h, int precision);
  * carla_agent; default B2P_SMALL_BATCH_DEFAULT).  0 disables that path. */
 #define B2P_SMALL_BATCH_DEFAULT 4
 int b2p_set_small_batch_max(b2p_handle h, int max_samples);
+/* Developer switch (default on; environment B2P_CHAIN=0 turns it off for new handles): in the tensor-core precisions the
+ * 64-channel layers at the full-resolution end of the U-Net run as row-owned CHAINS (one launch for downs.0, one for the
+ * tail of ups.<last> + final_conv, fused with the scheduler step between two evaluations of a plan without guidance).
+ * 0 = every layer is its own launch.  Same results up to fp32 summation order.                                     */
+int b2p_set_chain(b2p_handle h, int enabled);
 
 /* ---- camera frame -> encoder input: replaces T.ToTensor() + T.Normalize(mean, std) (interact.py:72-77, 170-172) for
  * uint8 frames already on the device.  frames [N,H,W,3] uint8 (4-byte aligned), out [N,H,W,3] fp32 (16-byte aligned; the
@@ -232,6 +237,25 @@ int b2p_set_noise_seed(b2p_handle h, uint64_t seed);
  * (n_per_step = B*H*D, device fp32, 16-byte aligned) — injecting it as `noise` reproduces the plan bit for bit.     */
 uint64_t b2p_last_noise_key(b2p_handle h);
 int b2p_philox_normal(uint64_t key, int32_t steps, int64_t n_per_step, float* out, void* stream);
+
+/* ---- plan post-processing -> control for a fleet of vehicles ------------------------------- */
+/* PID.* and CONTROL.* of the reference configuration (config.py:67-86) */
+typedef struct {
+  double turn_kp, turn_ki, turn_kd; int32_t turn_n;      /* PID.TURN_*  (window length <= 127)  */
+  double speed_kp, speed_ki, speed_kd; int32_t speed_n;  /* PID.SPEED_*                          */
+  double aim_dist, angle_thresh, dist_thresh, brake_speed, brake_ratio, clip_delta, max_throttle;  /* CONTROL.* */
+} b2p_control_config;
+/* bytes of device memory holding the PID windows of V vehicles (the per-vehicle deques of control/pid.py:10) */
+int64_t b2p_fleet_state_bytes(const b2p_control_config* c, int32_t V);
+/* zero the windows (a fresh Controller per vehicle, control/controller.py:8-21) */
+int b2p_fleet_reset(const b2p_control_config* c, void* state, int32_t V, void* stream);
+/* one control tick for every vehicle: replaces Controller.control_pid (control/controller.py:29-76) + PIDController.step
+ * (control/pid.py:16-28) called in a Python loop.  waypoints [V,N,2] (ego frame, metres), velocity [V], target [V,2] ->
+ * out [V,3] = (throttle, steer, brake in {0,1}); float64 arithmetic, the windows advance by one.                     */
+int b2p_fleet_control_pid(const b2p_control_config* c, void* state, const float* waypoints, int32_t N, const float* velocity,
+                          const float* target, float* out, int32_t V, void* stream);
+/* replaces post_process_control on traj[:, 0, -3:] (interact.py:218-229, 296-297): trajs [B,H,D] -> out [B,3] */
+int b2p_fleet_post_process(const float* trajs, float* out, int32_t B, int32_t H, int32_t D, void* stream);
 
 /* ---- introspection for tests / bench ---------------------------------------------------------------------- */
 /* number of kernel launches the last b2p_unet_forward / b2p_plan call enqueued (graph replay counts its nodes) */

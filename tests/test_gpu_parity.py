@@ -830,3 +830,108 @@ def test_plan_sharded_one_process_matches_the_single_device_plan():
     assert planner.plan_sharded(inp["x"], inp["feat"], target=tg, devices=[0, 0], out=pinned) is pinned and torch.equal(pinned, single)
     assert planner.plan_sharded(inp["x"][:0], inp["feat"][:0], devices=[0]).shape == (0, 16, 7)
     assert planner.shard_sizes(41, [0, 0, 0]) == [14, 14, 13]
+
+
+def test_chain_kernels_match_the_per_layer_path_and_the_oracle():
+    """csrc/chain64.cu (row-owned chains of the 64-channel layers; the scheduler step fused at the seam of two evaluations)
+    against the per-layer launches (model.set_chain(False)) and the oracle: forward at ragged batches in every guidance mode,
+    plans with every scheduler the seam fuses (DDIM, DDPM with injected and in-kernel noise, inpainting blend)."""
+    for mode in W.MODES:
+        model, sd = get_tc_model(mode, "bf16x3")
+        try:
+            for B in (5, 8, 21, 67):
+                inp = W.synth_inputs(B, 0, 500 + B)
+                t = torch.full((B,), 63, dtype=torch.long)
+                cond = inp["target"] if mode == "FREE_GUIDANCE" else None
+                kw = {"return_action_and_time_only": True} if mode == "CLASSIFIER_GUIDANCE" else {}
+                ref = U.unet_forward(sd, inp["x"], inp["feat"], t, cond, mode, **kw)
+                ref = ref[0] if isinstance(ref, tuple) else ref
+                outs = []
+                for ch in (True, False):
+                    model.set_chain(ch)
+                    o = model(inp["x"].to(DEV), inp["feat"].to(DEV), t.to(DEV), cond=None if cond is None else cond.to(DEV), **kw)
+                    outs.append((o[0] if isinstance(o, tuple) else o).cpu())
+                assert float((outs[0] - ref).abs().max()) <= 2e-4 and float((outs[1] - ref).abs().max()) <= 2e-4, (mode, B)
+                assert float((outs[0] - outs[1]).abs().max()) <= 1e-4, (mode, B)
+        finally:
+            model.set_chain(True)
+    model, sd = get_tc_model("NO_GUIDANCE", "bf16x3")
+    B = 19
+    for kind, T in (("guidance_ddim", 7), ("guidance_ddpm", 6), ("inpainting_ddim", 5), ("inpainting_ddpm", 4)):
+        inp = W.synth_inputs(B, T, 33)
+        inpaint, needs_noise = kind.startswith("inpainting"), kind != "guidance_ddim"
+        kw = dict(noise=inp["noise"] if needs_noise else None, target_traj=inp["target_traj"] if inpaint else None,
+                  target_mask=inp["mask"] if inpaint else None)
+        ref = OP.plan(sd, "NO_GUIDANCE", kind, inp["x"], inp["feat"], T, postprocess=False, **kw)
+        dkw = {k: (None if v is None else v.to(DEV)) for k, v in kw.items()}
+        try:
+            res = {}
+            for ch in (True, False):
+                model.set_chain(ch)
+                planner = P.DiffusionPlanner(model, make_sched(kind), _cfg("NO_GUIDANCE", T))
+                res[ch] = planner.plan(inp["x"].to(DEV), inp["feat"].to(DEV), postprocess=False, **dkw).cpu()
+                assert float((res[ch] - ref).abs().max()) <= 1e-3, (kind, ch)
+                if ch:
+                    assert planner.last_launch_count() < 31 * T + 8          # one seam launch instead of ~11 per step
+            assert float((res[True] - res[False]).abs().max()) <= 2e-4, kind
+        finally:
+            model.set_chain(True)
+    # in-kernel noise inside the seam launch == the stand-alone scheduler kernel's stream (same Philox counters)
+    planner = P.DiffusionPlanner(model, make_sched("guidance_ddpm"), _cfg("NO_GUIDANCE", 5))
+    x, f = inp["x"].to(DEV), inp["feat"].to(DEV)
+    planner.seed_noise(7)
+    a = planner.plan(x, f).clone()
+    import ctypes as C
+    from autonomous_driving_with_diffusion_model_b200 import _lib
+    key = _lib.load().b2p_last_noise_key(model._handle_for(torch.device(DEV)))
+    nz = torch.empty(5, B, 16, 7, device=DEV)
+    _lib.check(_lib.load().b2p_philox_normal(C.c_uint64(key), 5, B * 112, _lib.ptr(nz), model._stream()), None, "b2p_philox_normal")
+    assert torch.equal(planner.plan(x, f, noise=nz), a)
+
+
+def test_fleet_controller_matches_the_per_vehicle_host_controller():
+    """SURVEY.md 8f rank 2 (VERDICT r01 missing #5): the waypoint-following PID for a fleet — one thread per vehicle, windows on the
+    device — against one host ``Controller`` (pinned bit-for-bit to the reference, tests/golden/control_pid.npz) per vehicle
+    over 50 stateful ticks.  float64 on both sides; the only difference is libm's atan2."""
+    cfg = P.load_cfg()
+    V, N, ticks = 37, 16, 50
+    fleet = P.FleetController(cfg, V, DEV)
+    hosts = [P.Controller(cfg) for _ in range(V)]
+    g = torch.Generator().manual_seed(5)
+    for tick in range(ticks):
+        steps = torch.rand(V, N, 2, generator=g) * torch.tensor([0.6, 1.2]) + torch.tensor([-0.3, 0.05])
+        wp = steps.cumsum(1).float()
+        vel = (torch.rand(V, generator=g) * 6).float()
+        tgt = (torch.rand(V, 2, generator=g) * torch.tensor([8.0, 20.0]) + torch.tensor([-4.0, 1.0])).float()
+        got = fleet.control_pid(wp.to(DEV), vel.to(DEV), tgt.to(DEV)).cpu().double().numpy()
+        for v in range(V):
+            th, st, br = hosts[v].control_pid(wp[v].double(), vel[v:v + 1].double(), tgt[v].double())
+            want = np.array([float(th), float(st), float(br)])
+            assert np.allclose(got[v], want, rtol=1e-6, atol=1e-6), (tick, v, got[v], want)
+    fleet.reset()
+    fresh = P.FleetController(cfg, V, DEV)
+    assert torch.equal(fleet.control_pid(wp.to(DEV), vel.to(DEV), tgt.to(DEV)), fresh.control_pid(wp.to(DEV), vel.to(DEV), tgt.to(DEV)))
+    cases = np.array([[0.7, 0.1, 0.02], [0.2, -0.3, 0.4], [0.1, 0.5, 0.8], [0.0, 0.0, 0.04], [0.3, 0.2, 0.3], [0.6, -1.0, 0.55]])
+    trajs = torch.zeros(len(cases), 16, 7)
+    trajs[:, 0, -3:] = torch.from_numpy(cases).float()
+    want = np.stack([P.post_process_control(*c) for c in cases.astype(np.float32)])
+    assert np.array_equal(P.post_process_control_batch(trajs.to(DEV)).cpu().numpy(), want.astype(np.float32))
+
+
+def test_image_encoder_bf16_channels_last_bound(golden_dir):
+    """the encoder in bf16 channels-last (cuDNN, folded BN, fp32 pooling + fc).  Stated bound: feature
+    max-abs error <= 3e-2 of the feature's max-abs against the fp32 reference golden."""
+    g = np.load(os.path.join(golden_dir, "encoder_feature.npz"))
+    model, _ = get_model("NO_GUIDANCE")
+    img = W.synth_image(1, seed=2).to(DEV)
+    ref = torch.from_numpy(g["feat"])
+    try:
+        model.perception.set_precision("bf16")
+        with torch.no_grad():
+            feat = model.perception(img).float().cpu()
+        err = float((feat - ref).abs().max()) / float(ref.abs().max())
+        assert err <= 3e-2, err
+    finally:
+        model.perception.set_precision("fp32")
+    with torch.no_grad():
+        assert float((model.perception(img).cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
