@@ -48,42 +48,62 @@ struct TpSmem {
 };
 static_assert(sizeof(TpSmem) <= 110 * 1024, "two TrajPredict CTAs must fit one SM");
 
-// Y[s][n] = sum_k X[s][k] * Wt[k][n] + b[n].  Work item = (column n, group of RPG rows); the TP_NT threads cover
-// N x G items (G = 8 row groups for N = 64, 2 for N = 192 / 256).  The weight column is read straight from L2 (the 400 KB
-// of weights do not fit beside the 173 KB of saved activations), PF loads in flight per thread; k runs in ascending
-// order with one accumulator per output, so the result does not depend on the thread mapping.
+// Y[s][n] = sum_k X[s][k] * Wt[k][n] + b[n].  The weights are read straight from L2 (the 400 KB of weights do not fit beside the
+// saved activations), so what a linear layer costs is L2 round trips: K is therefore SPLIT ACROSS THE LANES of a warp (8 ways
+// for N = 64, 2 ways for N = 192 / 256) and every thread has ALL of its K / KS weights in flight at once (<= 32 loads) — one
+// or two round trips per layer instead of K / 16.  A warp owns 32 / KS output columns; thread (kq, n) accumulates the
+// granules g = j * KS + kq (4 consecutive k each: the KS lanes of a column read consecutive float4 of X, conflict-free), the
+// partial sums are combined by xor shuffles in a fixed order (deterministic), lanes kq == 0 write the result.
 template <bool ACCUM, int N>
 __device__ __forceinline__ void linear(const float* __restrict__ X, int ldx, const float* __restrict__ Wt, const float* __restrict__ b,
                                        float* __restrict__ Y, int ldy, int S, int K) {
-  constexpr int G = (TP_NT / N) >= 8 ? 8 : ((TP_NT / N) >= 2 ? 2 : 1);
-  constexpr int RPG = TP_MAXS / G;
-  constexpr int PF = 16;
-  const int tid = threadIdx.x;
-  if (tid >= N * G) return;
-  const int n = tid % N, row0 = (tid / N) * RPG;
-  float acc[RPG];
-  const float b0 = b ? __ldg(b + n) : 0.f;
+  constexpr int KS = N == 64 ? 8 : 2;
+  constexpr int NL = 32 / KS;                    // output columns per warp
+  constexpr int NW = N / NL;                     // warps with work (16, 12 or 16)
+  static_assert(NW <= TP_NT / 32 && N % NL == 0, "linear: tile mapping");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= NW) return;
+  const int kq = lane / NL, n = warp * NL + (lane % NL);
+  const int NG = K / (4 * KS);                   // granules per thread: <= 8 (K <= 256 with KS = 8, K = 64 with KS = 2)
+  float w[32];
 #pragma unroll
-  for (int r = 0; r < RPG; ++r) acc[r] = b0;
-  for (int k0 = 0; k0 < K; k0 += PF) {
-    float w[PF];
+  for (int j = 0; j < 8; ++j) {
+    if (j < NG) {
+      const float* wp = Wt + (size_t)((j * KS + kq) * 4) * N + n;
 #pragma unroll
-    for (int j = 0; j < PF; ++j) w[j] = __ldg(Wt + (size_t)(k0 + j) * N + n);
-#pragma unroll
-    for (int j4 = 0; j4 < PF; j4 += 4) {
-#pragma unroll
-      for (int r = 0; r < RPG; ++r) {
-        const float4 x = *reinterpret_cast<const float4*>(X + (row0 + r) * ldx + k0 + j4);
-        acc[r] = fmaf(x.x, w[j4], acc[r]);
-        acc[r] = fmaf(x.y, w[j4 + 1], acc[r]);
-        acc[r] = fmaf(x.z, w[j4 + 2], acc[r]);
-        acc[r] = fmaf(x.w, w[j4 + 3], acc[r]);
-      }
+      for (int e = 0; e < 4; ++e) w[j * 4 + e] = __ldg(wp + (size_t)e * N);
     }
   }
+  const float b0 = b ? __ldg(b + n) : 0.f;
+#pragma unroll 1
+  for (int r0 = 0; r0 < TP_MAXS; r0 += 8) {
+    float acc[8];
 #pragma unroll
-  for (int r = 0; r < RPG; ++r)
-    if (row0 + r < S) { if (ACCUM) Y[(row0 + r) * ldy + n] += acc[r]; else Y[(row0 + r) * ldy + n] = acc[r]; }
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < NG) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float4 x = *reinterpret_cast<const float4*>(X + (r0 + r) * ldx + (j * KS + kq) * 4);
+          acc[r] = fmaf(x.x, w[j * 4], acc[r]);
+          acc[r] = fmaf(x.y, w[j * 4 + 1], acc[r]);
+          acc[r] = fmaf(x.z, w[j * 4 + 2], acc[r]);
+          acc[r] = fmaf(x.w, w[j * 4 + 3], acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int o = NL; o < 32; o <<= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    }
+    if (kq == 0) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r0 + r < S) { if (ACCUM) Y[(r0 + r) * ldy + n] += acc[r] + b0; else Y[(r0 + r) * ldy + n] = acc[r] + b0; }
+    }
+  }
 }
 
 // y = LN(x) per row of 64; one warp per row.  Saves the normalised value and rstd when xh != null.
