@@ -708,6 +708,7 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
       ca.out_hi = hi_ptr(h->ops[4].out); ca.out_lo = lo_ptr(h->ops[4].out);
     }
     ca.B = rows; ca.H = h->H; ca.D = h->D; ca.wpack = h->d_chain;
+    ca.ns = 8;   // full 128-row tiles.  Half tiles (4 trajectories, twice the CTAs) measured SLOWER: a warp's TMEM lane quadrant is its SM sub-partition, so rows 64..127 idle two of the four schedulers
     ca.x = x; ca.x_period = x_period;
     ca.temb_rows = temb_rows; ca.temb_stride = h->temb_total;
     ca.temb2[0] = ttab_row; ca.temb2[1] = seam ? seam->next_ttab_row : nullptr;

@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
   float (*headp)[8][TC_M] = reinterpret_cast<float (*)[8][TC_M]>(smem + CH_OFF_HEADP);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b0 = blockIdx.x * CH_NS;
-  const int nb = a.B - b0 < CH_NS ? a.B - b0 : CH_NS;
+  const int b0 = blockIdx.x * a.ns;
+  const int nb = a.B - b0 < a.ns ? a.B - b0 : a.ns;
   const int HD = a.H * a.D;
 
   if (tid == 0) {
@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // rows that no trajectory of this CTA owns are never written: start from zero so the tensor core never reads stale bit patterns
+  for (int i = tid; i < 3 * CH_ACT_BYTES / 16; i += CH_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   // weights-only tables: independent of the preceding kernels
   if (a.xprojW)
     for (int i = tid; i < a.D * 64 + 64; i += CH_THREADS) sh->xw[i] = i < a.D * 64 ? __ldg(a.xprojW + i) : __ldg(a.xprojB + i - a.D * 64);
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       tc_fence_after();
       if (hf == 0 && a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 5] = clock64();
       if (hf == 1 && tid == 0 && oi + 1 < a.n_ops) issue_weights(oi + 1);   // the weight buffer is free: every MMA of this op has retired
+      if (((quad * 32) >> op.log2L) >= nb) continue;      // none of this warp's 32 rows belongs to a trajectory (half tiles, L = 8 ops, last CTA)
 #pragma unroll 1
       for (int o = 0; o < n_out; ++o) {
         float v[CH_EC];
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
 }
 
 int launch_chain64(const ChainArgs& a, int nsplit, cudaStream_t s) {
-  if (a.n_ops < 1 || a.n_ops > CH_MAXOPS || a.B <= 0 || a.H != 16 || a.D < 1 || a.D > 8 || (a.H * a.D) % 4 != 0) return B2P_ERR_INVALID_ARG;
+  if ((a.ns != 4 && a.ns != 8) || a.n_ops < 1 || a.n_ops > CH_MAXOPS || a.B <= 0 || a.H != 16 || a.D < 1 || a.D > 8 || (a.H * a.D) % 4 != 0) return B2P_ERR_INVALID_ARG;
   for (int i = 0; i < a.n_ops; ++i) {
     const ChainOp& op = a.ops[i];
     if (op.T < 1 || op.T > 5 || (op.L != 8 && op.L != 16) || op.in_buf > 2 || op.out_buf > 2 || op.ksteps < 1 || op.ksteps > 4) return B2P_ERR_INVALID_ARG;
@@ -438,7 +441,7 @@ int launch_chain64(const ChainArgs& a, int nsplit, cudaStream_t s) {
   const size_t smem = chain64_smem_bytes();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((a.B + CH_NS - 1) / CH_NS); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cfg.gridDim = dim3((a.B + a.ns - 1) / a.ns); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;

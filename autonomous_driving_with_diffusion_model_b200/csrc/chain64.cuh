@@ -9,7 +9,7 @@
 
 namespace b2p {
 
-constexpr int CH_NS = 8;          // trajectories owned by one CTA (8 x 16 positions = one 128-row MMA tile)
+constexpr int CH_NS = 8;          // most trajectories one CTA can own (8 x 16 positions = one 128-row MMA tile)
 constexpr int CH_MAXOPS = 12;
 
 enum { CH_CONV = 0, CH_DOWN = 1, CH_UP = 2 };                               // ChainOp.kind
@@ -37,6 +37,7 @@ struct ChainArgs {
   int n_ops;
   ChainOp ops[CH_MAXOPS];
   int B, H, D;                         // batch rows of this launch; horizon (16) and transition dim of x
+  int ns;                              // trajectories per CTA: 8 (full tiles) or 4 (half tiles; measured slower, see api.cu)
   const uint8_t* wpack;
   // first op reading its A operand from global memory (an evaluation's tail: the output of the last per-layer launch)
   const __nv_bfloat16* in_hi; const __nv_bfloat16* in_lo;   // [B, ops[0].L, 64]
