@@ -90,6 +90,7 @@ struct b2p_handle_s {
   bool chain_ok = false;
   bool chain_on = true;                // b2p_set_chain / B2P_CHAIN: off = every layer is its own launch
   unsigned long long* d_chain_trace = nullptr;   // developer stage clocks (B2P_CHAIN_TRACE=1)
+  size_t l2_window_bytes = 0;          // persisting-L2 window over d_pack16 (0: disabled, B2P_L2_WINDOW=0)
   int chain_u0 = -1;                   // index of the last up level's first conv (runs per-layer, with the residual projection as a sixth tap)
   std::vector<uint32_t> chain_woff;    // per op: byte offset of its pre-swizzled weight image in d_chain (0xffffffff: not a chain op)
   std::vector<uint8_t> chain_host;
@@ -667,6 +668,7 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
   };
   bool proj_done = false;   // residual projection of the raw trajectory already produced by the first conv launch
   // ---- row-owned chain kernel for the 64-channel layers (tensor-core precisions) ----
+  l2_weight_window() = L2Window{h->d_pack16, tc ? h->l2_window_bytes : 0};
   const bool chain = tc && h->chain_ok && h->chain_on;
   const int u0 = h->chain_u0;
   if (seam && !chain) return h->fail(B2P_ERR_STATE, "seam fusion needs the chain kernel");
@@ -999,6 +1001,21 @@ int b2p_finalize_weights(b2p_handle h) {
   if (h->d_pack16) { B2P_CUDA_TRY(cudaFree(h->d_pack16)); h->d_pack16 = nullptr; }
   B2P_CUDA_TRY(cudaMalloc((void**)&h->d_pack16, h->pack16_host.size() * sizeof(uint16_t) + 256));
   B2P_CUDA_TRY(cudaMemcpy(h->d_pack16, h->pack16_host.data(), h->pack16_host.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  {  // L2 residency of the tensor-core weight pack: reserve persisting lines and remember the window (applied per launch)
+    static int want = -1;
+    if (want < 0) { const char* e = getenv("B2P_L2_WINDOW"); want = e ? atoi(e) : 1; }
+    h->l2_window_bytes = 0;
+    if (want) {
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        size_t bytes = h->pack16_host.size() * sizeof(uint16_t);
+        if (bytes > (size_t)prop.accessPolicyMaxWindowSize) bytes = (size_t)prop.accessPolicyMaxWindowSize;
+        size_t lim = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess) h->l2_window_bytes = bytes;
+        else cudaGetLastError();
+      }
+    }
+  }
   if (!tp_offs.empty()) resolve_trajpred(h, tp_offs);
   // workspace offsets depend on the buffer table: force re-allocation
   if (h->d_ws) { B2P_CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; h->cap = 0; }

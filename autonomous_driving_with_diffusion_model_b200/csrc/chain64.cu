@@ -26,7 +26,8 @@
 
 namespace b2p {
 
-constexpr int CH_THREADS = 512;                      // 16 warps: 4 per TMEM lane quadrant (1024 threads x 8 columns measured no faster: the epilogue is throughput-bound)
+constexpr int CH_EPI_THREADS = 512;                  // 16 epilogue warps: 4 per TMEM lane quadrant
+constexpr int CH_THREADS = CH_EPI_THREADS;           // thread 32 also issues the MMAs (a 17th, MMA-only warp measured no faster: the epilogue is what an op costs)
 constexpr int CH_EC = 8;                             // columns per epilogue thread and column half: one GroupNorm group, one 16-byte chunk
 constexpr int CH_SL = 4;                             // column slices per half (4 warps per TMEM lane quadrant)
 constexpr int CH_HCOLS = 160;                        // TMEM column stride between the two column halves (5 taps x 32 channels)
@@ -37,7 +38,7 @@ constexpr int CH_OFF_W = 3 * CH_ACT_BYTES;            // weight image of the cur
 constexpr int CH_W_BYTES = 2 * 5 * CH_TAP_BYTES;
 constexpr int CH_OFF_HEADP = CH_OFF_W + CH_W_BYTES;   // head partial sums [slice][8][128 rows]
 constexpr int CH_OFF_MISC = CH_OFF_HEADP + CH_SL * 8 * 128 * 4;
-static_assert(CH_THREADS == 512, "the epilogue mapping assumes 16 warps: 4 lane quadrants x 4 column slices of 8 channels per half");
+static_assert(CH_EPI_THREADS == 512, "the epilogue mapping assumes 16 warps: 4 lane quadrants x 4 column slices of 8 channels per half");
 constexpr int CH_MAX_HD = 16 * 8;                     // horizon 16 x transition dim <= 8 (im2col K = 5 * D <= 64; one scheduler element per thread)
 
 struct __align__(16) ChainShared {
@@ -81,6 +82,49 @@ __device__ __noinline__ float sched_elem(const SchedK& k, int sample, int pos, i
   return step_one(k, sample, pos, col, m, 0.f, x, nz, tj, mk, x0);
 }
 __device__ __noinline__ float4 philox_group(unsigned long long seed, unsigned group, unsigned step) { return philox_normal4(seed, group, step); }
+
+// ---- epilogue building blocks with COMPILE-TIME tap counts / shifts / group sizes: the shuffles sit in straight-line code, so the
+// compiler emits plain SHFL instead of wrapping every one in a convergence barrier (the epilogue is instruction-issue bound) ----
+// v[c] += sum_i Y_blk(i)[l + d(i)] (zero outside the trajectory)
+template <int NT>
+__device__ __forceinline__ void tap_combine(float (&v)[CH_EC], uint32_t tbase, const int (&blk)[NT], const int (&sh)[NT], int l, int L, int lane) {
+  float y[NT][CH_EC];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) tmem_ld<CH_EC, false>(tbase + blk[i] * 32, y[i]);   // every tap block in flight at once: ONE exposed TMEM latency per half
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int d = sh[i];
+    if (d == 0) {
+#pragma unroll
+      for (int c = 0; c < CH_EC; ++c) v[c] += y[i][c];
+    } else {
+      const bool valid = (l + d >= 0) && (l + d < L);
+      const int src = (lane + d) & 31;
+#pragma unroll
+      for (int c = 0; c < CH_EC; ++c) { const float g = __shfl_sync(0xffffffffu, y[i][c], src); if (valid) v[c] += g; }
+    }
+  }
+}
+// GroupNorm(8) + Mish of the thread's 8 channels: a group = these channels x the L rows (adjacent lanes) of a trajectory
+template <int L>
+__device__ __forceinline__ void group_norm8_mish(float (&v)[CH_EC], const float* gamma, const float* beta) {
+  const float inv_n = 1.0f / (float)(8 * L);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s += v[c];
+#pragma unroll
+  for (int of = 1; of < L; of <<= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
+  const float mean = s * inv_n;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { const float dd = v[c] - mean; q = fmaf(dd, dd, q); }
+#pragma unroll
+  for (int of = 1; of < L; of <<= 1) q += __shfl_xor_sync(0xffffffffu, q, of);
+  const float rs = rsqrtf(q * inv_n + 1e-5f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = mish_fast((v[c] - mean) * rs * gamma[c] + beta[c]);
+}
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_constant__ ChainArgs a) {
@@ -230,7 +274,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
 
     // ------------- everything added after GroupNorm / Mish is fetched while the tensor core works -------------
     const int l = r & (L - 1), sidx = r >> op.log2L;
-    const bool row_ok = sidx < nb;
+    const bool epi = warp < CH_EPI_THREADS / 32;             // the extra warp only issues MMAs
+    const bool row_ok = epi && sidx < nb;
     const int b = b0 + sidx;
     float addv[2][CH_EC];
 #pragma unroll
@@ -280,55 +325,28 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       tc_fence_after();
       if (hf == 0 && a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 5] = clock64();
       if (hf == 1 && tid == 0 && oi + 1 < a.n_ops) issue_weights(oi + 1);   // the weight buffer is free: every MMA of this op has retired
-      if (((quad * 32) >> op.log2L) >= nb) continue;      // none of this warp's 32 rows belongs to a trajectory (half tiles, L = 8 ops, last CTA)
+      if (!epi || ((quad * 32) >> op.log2L) >= nb) continue;   // the MMA warp; or none of this warp's 32 rows belongs to a trajectory (L = 8 ops, last CTA)
 #pragma unroll 1
       for (int o = 0; o < n_out; ++o) {
         float v[CH_EC];
 #pragma unroll
         for (int c = 0; c < CH_EC; ++c) v[c] = sh->vec[oi & 1][0][ch0 + c];
         // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the trajectory) ----
-        // The TMEM load of tap i+1 is in flight while tap i is shifted and added (tcgen05.wait::ld waits for every outstanding load,
-        // so the next one is issued right after the wait).
-        const int nt = op.kind == CH_UP ? 2 : op.T;
-        const bool up = op.kind == CH_UP;
+        // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the trajectory); the op kind is uniform over the CTA ----
         const uint32_t tbase = taddr + hf * CH_HCOLS;
-        auto tap_blk = [&](int i) { return up ? (o == 0 ? (i == 0 ? 1 : 3) : (i == 0 ? 0 : 2)) : i; };   // convT: out[2m] = Y1[m] + Y3[m-1]; out[2m+1] = Y0[m+1] + Y2[m]
-        auto tap_shift = [&](int i) { return up ? (o == 0 ? (i == 0 ? 0 : -1) : (i == 0 ? 1 : 0)) : i - op.pad; };
-        float y[2][CH_EC];
-        tmem_ld<CH_EC, false>(tbase + tap_blk(0) * 32, y[0]);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          if (i < nt) {
-            tmem_ld_wait();
-            if (i + 1 < nt) tmem_ld<CH_EC, false>(tbase + tap_blk(i + 1) * 32, y[(i + 1) & 1]);
-            const int d = tap_shift(i);
-            if (d == 0) {
-#pragma unroll
-              for (int c = 0; c < CH_EC; ++c) v[c] += y[i & 1][c];
-            } else {
-              const bool valid = (l + d >= 0) && (l + d < L);
-              const int src = (lane + d) & 31;
-#pragma unroll
-              for (int c = 0; c < CH_EC; ++c) { const float g = __shfl_sync(0xffffffffu, y[i & 1][c], src); v[c] += valid ? g : 0.f; }
-            }
-          }
+        if (op.kind == CH_UP) {        // ConvTranspose1d(k4, s2, p1): out[2m] = Y1[m] + Y3[m-1];  out[2m+1] = Y0[m+1] + Y2[m]
+          if (o == 0) tap_combine<2>(v, tbase, {1, 3}, {0, -1}, l, L, lane);
+          else tap_combine<2>(v, tbase, {0, 2}, {1, 0}, l, L, lane);
+        } else if (op.T == 5) {
+          tap_combine<5>(v, tbase, {0, 1, 2, 3, 4}, {-2, -1, 0, 1, 2}, l, L, lane);
+        } else if (op.T == 3) {
+          tap_combine<3>(v, tbase, {0, 1, 2}, {-1, 0, 1}, l, L, lane);
+        } else {
+          tap_combine<1>(v, tbase, {0}, {0}, l, L, lane);
         }
-        if (op.gn) {   // GroupNorm(8): a group = the thread's 8 consecutive channels x the L rows (adjacent lanes) of a trajectory
-          const float inv_n = 1.0f / (float)(8 * L);
-          float s = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) s += v[c];
-#pragma unroll 1
-          for (int of = 1; of < L; of <<= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
-          const float mean = s * inv_n;
-          float q = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) { const float dd = v[c] - mean; q = fmaf(dd, dd, q); }
-#pragma unroll 1
-          for (int of = 1; of < L; of <<= 1) q += __shfl_xor_sync(0xffffffffu, q, of);
-          const float rs = rsqrtf(q * inv_n + 1e-5f);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) v[c] = mish_fast((v[c] - mean) * rs * sh->vec[oi & 1][1][ch0 + c] + sh->vec[oi & 1][2][ch0 + c]);
+        if (op.gn) {
+          if (L == 16) group_norm8_mish<16>(v, sh->vec[oi & 1][1] + ch0, sh->vec[oi & 1][2] + ch0);
+          else group_norm8_mish<8>(v, sh->vec[oi & 1][1] + ch0, sh->vec[oi & 1][2] + ch0);
         }
 #pragma unroll
         for (int c = 0; c < CH_EC; ++c) v[c] += addv[hf][c];
@@ -385,7 +403,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       const int hd = a.head_dim;
 #pragma unroll
       for (int d = 0; d < 8; ++d)
-        if (d < hd) headp[slice][d][r] = hsum[d];
+        if (d < hd && epi) headp[slice][d][r] = hsum[d];
       __syncthreads();
       if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 10] = clock64();
       for (int idx = tid; idx < TC_M * hd; idx += CH_THREADS) {   // one (row, d) sum at a time
@@ -442,10 +460,10 @@ int launch_chain64(const ChainArgs& a, int nsplit, cudaStream_t s) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((a.B + a.ns - 1) / a.ns); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = add_l2_window_attr(attr, 1);
   if (nsplit == 2) {
     B2P_CUDA_TRY(cudaFuncSetAttribute(chain64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return (int)cudaLaunchKernelEx(&cfg, chain64_kernel<2>, a);

@@ -73,6 +73,23 @@ inline void prefer_max_smem_carveout(const void* kernel) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+// L2 residency policy of the packed weights (north_star: "L2-resident weights"): the tensor-core launches carry an access-policy
+// window over the 16-bit weight pack (hit ratio 1, persisting; everything else streams), so activations of a large batch cannot
+// evict the weights between the T iterations.  Set per thread by the API layer before it enqueues an evaluation; bytes == 0: none.
+struct L2Window { const void* base; size_t bytes; };
+inline L2Window& l2_weight_window() { static thread_local L2Window w{nullptr, 0}; return w; }
+inline int add_l2_window_attr(cudaLaunchAttribute* attr, int n) {
+  const L2Window& w = l2_weight_window();
+  if (!w.bytes) return n;
+  attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+  attr[n].val.accessPolicyWindow.base_ptr = const_cast<void*>(w.base);
+  attr[n].val.accessPolicyWindow.num_bytes = w.bytes;
+  attr[n].val.accessPolicyWindow.hitRatio = 1.0f;
+  attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  return n + 1;
+}
+
 // launch `kernel` with the programmatic-stream-serialization attribute (the kernel must call pdl_wait() before it reads
 // anything produced by the preceding kernel)
 template <typename... KArgs, typename... Args>

@@ -631,14 +631,17 @@ static int launch_t(const TcMaps& maps, const TcArgs& a_in, dim3 grid, cudaStrea
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = a.cluster_l; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   static int pdl = -1;
   if (pdl < 0) { const char* e = getenv("B2P_TC_PDL"); pdl = e ? atoi(e) : 1; }
-  cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
+  int na = 1;
+  if (pdl) na = 2; else attr[1] = attr[0];
+  na = add_l2_window_attr(attr, na);
+  cfg.attrs = attr; cfg.numAttrs = na;
   return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<NSPLIT, TN>, maps, a);
 }
 
