@@ -27,7 +27,7 @@
 namespace b2p {
 
 constexpr int CH_EPI_THREADS = 512;                  // 16 epilogue warps: 4 per TMEM lane quadrant
-constexpr int CH_THREADS = CH_EPI_THREADS;           // thread 32 also issues the MMAs (a 17th, MMA-only warp measured no faster: the epilogue is what an op costs)
+constexpr int CH_THREADS = CH_EPI_THREADS;           // warp 1 also issues the MMAs (a 17th, MMA-only warp measured no faster: the epilogue is what an op costs)
 constexpr int CH_EC = 8;                             // columns per epilogue thread and column half: one GroupNorm group, one 16-byte chunk
 constexpr int CH_SL = 4;                             // column slices per half (4 warps per TMEM lane quadrant)
 constexpr int CH_HCOLS = 160;                        // TMEM column stride between the two column halves (5 taps x 32 channels)
@@ -240,11 +240,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     __syncthreads();
     if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 1] = clock64();
 
-    if (tid == 32) {
-      // =============================== MMA issue (one thread) ===============================
+    if (warp == 1) {
+      // =============================== MMA issue (warp 1: warp-uniform loop, one elected lane issues) ===============================
       mbar_wait(&sh->wbar, wpar);
       tc_fence_after();
-      if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 2] = clock64();
+      if (a.trace && blockIdx.x == 0 && lane == 0) a.trace[oi * 16 + 2] = clock64();
       const uint32_t sa = smem_u32(smem + (op.in_buf < 0 ? 0 : op.in_buf) * CH_ACT_BYTES);
       const uint32_t sb = smem_u32(wbuf);
       const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + CH_HALF);
@@ -259,15 +259,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
 #pragma unroll 1
         for (int k = 0; k < op.ksteps; ++k) {
           const uint64_t ko = (uint64_t)(k * TC_UMMA_K * 2 / 16);  // +32 B per K step, in 16-byte units
-          umma(dcol, a_hi + ko, b_hi + ko, idn, k == 0 ? 0u : 1u);
+          umma_w(dcol, a_hi + ko, b_hi + ko, idn, k == 0 ? 0u : 1u);
           if (NSPLIT == 2) {
-            umma(dcol, a_lo + ko, b_hi + ko, idn, 1u);
-            umma(dcol, a_hi + ko, b_lo + ko, idn, 1u);
+            umma_w(dcol, a_lo + ko, b_hi + ko, idn, 1u);
+            umma_w(dcol, a_hi + ko, b_lo + ko, idn, 1u);
           }
         }
-        umma_commit(&sh->mma_bar[hf]);
+        umma_commit_w(&sh->mma_bar[hf]);
       }
-      if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 3] = clock64();
+      if (a.trace && blockIdx.x == 0 && lane == 0) a.trace[oi * 16 + 3] = clock64();
     }
     wpar ^= 1;
     __syncwarp();

@@ -272,8 +272,8 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       issue(j, s, true, true);
       if (++s == stages) { s = 0; par ^= 1; }
     }
-  } else if (threadIdx.x == 32) {
-    // =============================== MMA issuer (one thread) ===============================
+  } else if (warp == 1) {
+    // =============================== MMA issuer (warp 1: warp-uniform loop, one elected lane issues) ===============================
     // All taps of a chunk are adjacent in shared memory ([T*TN rows] x 128 B, K-major), so ONE tcgen05.mma with
     // N = T*TN (<= 256; a fifth 64-wide tap takes a second instruction) covers them.  Descriptors are built once per
     // stage and advanced by adding to the address field.
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     for (int it = 0, s = 0, par = 0; it < n_local; ++it, s = (s + 1 == stages ? 0 : s + 1), par ^= (s == 0)) {   // s = it % stages, par = (it / stages) & 1
       mbar_wait(&sh->full[s], par);
       tc_fence_after();
-      if (it == 0) TC_T(2);
+      if (it == 0 && lane == 0) TC_T(2);
       const uint32_t sa = smem_u32(smem + s * stage_bytes);
       const uint32_t sb = sa + NSPLIT * A_BYTES;
       const bool res_phase = it >= main_iters;
@@ -299,21 +299,21 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
           if (concat) {
             // an M = 128 MMA fetches its operands from shared memory at ~64 B/clk: with N = 48 the 4 KB A slice dominates, so
             // two instructions that read A_hi once and A_lo once beat three that read A_hi twice
-            umma(tmem_base, a_hi + ko, b_hi + ko, idescC, acc);          // blocks [0,T): hi*hi, blocks [T,2T): hi*lo
-            umma(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);           // blocks [0,T) += lo*hi
+            umma_w(tmem_base, a_hi + ko, b_hi + ko, idescC, acc);          // blocks [0,T): hi*hi, blocks [T,2T): hi*lo
+            umma_w(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);           // blocks [0,T) += lo*hi
             continue;
           }
-          umma(tmem_base, a_hi + ko, b_hi + ko, idescA, acc);
+          umma_w(tmem_base, a_hi + ko, b_hi + ko, idescA, acc);
           if (NSPLIT == 2) {
-            umma(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);
-            umma(tmem_base, a_hi + ko, b_lo + ko, idescA, 1u);
+            umma_w(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);
+            umma_w(tmem_base, a_hi + ko, b_lo + ko, idescA, 1u);
           }
           if (nA < T) {
             const uint64_t t4 = (uint64_t)(nA * BT_BYTES / 16);
-            umma(tmem_base + nA * TN, a_hi + ko, b_hi + t4 + ko, idescR, acc);
+            umma_w(tmem_base + nA * TN, a_hi + ko, b_hi + t4 + ko, idescR, acc);
             if (NSPLIT == 2) {
-              umma(tmem_base + nA * TN, a_lo + ko, b_hi + t4 + ko, idescR, 1u);
-              umma(tmem_base + nA * TN, a_hi + ko, b_lo + t4 + ko, idescR, 1u);
+              umma_w(tmem_base + nA * TN, a_lo + ko, b_hi + t4 + ko, idescR, 1u);
+              umma_w(tmem_base + nA * TN, a_hi + ko, b_lo + t4 + ko, idescR, 1u);
             }
           }
         }
@@ -322,17 +322,17 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
 #pragma unroll
         for (int k = 0; k < TC_K / TC_UMMA_K; ++k) {
           const uint64_t ko = (uint64_t)(k * TC_UMMA_K * 2 / 16);
-          umma(d, a_hi + ko, b_hi + ko, idescB, (first && k == 0) ? 0u : 1u);
+          umma_w(d, a_hi + ko, b_hi + ko, idescB, (first && k == 0) ? 0u : 1u);
           if (NSPLIT == 2) {
-            umma(d, a_lo + ko, b_hi + ko, idescB, 1u);
-            umma(d, a_hi + ko, b_lo + ko, idescB, 1u);
+            umma_w(d, a_lo + ko, b_hi + ko, idescB, 1u);
+            umma_w(d, a_hi + ko, b_lo + ko, idescB, 1u);
           }
         }
       }
-      if (CL > a.cluster_n) umma_commit_mc(&sh->empty[s], cmask); else umma_commit(&sh->empty[s]);   // the stage is free in a CTA once ALL cluster consumers released it
+      if (CL > a.cluster_n) umma_commit_mc_w(&sh->empty[s], cmask); else umma_commit_w(&sh->empty[s]);   // the stage is free in a CTA once ALL cluster consumers released it
     }
-    umma_commit(&sh->tmem_full);
-    TC_T(3);
+    umma_commit_w(&sh->tmem_full);
+    if (lane == 0) TC_T(3);
   }
   __syncwarp();
   griddep_wait();                 // everything below may read the previous kernels' outputs (residuals)

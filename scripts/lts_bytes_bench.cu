@@ -1,0 +1,66 @@
+// Developer micro-benchmark: how does ncu's lts__t_bytes count an L2-resident 64 MB weight stream?  (the batch-1
+// GEMV path showed 126.5 MB of lts__t_bytes per evaluation against 64.1 MB of weights.)  Three readers of the same buffer:
+//   ldg16   : ld.global.nc.v4 (16 B per thread, coalesced)
+//   cpasync : cp.async.cg.shared.global 16 B per thread (what conv_gemv.cu uses), coalesced
+//   bulk    : cp.async.bulk 4 KB per CTA iteration (what chain64.cu uses)
+// Run under:  ncu --metrics lts__t_bytes.sum,lts__t_sectors.sum,lts__t_sectors_srcunit_tex.sum,lts__t_sectors_op_read.sum,dram__bytes_read.sum --cache-control none
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__global__ void ldg16(const uint4* __restrict__ p, size_t n, uint4* sink) {
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 v = __ldg(p + i);
+    acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+  }
+  if (acc.x == 0x12345678u) *sink = acc;
+}
+
+__global__ void cpasync(const uint4* __restrict__ p, size_t n, uint4* sink) {
+  __shared__ uint4 buf[256];
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(&buf[threadIdx.x]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(p + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    uint4 v = buf[threadIdx.x];
+    acc.x ^= v.x; acc.y ^= v.y;
+  }
+  if (acc.x == 0x12345678u) *sink = acc;
+}
+
+__global__ void bulk(const uint8_t* __restrict__ p, size_t bytes, uint4* sink) {
+  __shared__ __align__(128) uint8_t buf[4096];
+  __shared__ uint64_t bar;
+  unsigned sb = (unsigned)__cvta_generic_to_shared(&bar), sd = (unsigned)__cvta_generic_to_shared(buf);
+  if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sb)); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  __syncthreads();
+  unsigned par = 0;
+  for (size_t off = (size_t)blockIdx.x * 4096; off < bytes; off += (size_t)gridDim.x * 4096) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb), "r"(4096u) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sd), "l"(p + off), "r"(4096u), "r"(sb) : "memory");
+    }
+    asm volatile("{\n.reg .pred p;\nW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D;\nbra W;\nD:\n}" ::"r"(sb), "r"(par) : "memory");
+    par ^= 1;
+    __syncthreads();
+  }
+  if (buf[threadIdx.x] == 0x5a && threadIdx.x == 999) *sink = make_uint4(1, 2, 3, 4);
+}
+
+int main() {
+  const size_t bytes = 64ull << 20;
+  uint8_t* p; uint4* sink;
+  cudaMalloc(&p, bytes); cudaMalloc(&sink, 64);
+  cudaMemset(p, 1, bytes);
+  for (int rep = 0; rep < 2; ++rep) {   // rep 0 warms L2 (126 MB), rep 1 is the one to read in the ncu log
+    ldg16<<<148 * 4, 256>>>((const uint4*)p, bytes / 16, sink);
+    cpasync<<<148 * 4, 256>>>((const uint4*)p, bytes / 16, sink);
+    bulk<<<148 * 2, 128>>>(p, bytes, sink);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  printf("done: %s, buffer %zu MB\n", cudaGetErrorString(e), bytes >> 20);
+  return e != cudaSuccess;
+}
