@@ -608,11 +608,11 @@ int tc_make_weight_map(CUtensorMap* m, const void* base, int taps, int Cout, int
 template <int NSPLIT, int TN>
 static int launch_t(const TcMaps& maps, const TcArgs& a_in, dim3 grid, cudaStream_t s) {
   TcArgs a = a_in;
-  // B2P_TC_BIGRING=1 (experiment, off): give a narrow-tile layer that fits the chip with one CTA per SM the deep ring.
-  // Measured no faster — the main loop of those layers is paced by the MMAs' shared-memory operand reads, not by the
-  // bytes in flight — and slightly slower overall because the next layer's CTAs can no longer co-reside.
+  // B2P_TC_BIGRING (default 1): a narrow-tile layer that fits the chip with one CTA per SM gets the deep (208 KB, 4-stage) ring.
+  // Round 1 measured no gain (the main loop was paced by the MMA issue loop); with the warp-uniform issue loop the TMA latency of
+  // the 2-stage ring shows, and the deep ring is worth 1.5 % per iteration at B = 256 (0: 106 KB ring, two CTAs per SM).
   static int bigring = -1;
-  if (bigring < 0) { const char* e = getenv("B2P_TC_BIGRING"); bigring = e ? atoi(e) : 0; }
+  if (bigring < 0) { const char* e = getenv("B2P_TC_BIGRING"); bigring = e ? atoi(e) : 1; }
   static int concat = -1;
   if (concat < 0) { const char* e = getenv("B2P_TC_CONCAT"); concat = e ? atoi(e) : 1; }
   // worth it when the A_hi re-reads it saves (64 cycles per K step, 4 K steps per 64-channel chunk) outweigh the extra TMEM
