@@ -181,7 +181,7 @@ __device__ __forceinline__ void gv_dot(const float* __restrict__ wcol, int wstri
   gv_reduce<CW * RT>(acc, lane, 16);
 }
 
-__host__ __device__ inline int gv_pad4(int n) { return (n + 3) & ~3; }
+__host__ __device__ inline int gv_pad4(int n) { return (n + 7) & ~7; }   // floats; name kept: regions are padded to 32 bytes (see the carve-up)
 
 // NC = channels per CTA (power of two <= 8), cls = CTAs per cluster (= GroupNorm group size / NC, or 1)
 // CW = output channels per warp (2 when the CTA owns >= 2 channels: activation reads from shared memory are shared)
@@ -206,8 +206,10 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
   const int lng = lnc - (CW == 2 ? 1 : 0);            // log2(channel groups of CW channels)
   const int ns = GV_NW >> lng;                        // K slices per channel group
   const bool vecW = (Cin & 3) == 0, vecR = (RCin & 3) == 0;
-  // dynamic shared memory carve-up (every region 16-byte aligned)
-  float* Wsm = dyn;                                   // [NC][Keff]
+  // dynamic shared memory carve-up.  Every region is 32-BYTE aligned: a 16-byte cp.async whose shared-memory destination is 16 but
+  // not 32 bytes aligned makes L2 return every 32-byte sector TWICE (measured: scripts/lts_bytes_bench.cu, profiles/r02_lts_bytes_bench.csv;
+  // the dynamic block starts after the 3024-byte static block, which is what doubled lts__t_bytes of this path in round 1).
+  float* Wsm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dyn) + 127) & ~(uintptr_t)127);   // [NC][Keff]
   float* RWsm = Wsm + gv_pad4(NC * Keff);             // [NC][RCin]
   float* X = RWsm + gv_pad4(NC * RCin);               // [Lin + 1][Cin], last row zero (padding taps read it)
   float* RX = X + gv_pad4((Lin + 1) * Cin);           // [L][RCin]
@@ -352,7 +354,7 @@ static int gv_pick_nc(const ConvArgs& a) {
 
 static size_t gv_smem_floats(const ConvArgs& a, int nc) {
   const int Cin = a.C0 + a.C1, RCin = a.RC0 + a.RC1, Keff = (a.jmax - a.jmin + 1) * Cin;
-  return (size_t)gv_pad4(nc * Keff) + gv_pad4(nc * RCin) + gv_pad4((a.Lin + 1) * Cin) + gv_pad4(a.Lout * RCin);
+  return (size_t)gv_pad4(nc * Keff) + gv_pad4(nc * RCin) + gv_pad4((a.Lin + 1) * Cin) + gv_pad4(a.Lout * RCin) + 32 /* 128-byte base alignment */;
 }
 
 template <int RT, int CW>

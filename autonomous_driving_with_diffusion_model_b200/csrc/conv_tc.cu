@@ -652,6 +652,18 @@ int tc_pick_tile_n(int nrows, int Cout, bool has_head) {
   if (forced < 0) { const char* e = getenv("B2P_TC_TN"); forced = e ? atoi(e) : 0; }
   if (has_head) return 64;
   if (forced == 16 || forced == 32 || forced == 64) return forced;
+  {  // developer experiment: B2P_TC_TN_MAP="<Cout>:<TN>,..." overrides the width for layers with that many output channels
+    static int map_c[8], map_t[8], nmap = -1;
+    if (nmap < 0) {
+      nmap = 0;
+      const char* e = getenv("B2P_TC_TN_MAP");
+      while (e && *e && nmap < 8) {
+        int c = 0, t = 0, used = 0;
+        if (sscanf(e, "%d:%d%n", &c, &t, &used) == 2) { map_c[nmap] = c; map_t[nmap] = t; ++nmap; e += used; if (*e == ',') ++e; } else break;
+      }
+    }
+    for (int i = 0; i < nmap; ++i) if (map_c[i] == Cout && (map_t[i] == 16 || map_t[i] == 32 || map_t[i] == 64)) return map_t[i];
+  }
   const int mt = (nrows + TC_M - 1) / TC_M;
   int tn = 64;
   while (tn > 16 && mt * (Cout / (tn / 2)) <= 148) tn /= 2;

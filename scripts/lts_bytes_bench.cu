@@ -50,6 +50,28 @@ __global__ void bulk(const uint8_t* __restrict__ p, size_t bytes, uint4* sink) {
   if (buf[threadIdx.x] == 0x5a && threadIdx.x == 999) *sink = make_uint4(1, 2, 3, 4);
 }
 
+// the access pattern of conv_gemv.cu's weight fetch: 64 CTAs x 512 threads, each CTA copies 8 channel rows of 1536 floats (the 3
+// reachable taps of a [C_out][5 taps][512] K-major layer) with 16-byte cp.async.cg, threads 0..383 one granule per row
+__global__ void __launch_bounds__(512) gvlike(const float* __restrict__ w, uint4* sink, int variant) {
+  extern __shared__ __align__(16) float dyn[];
+  const int tid = threadIdx.x, col0 = blockIdx.x * 8;
+  for (int c = 0; c < 8; ++c) {
+    const float* src = w + ((size_t)(col0 + c) * 5 + 1) * 512;
+    float* dst = dyn + c * 1536 + (variant == 2 ? 4 : 0);   // variant 2: destination 16 (mod 32) bytes, as after conv_gemv's 3024-byte static block
+    if (variant == 0 || variant == 2) {
+      for (int i = tid * 4; i < 1536; i += 512 * 4) {
+        unsigned s = (unsigned)__cvta_generic_to_shared(dst + i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(src + i) : "memory");
+      }
+    } else {
+      for (int i = tid * 4; i < 1536; i += 512 * 4) *reinterpret_cast<float4*>(dst + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  if (dyn[tid] == 123.f && tid == 999) *sink = make_uint4(1, 2, 3, 4);
+}
+
 int main() {
   const size_t bytes = 64ull << 20;
   uint8_t* p; uint4* sink;
@@ -59,6 +81,22 @@ int main() {
     ldg16<<<148 * 4, 256>>>((const uint4*)p, bytes / 16, sink);
     cpasync<<<148 * 4, 256>>>((const uint4*)p, bytes / 16, sink);
     bulk<<<148 * 2, 128>>>(p, bytes, sink);
+  }
+  cudaFuncSetAttribute(gvlike, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1536 * 4 + 64);
+  for (int rep = 0; rep < 2; ++rep)
+    for (int v = 0; v < 2; ++v) gvlike<<<64, 512, 8 * 1536 * 4>>>((const float*)p, sink, v);   // 512 channels: reads 3.1 MB of a 5.2 MB layer
+  // the launch configuration of conv_gemv.cu: maximum shared-memory carve-out, then + clusters of 8 CTAs, then + programmatic serialization
+  cudaFuncSetAttribute(gvlike, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  gvlike<<<64, 512, 8 * 1536 * 4>>>((const float*)p, sink, 0);
+  gvlike<<<64, 512, 8 * 1536 * 4 + 64>>>((const float*)p, sink, 2);
+  for (int na = 1; na <= 2; ++na) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(64); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 8 * 1536 * 4;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = na;
+    cudaLaunchKernelEx(&cfg, gvlike, (const float*)p, sink, 0);
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("done: %s, buffer %zu MB\n", cudaGetErrorString(e), bytes >> 20);
