@@ -87,7 +87,7 @@ template <int TN> struct SmemPlan {
   static constexpr int cx_off = ring;                                      // cluster exchange buffer (TN < 64), 4 KB
   static constexpr int shared_off = TN == 64 ? ring : ring + 4 * 1024;     // TcShared
   static constexpr int total = shared_off + 1024 /*alignment slack*/ + (int)sizeof(TcShared);
-  static constexpr int min_ctas = TN == 16 ? 2 : 1;
+  static constexpr int min_ctas = 1;   // TN == 16 launches are one wave of <= 148 CTAs with the deep ring (one CTA per SM): the full register file per CTA
 };
 constexpr int EPI_XCHG_BYTES = 2 * TC_M * 4 * 4;
 struct EpiScratch {
@@ -106,7 +106,12 @@ struct EpiScratch {
 // Called by ALL threads of the CTA (contains __syncthreads / a cluster barrier).
 template <int CG, int TN>
 __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int row, int slice, int crank, int cbase, const EpiScratch& es,
-                                                const float* gamma, const float* beta) {
+                                                const float* gamma, const float* beta, int tr = -1) {
+#ifdef B2P_TC_TRACE
+#define GN_T(k) do { if (tr >= 0 && threadIdx.x == 64) tc_trace[tr * 16 + (k)] = clock64(); } while (0)
+#else
+#define GN_T(k)
+#endif
   constexpr int EC = TN / 4;
   constexpr int W = CG < EC ? CG : EC;              // channels of one group inside this thread
   constexpr int NG = EC / W;                        // groups per thread
@@ -128,10 +133,13 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
     for (int o = 1; o < L; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     m2[g] = q;
   }
+  GN_T(11);
   if (SL > 1) {                                      // merge the slices of this CTA (NG == 1 here)
     es.xchg[0][slice][row] = mean[0];
     es.xchg[1][slice][row] = m2[0];
-    __syncthreads();
+    // only the four warps that own these 32 rows (same TMEM lane quadrant, the four column slices) exchange: a 128-thread named
+    // barrier per quadrant instead of a CTA-wide one, so a quadrant does not wait for the slowest warp of the other three
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + (row >> 5)) : "memory");
     const int base = slice & ~(SL - 1);
     float ms = 0.f, qs = 0.f;
 #pragma unroll
@@ -141,6 +149,7 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
     for (int j = 0; j < SL; ++j) { float d = es.xchg[0][base + j][row] - mu; qs += es.xchg[1][base + j][row] + (float)(W * L) * d * d; }
     mean[0] = mu; m2[0] = qs;
   }
+  GN_T(12);
   if (CN > 1) {                                      // merge the CTAs of the cluster sub-group
     // every CTA pushes its per-row (mean, M2) into all CN CTAs with asynchronous stores that signal the receiver's
     // mbarrier; nobody waits for a cluster-wide barrier, each CTA only waits until ITS CN x 128 pairs have landed
@@ -158,6 +167,7 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
     for (int c = 0; c < CN; ++c) { float d = es.cx[c][row].x - mu; qs += es.cx[c][row].y + (float)(WC * L) * d * d; }
     mean[0] = mu; m2[0] = qs;
   }
+  GN_T(13);
   const float inv_n = 1.0f / (float)(CG * L);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
@@ -409,7 +419,36 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       for (int c = 0; c < EC; ++c) v[c] = sh->bias[col0 + c];
       // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the sample) ----
       if (n_local > 0) {
-        if (EC <= 8) {
+        if (EC == 4) {
+          // narrowest tiles: EVERY tap block (and its hi*lo twin when the products are concatenated) is loaded before ONE wait — a
+          // TMEM load round trip costs 700-900 cycles with 16 warps reading at once (profiles/r02_tc_stage_trace_b256.txt) — and the
+          // twins are added before the row shift (the shift is linear), which halves the shuffles.  Straight-line code: taps beyond
+          // nt contribute zero, so no shuffle sits behind a data-dependent branch.
+          const bool twin = NSPLIT == 2 && a.concat;
+          const int nt = a.nt[o];
+          float y[5][EC], y2[5][EC];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            if (i < nt) {
+              tmem_ld<EC, false>(taddr + a.tap_blk[o][i] * TN, y[i]);
+              if (twin) tmem_ld<EC, false>(taddr + (T + a.tap_blk[o][i]) * TN, y2[i]);
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const bool on = i < nt;
+            const int d = on ? a.tap_shift[o][i] : 0;
+            const bool valid = on && (l + d >= 0) && (l + d < L);
+            const int src = (lane + d) & 31;
+#pragma unroll
+            for (int c = 0; c < EC; ++c) {
+              const float t = on ? (twin ? y[i][c] + y2[i][c] : y[i][c]) : 0.f;
+              const float g = __shfl_sync(0xffffffffu, t, src);
+              v[c] += valid ? g : 0.f;
+            }
+          }
+        } else if (EC <= 8) {
           // narrow tiles: issue the TMEM loads of all taps back to back and wait once
           float y[5][EC];
 #pragma unroll
@@ -459,12 +498,18 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
           }
         }
       }
+#ifdef B2P_TC_TRACE
+      const int gtr = (blockIdx.x == 0 && blockIdx.y == 0) ? (int)((a.dbg >> 8) & 8191) : -1;
+      if (gtr >= 0 && threadIdx.x == 64) tc_trace[gtr * 16 + 10] = clock64();
+#else
+      const int gtr = -1;
+#endif
       if (a.gn_gamma) {
         switch (a.cg) {
-          case 8: group_norm_mish<8, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0); break;
-          case 16: group_norm_mish<16, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0); break;
-          case 32: group_norm_mish<32, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0); break;
-          default: group_norm_mish<64, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0); break;
+          case 8: group_norm_mish<8, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
+          case 16: group_norm_mish<16, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
+          case 32: group_norm_mish<32, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
+          default: group_norm_mish<64, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
         }
       }
       const bool ok = row_ok && (l & (a.out_ldiv - 1)) == 0;   // out_ldiv is 1 or 2 (stride of the conv): masks and shifts, not divisions

@@ -47,6 +47,14 @@ for i, r in enumerate(rows):
     tails.append(tail); rels.append(rel)
     print(f"{i:4d}   " + "  ".join(f"{v:16d}" for v in d) + f"   {nxt:8d} {tail:8d} {rel:8d}")
 print("sum    " + "  ".join(f"{int(v):16d}" for v in tot))
+print("epilogue detail (cycles): layer  tap combine (accumulators ready -> GroupNorm entry) | own-part statistics | slice exchange | cluster exchange | normalise + Mish")
+ed = np.zeros(5)
+for i, r in enumerate(rows):
+    if r[10] and r[13]:
+        d = [r[10] - r[4], r[11] - r[10], r[12] - r[11], r[13] - r[12], r[5] - r[13]]
+        ed += np.array(d)
+        print(f"{i:4d}   " + "  ".join(f"{v:8d}" for v in d))
+print("sum    " + "  ".join(f"{int(v):8d}" for v in ed) + "   us: " + "  ".join(f"{v / 1965:.1f}" for v in ed))
 hr = rows[-1]
 print(f"head layer (TN=64): GroupNorm done {hr[5]-hr[4]}, end {hr[6]-hr[4]} cycles after the accumulators were ready")
 print(f"tail total {sum(tails) / 1e3:.1f} us, release total {sum(rels) / 1e3:.1f} us (includes non-tcgen05 kernels between steps)")
