@@ -420,8 +420,24 @@ def mode_report(P, W, dev, B: int, precision: str):
             torch.cuda.synchronize()
             out[f"with_encoder_{scenes}_scenes"] = {"traj_per_s": B / (e1.elapsed_time(e2) / 3 * 1e-3), "ms_per_plan": e1.elapsed_time(e2) / 3,
                                                     "encoder_ms": e0.elapsed_time(e1) / 3, "batch": B, "image": "3x256x900 fp32 per scene",
-                                                    "encoder": f"ResNet-34 on torch/cuDNN ({getattr(m.perception, 'compute_dtype', 'fp32')}, channels-last, folded BN; "
-                                                               "library code, SURVEY 8f rank 1), one pass per scene, hoisted"}
+                                                    "encoder": "ResNet-34 on torch/cuDNN (fp32/TF32, channels-last, folded BN; library code, SURVEY 8f rank 1), "
+                                                               "one pass per scene, hoisted"}
+            # the same with the encoder in bf16 channels-last (stated bound: feature max-abs error <= 3e-2 of its max-abs vs the fp32 golden)
+            m.perception.set_precision("bf16")
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                enc_only()
+            e1.record()
+            for _ in range(3):
+                run()
+            e2.record()
+            torch.cuda.synchronize()
+            out[f"with_encoder_{scenes}_scenes"].update(encoder_ms_bf16=e0.elapsed_time(e1) / 3, ms_per_plan_bf16_encoder=e1.elapsed_time(e2) / 3,
+                                                        traj_per_s_bf16_encoder=B / (e1.elapsed_time(e2) / 3 * 1e-3))
+            m.perception.set_precision("fp32")
             del img
         # closed-loop tick at batch 1: a NEW camera frame every tick (interact.py:170-176 -> generate_traj), encoder included
         frames = [torch.randn(1, 3, 256, 900, device=dev) for _ in range(4)]
