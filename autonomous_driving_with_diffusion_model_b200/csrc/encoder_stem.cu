@@ -1,0 +1,261 @@
+// Image-encoder stem on the tensor cores (the caller in front of the sampling loop):
+//   conv1 7x7 / stride 2 / pad 3 (3 -> 64) + folded BatchNorm + ReLU        modeling/resnet.py:193-197, 279-281   (stem_conv_kernel)
+//   MaxPool2d(3, stride 2, pad 1)                                             modeling/resnet.py:198, 282           (maxpool_nhwc_kernel)
+// for the encoder's bf16 mode.  cuDNN runs this layer (C_in = 3) as an Ampere-generation indexed implicit GEMM and torch's NHWC
+// max-pool is 10x off the memory roofline: together 11.8 of the 22.3 ms the bf16 encoder spends on 256 camera frames
+// (profiles/r02_encoder_profile.txt).  Here the convolution is a [pixels x 147] x [147 x 64] GEMM on tcgen05:
+//   * a CTA owns tiles of 128 consecutive output pixels.  Its 256 threads gather the 7 x 7 x 3 input window of their pixel straight
+//     from the fp32 image (any strides: NCHW or channels-last), round to bf16 and store it as the K-major, 128-byte-swizzled A
+//     operand (K order = (kernel row, kernel column, channel), K padded 147 -> 160 = 10 instructions of K = 16);
+//   * the folded weights arrive once per CTA as a pre-swizzled 24 KB image (bulk copy), B operand of every tile;
+//   * accumulators in TMEM (64 fp32 columns); the epilogue adds the folded bias, applies ReLU and stores bf16 NHWC rows (128 B per pixel).
+// Three CTAs per SM (72 KB of shared memory, 64 TMEM columns each) overlap one another's gather / MMA / store phases, so the kernel
+// itself stays a simple sequential loop.  HBM-bound: 12 B read (once; the 12x window overlap is served by L1/L2) and 32 B written per
+// input pixel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace b2p {
+
+constexpr int ST_THREADS = 256;
+constexpr int ST_KREAL = 7 * 7 * 3;            // 147
+constexpr int ST_UNITS = 19;                   // 16-byte units (8 bf16) holding real K elements
+constexpr int ST_KSTEPS = 10;                  // K = 160: the unit after the last real one is zero, K steps 10 and 11 of the third chunk are never issued
+constexpr int ST_A_CHUNK = 128 * 128;          // one 64-element K chunk of the A tile: [128 rows][128 B]
+constexpr int ST_B_CHUNK = 64 * 128;           // one K chunk of the weight image: [64 channels][128 B]
+constexpr int ST_A_BYTES = 3 * ST_A_CHUNK;
+constexpr int ST_B_BYTES = 3 * ST_B_CHUNK;
+
+struct __align__(16) StemShared {
+  uint64_t wbar;       // weight image landed
+  uint64_t mma_bar;    // the tile's MMAs have retired
+  uint32_t tmem_base;
+  uint32_t pad;
+  float bias[64];
+};
+
+struct StemArgs {
+  const float* img;
+  long long sn;                 // element stride between images
+  int sc, sh, sw;               // element strides inside an image
+  int N, H, W, OH, OW;
+  long long total;              // N * OH * OW output pixels
+  int ntiles;
+  const uint8_t* wimg;          // [3 chunks][64][128 B] bf16, swizzled (stem_weight_image() in modeling.py)
+  const float* bias;            // [64] folded BatchNorm bias
+  __nv_bfloat16* out;           // [N, OH, OW, 64]
+};
+
+size_t stem_smem_bytes() { return ST_A_BYTES + ST_B_BYTES + sizeof(StemShared) + 1024; }
+
+__device__ __forceinline__ uint32_t st_swz(int r, int u) { return (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// units [J0, J1) of row m: 8 consecutive K elements each, K index = (r * 7 + kx) * 3 + c
+template <int J0, int J1>
+__device__ __forceinline__ void stem_gather(uint8_t* A, int m, const float* __restrict__ p, int off0, int sc, int sh, int sw, unsigned rowok, unsigned colok) {
+#pragma unroll
+  for (int j = J0; j < J1; ++j) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = j * 8 + e;
+      if (k < ST_KREAL) {
+        const int r = k / 21, kx = (k % 21) / 3, c = k % 3;
+        const bool ok = ((rowok >> r) & 1u) && ((colok >> kx) & 1u);
+        v[e] = ok ? __ldg(p + (off0 + r * sh + kx * sw + c * sc)) : 0.f;
+      } else {
+        v[e] = 0.f;
+      }
+    }
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(A + (j >> 3) * ST_A_CHUNK + st_swz(m, j & 7)) = q;
+  }
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 3) stem_conv_kernel(const StemArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* A = smem;
+  uint8_t* Bw = smem + ST_A_BYTES;
+  StemShared* sh = reinterpret_cast<StemShared*>(smem + ST_A_BYTES + ST_B_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&sh->wbar, 1);
+    mbar_init(&sh->mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&sh->wbar, ST_B_BYTES);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(Bw)), "l"(a.wimg),
+                 "r"((uint32_t)ST_B_BYTES), "r"(smem_u32(&sh->wbar)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(64u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid >= 64 && tid < 128) sh->bias[tid - 64] = __ldg(a.bias + (tid - 64));
+  if (tid < 128) *reinterpret_cast<uint4*>(A + 2 * ST_A_CHUNK + st_swz(tid, 3)) = make_uint4(0, 0, 0, 0);   // K 152..159: zero for every tile
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_base;
+  const uint32_t idesc = umma_idesc_n(64);
+  const int m = tid & 127, half = tid >> 7;
+  const int opi = a.OH * a.OW;
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    // ---- gather: this thread's half of the 7x7x3 window of output pixel g ----
+    {
+      const long long g = (long long)tile * 128 + m;
+      unsigned rowok = 0, colok = 0;
+      const float* p = a.img;
+      int off0 = 0;
+      if (g < a.total) {
+        const int n = (int)(g / opi);
+        const int rem = (int)(g - (long long)n * opi);
+        const int oy = rem / a.OW, ox = rem - oy * a.OW;
+        const int iy0 = 2 * oy - 3, ix0 = 2 * ox - 3;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+          if (iy0 + r >= 0 && iy0 + r < a.H) rowok |= 1u << r;
+          if (ix0 + r >= 0 && ix0 + r < a.W) colok |= 1u << r;
+        }
+        p = a.img + (long long)n * a.sn;
+        off0 = iy0 * a.sh + ix0 * a.sw;
+      }
+      if (half == 0) stem_gather<0, 10>(A, m, p, off0, a.sc, a.sh, a.sw, rowok, colok);
+      else stem_gather<10, ST_UNITS>(A, m, p, off0, a.sc, a.sh, a.sw, rowok, colok);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of A -> visible to the tensor core
+    __syncthreads();
+    if (warp == 0) {
+      if (tile == (int)blockIdx.x) mbar_wait(&sh->wbar, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < ST_KSTEPS; ++ks) {
+        const uint64_t ad = umma_desc(smem_u32(A) + (ks >> 2) * ST_A_CHUNK) + (uint64_t)((ks & 3) * 2);
+        const uint64_t bd = umma_desc(smem_u32(Bw) + (ks >> 2) * ST_B_CHUNK) + (uint64_t)((ks & 3) * 2);
+        umma_w(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      }
+      umma_commit_w(&sh->mma_bar);
+    }
+    mbar_wait(&sh->mma_bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    // ---- epilogue: thread = (row of its warp's TMEM lane quadrant, 32-channel half) ----
+    {
+      const int q = warp & 3, hf = warp >> 2;
+      const int row = q * 32 + lane;
+      float v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32);
+      tmem_ld<16, false>(taddr, v);
+      tmem_ld<16, false>(taddr + 16, v + 16);
+      tmem_ld_wait();
+      const long long g = (long long)tile * 128 + row;
+      if (g < a.total) {
+        uint4* dst = reinterpret_cast<uint4*>(a.out + g * 64 + hf * 32);
+        const float* bs = sh->bias + hf * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(fmaxf(v[8 * i + 0] + bs[8 * i + 0], 0.f), fmaxf(v[8 * i + 1] + bs[8 * i + 1], 0.f));
+          o.y = pack_bf16x2(fmaxf(v[8 * i + 2] + bs[8 * i + 2], 0.f), fmaxf(v[8 * i + 3] + bs[8 * i + 3], 0.f));
+          o.z = pack_bf16x2(fmaxf(v[8 * i + 4] + bs[8 * i + 4], 0.f), fmaxf(v[8 * i + 5] + bs[8 * i + 5], 0.f));
+          o.w = pack_bf16x2(fmaxf(v[8 * i + 6] + bs[8 * i + 6], 0.f), fmaxf(v[8 * i + 7] + bs[8 * i + 7], 0.f));
+          dst[i] = o;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // TMEM and the A tile are free for the next tile
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
+  }
+}
+
+// MaxPool2d(3, 2, 1) on NHWC bf16: a thread owns 8 channels (16 bytes) of one output pixel; padding never wins (window centre is always inside)
+__global__ void __launch_bounds__(256) maxpool_nhwc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W, int OH, int OW, int C8) {
+  const long long total = (long long)N * OH * OW * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % C8);
+    long long px = i / C8;
+    const int ox = (int)(px % OW); px /= OW;
+    const int oy = (int)(px % OH);
+    const int n = (int)(px / OH);
+    const int y0 = 2 * oy - 1, x0 = 2 * ox - 1;
+    const uint4* base = in + (long long)n * H * W * C8 + cg;
+    uint4 best = __ldg(base + ((long long)(2 * oy) * W + 2 * ox) * C8);
+    __nv_bfloat162* b2 = reinterpret_cast<__nv_bfloat162*>(&best);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = y0 + dy;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = x0 + dx;
+        if (x < 0 || x >= W || (dy == 1 && dx == 1)) continue;
+        uint4 v = __ldg(base + ((long long)y * W + x) * C8);
+        const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b2[k] = __hmax2(b2[k], v2[k]);
+      }
+    }
+    out[i] = best;
+  }
+}
+
+}  // namespace b2p
+
+using namespace b2p;
+
+extern "C" int b2p_encoder_stem_bf16(const float* img, int64_t stride_n, int64_t stride_c, int64_t stride_h, int64_t stride_w, int32_t N, int32_t H,
+                                     int32_t W, const void* weight_image, const float* bias, void* out_nhwc_bf16, void* stream) {
+  if (!img || !weight_image || !bias || !out_nhwc_bf16 || N <= 0 || H < 1 || W < 1) return B2P_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(weight_image) & 15) || (reinterpret_cast<uintptr_t>(out_nhwc_bf16) & 15)) return B2P_ERR_INVALID_ARG;
+  // offsets inside one image are 32-bit in the kernel
+  const int64_t span = (stride_c < 0 ? -stride_c : stride_c) * 3 + (stride_h < 0 ? -stride_h : stride_h) * (int64_t)(H + 8) + (stride_w < 0 ? -stride_w : stride_w) * (int64_t)(W + 8);
+  if (span >= (1LL << 31)) return B2P_ERR_INVALID_ARG;
+  StemArgs a{};
+  a.img = img; a.sn = stride_n; a.sc = (int)stride_c; a.sh = (int)stride_h; a.sw = (int)stride_w;
+  a.N = N; a.H = H; a.W = W; a.OH = (H + 6 - 7) / 2 + 1; a.OW = (W + 6 - 7) / 2 + 1;
+  a.total = (long long)N * a.OH * a.OW;
+  const long long ntiles = (a.total + 127) / 128;
+  if (ntiles >= (1LL << 31)) return B2P_ERR_INVALID_ARG;
+  a.ntiles = (int)ntiles;
+  a.wimg = reinterpret_cast<const uint8_t*>(weight_image); a.bias = bias; a.out = reinterpret_cast<__nv_bfloat16*>(out_nhwc_bf16);
+  const int smem = (int)stem_smem_bytes();
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2P_CUDA_TRY(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B2P_CUDA_TRY(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set = true;
+  }
+  const int grid = a.ntiles < 148 * 3 ? a.ntiles : 148 * 3;
+  stem_conv_kernel<<<grid, ST_THREADS, smem, (cudaStream_t)stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b2p_maxpool3x3s2_nhwc_bf16(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (!in || !out || N <= 0 || H < 1 || W < 1 || C < 8 || C % 8) return B2P_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return B2P_ERR_INVALID_ARG;
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  const long long total = (long long)N * OH * OW * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = 148LL * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  maxpool_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), N, H, W, OH, OW, C / 8);
+  return (int)cudaGetLastError();
+}

@@ -193,6 +193,39 @@ class ImageEncoder(_Tree):
         w = (conv_w.detach().float() * scale.view(-1, 1, 1, 1)).to(dt).contiguous(memory_format=torch.channels_last)
         return w, (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).to(dt).contiguous()
 
+    def _stem_operands(self):
+        """conv1 with bn1 folded, as the operand image ``b2p_encoder_stem_bf16`` takes (include/b200plan.h): K index
+        (kernel row, kernel column, channel) padded 147 -> 192, bf16, [K chunk of 64][out channel][16-byte unit ^ (channel % 8)][8]."""
+        bn = self.bn1
+        scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + 1e-5)
+        w = self.conv1.weight.detach().float() * scale.view(-1, 1, 1, 1)                       # [64, 3, 7, 7]
+        wk = F.pad(w.permute(0, 2, 3, 1).reshape(64, 147), (0, 45)).to(torch.bfloat16).view(64, 3, 8, 8)
+        n = torch.arange(64, device=w.device).view(64, 1, 1)
+        src = (torch.arange(8, device=w.device).view(1, 1, 8) ^ (n & 7)).expand(64, 3, 8)
+        image = torch.gather(wk, 2, src.unsqueeze(-1).expand(64, 3, 8, 8)).permute(1, 0, 2, 3).contiguous()
+        bias = (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
+        return image, bias
+
+    def _stem_bf16(self, img: torch.Tensor, image: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+        """conv1 + bn1 + relu + maxpool (modeling/resnet.py:279-282) by the hand-written kernels of csrc/encoder_stem.cu -> bf16 channels-last."""
+        from . import _lib
+        import ctypes as C
+        n, c, h, w = img.shape
+        if c != 3:
+            raise ValueError("the encoder expects [N,3,H,W] images")
+        oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        ph, pw = (oh - 1) // 2 + 1, (ow - 1) // 2 + 1
+        y = torch.empty((n, 64, oh, ow), dtype=torch.bfloat16, device=img.device, memory_format=torch.channels_last)
+        x = torch.empty((n, 64, ph, pw), dtype=torch.bfloat16, device=img.device, memory_format=torch.channels_last)
+        lib = _lib.load()
+        stream = C.c_void_p(torch.cuda.current_stream(img.device).cuda_stream)
+        sn, sc, sh, sw = img.stride()
+        with torch.cuda.device(img.device):
+            _lib.check(lib.b2p_encoder_stem_bf16(_lib.ptr(img), sn, sc, sh, sw, n, h, w, _lib.ptr(image), _lib.ptr(bias), _lib.ptr(y), stream),
+                       None, "b2p_encoder_stem_bf16")
+            _lib.check(lib.b2p_maxpool3x3s2_nhwc_bf16(_lib.ptr(y), _lib.ptr(x), n, oh, ow, 64, stream), None, "b2p_maxpool3x3s2_nhwc_bf16")
+        return x
+
     def _tensors(self):
         if getattr(self, "_tlist", None) is None:
             object.__setattr__(self, "_tlist", list(self.state_dict(keep_vars=True).values()))
@@ -218,7 +251,7 @@ class ImageEncoder(_Tree):
         key = (self.compute_dtype,) + tuple([(t.data_ptr(), t._version) for t in self._tensors()])
         cache = getattr(self, "_fold_cache", None)
         if cache is None or cache[0] != key:
-            stem = self._fold(self.conv1.weight, self.bn1)
+            stem = self._stem_operands() if self.compute_dtype == "bf16" else self._fold(self.conv1.weight, self.bn1)
             blocks = []
             for blk, stride in self._blocks():
                 ds = None
@@ -234,8 +267,11 @@ class ImageEncoder(_Tree):
     def _forward_fused(self, img: torch.Tensor) -> torch.Tensor:
         _, (w, b), blocks = self._folded()
         one, zero = [1, 1], [0, 0]
-        x = torch.cudnn_convolution_relu(img.to(w.dtype).contiguous(memory_format=torch.channels_last), w, b, [2, 2], [3, 3], one, 1)
-        x = F.max_pool2d(x, 3, 2, 1)
+        if self.compute_dtype == "bf16":
+            x = self._stem_bf16(img, w, b)
+        else:
+            x = torch.cudnn_convolution_relu(img.contiguous(memory_format=torch.channels_last), w, b, [2, 2], [3, 3], one, 1)
+            x = F.max_pool2d(x, 3, 2, 1)
         for stride, (w1, b1), (w2, b2), ds in blocks:
             y = torch.cudnn_convolution_relu(x, w1, b1, [stride, stride], one, one, 1)
             if ds is not None:

@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define B2P_ABI_VERSION 6
+#define B2P_ABI_VERSION 7
 
 typedef enum {
   B2P_OK = 0,
@@ -135,6 +135,17 @@ int b2p_set_chain(b2p_handle h, int enabled);
  * bit-identical to the host transform.  No handle: the transform has no state. */
 int b2p_preprocess_frames(const uint8_t* frames_nhwc, float* out_nhwc, int64_t n_pixels, const float mean[3], const float std_[3],
                           void* stream);
+
+/* ---- image-encoder stem (bf16 mode of the encoder): replaces conv1 + bn1 + relu and maxpool of the reference ResNet
+ * (modeling/resnet.py:193-198, 279-282) on the device.  img: fp32, logical [N,3,H,W] with ELEMENT strides
+ * (stride_n, stride_c, stride_h, stride_w) — NCHW and channels-last both work.  weight_image: the BatchNorm-folded conv1 weights as
+ * a 24,576-byte bf16 operand image: K index k = (kernel_row * 7 + kernel_col) * 3 + channel, padded to 192; element (n, k) at byte
+ * (k / 64) * 8192 + n * 128 + ((((k % 64) / 8) ^ (n % 8)) * 16) + (k % 8) * 2  (K-major, 128-byte swizzle).  bias [64] fp32 (folded).
+ * out: bf16 [N, OH, OW, 64] (channels-last), OH = (H - 1) / 2 + 1, OW likewise, 16-byte aligned.  bf16 products, fp32 accumulation. */
+int b2p_encoder_stem_bf16(const float* img, int64_t stride_n, int64_t stride_c, int64_t stride_h, int64_t stride_w, int32_t N, int32_t H,
+                          int32_t W, const void* weight_image, const float* bias, void* out_nhwc_bf16, void* stream);
+/* MaxPool2d(kernel 3, stride 2, padding 1) on bf16 [N,H,W,C] -> [N,(H-1)/2+1,(W-1)/2+1,C], C a multiple of 8, 16-byte aligned. */
+int b2p_maxpool3x3s2_nhwc_bf16(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
 
 /* ---- denoiser: replaces TemporalMapUnet.forward (modeling/temporal.py:197-245) with the image feature hoisted --
  * x        [B, H, D]            noisy trajectories

@@ -935,3 +935,36 @@ def test_image_encoder_bf16_channels_last_bound(golden_dir):
         model.perception.set_precision("fp32")
     with torch.no_grad():
         assert float((model.perception(img).cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("shape", [(3, 37, 53), (2, 64, 130), (1, 256, 900)])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_encoder_stem_kernels_vs_torch(shape, channels_last):
+    """csrc/encoder_stem.cu (conv1 7x7/2 + folded bn1 + relu on tcgen05, then the 3x3/2 max-pool; modeling/resnet.py:279-282) against
+    torch in fp32 on the SAME bf16-rounded operands: only the fp32 summation order and the final bf16 rounding differ, so the bound
+    is one bf16 ulp of the value (2^-7 relative) + 1e-3 absolute.  Odd sizes exercise the padding and the ragged last tile."""
+    import torch.nn.functional as F
+    model, _ = get_model("NO_GUIDANCE")
+    enc = model.perception
+    n, h, w = shape
+    g = torch.Generator().manual_seed(11)
+    img = torch.randn(n, 3, h, w, generator=g).to(DEV)
+    if channels_last:
+        img = img.contiguous(memory_format=torch.channels_last)
+    image, bias = enc._stem_operands()
+    got = enc._stem_bf16(img, image, bias)
+    assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
+    bn = enc.bn1
+    scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + 1e-5)
+    wf = (enc.conv1.weight.detach().float() * scale.view(-1, 1, 1, 1)).bfloat16().float()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = F.relu(F.conv2d(img.bfloat16().float(), wf, bias, 2, 3))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    want = F.max_pool2d(y, 3, 2, 1)
+    assert got.shape == want.shape
+    diff = (got.float() - want).abs()
+    bound = want.abs() * 2.0 ** -7 + 1e-3
+    assert bool((diff <= bound).all()), float((diff - bound).max())
