@@ -241,10 +241,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 1] = clock64();
 
     if (warp == 1) {
-      // =============================== MMA issue (warp 1: warp-uniform loop, one elected lane issues) ===============================
+      // =============================== MMA issue (one elected lane of warp 1 runs the whole loop: tc_ptx.cuh elect_one) ===============================
+      if (elect_one()) {
       mbar_wait(&sh->wbar, wpar);
       tc_fence_after();
-      if (a.trace && blockIdx.x == 0 && lane == 0) a.trace[oi * 16 + 2] = clock64();
+      if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 2] = clock64();
       const uint32_t sa = smem_u32(smem + (op.in_buf < 0 ? 0 : op.in_buf) * CH_ACT_BYTES);
       const uint32_t sb = smem_u32(wbuf);
       const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + CH_HALF);
@@ -259,15 +260,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
 #pragma unroll 1
         for (int k = 0; k < op.ksteps; ++k) {
           const uint64_t ko = (uint64_t)(k * TC_UMMA_K * 2 / 16);  // +32 B per K step, in 16-byte units
-          umma_w(dcol, a_hi + ko, b_hi + ko, idn, k == 0 ? 0u : 1u);
+          umma(dcol, a_hi + ko, b_hi + ko, idn, k == 0 ? 0u : 1u);
           if (NSPLIT == 2) {
-            umma_w(dcol, a_lo + ko, b_hi + ko, idn, 1u);
-            umma_w(dcol, a_hi + ko, b_lo + ko, idn, 1u);
+            umma(dcol, a_lo + ko, b_hi + ko, idn, 1u);
+            umma(dcol, a_hi + ko, b_lo + ko, idn, 1u);
           }
         }
-        umma_commit_w(&sh->mma_bar[hf]);
+        umma_commit(&sh->mma_bar[hf]);
       }
-      if (a.trace && blockIdx.x == 0 && lane == 0) a.trace[oi * 16 + 3] = clock64();
+      if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 3] = clock64();
+      }
     }
     wpar ^= 1;
     __syncwarp();

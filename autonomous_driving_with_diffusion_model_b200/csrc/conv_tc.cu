@@ -237,8 +237,9 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   if (mcast) cluster_sync_all();                   // peers' barriers are initialised before anyone multicasts / commits into them
   const uint32_t tmem_base = sh->tmem_base;
 
-  if (threadIdx.x == 0) {
-    // =============================== TMA producer (one thread) ===============================
+  if (warp == 0) {
+    if (elect_one()) {
+    // =============================== TMA producer (one elected lane of warp 0: the loads compile to plain UTMALDGs) ===============================
     prefetch_tmap(&maps.a[0][0]);
     prefetch_tmap(&maps.w[0]);
     if (NSPLIT == 2) { prefetch_tmap(&maps.a[0][1]); prefetch_tmap(&maps.w[1]); }
@@ -282,8 +283,9 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       issue(j, s, true, true);
       if (++s == stages) { s = 0; par ^= 1; }
     }
+    }
   } else if (warp == 1) {
-    // =============================== MMA issuer (warp 1: warp-uniform loop, one elected lane issues) ===============================
+    // =============================== MMA issuer (one elected lane of warp 1 runs the whole loop: tc_ptx.cuh elect_one) ===============================
     // All taps of a chunk are adjacent in shared memory ([T*TN rows] x 128 B, K-major), so ONE tcgen05.mma with
     // N = T*TN (<= 256; a fifth 64-wide tap takes a second instruction) covers them.  Descriptors are built once per
     // stage and advanced by adding to the address field.
@@ -291,10 +293,11 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     const uint32_t idescA = umma_idesc_n(nA * TN), idescB = umma_idesc_n(TN), idescR = umma_idesc_n((T - nA) * TN);   // idescR: the taps beyond the first instruction
     const bool concat = NSPLIT == 2 && a.concat;                         // W_hi and W_lo are adjacent in N: A_hi x [W_hi | W_lo] is one instruction
     const uint32_t idescC = umma_idesc_n(concat ? 2 * T * TN : TN);
+    if (elect_one()) {
     for (int it = 0, s = 0, par = 0; it < n_local; ++it, s = (s + 1 == stages ? 0 : s + 1), par ^= (s == 0)) {   // s = it % stages, par = (it / stages) & 1
       mbar_wait(&sh->full[s], par);
       tc_fence_after();
-      if (it == 0 && lane == 0) TC_T(2);
+      if (it == 0) TC_T(2);
       const uint32_t sa = smem_u32(smem + s * stage_bytes);
       const uint32_t sb = sa + NSPLIT * A_BYTES;
       const bool res_phase = it >= main_iters;
@@ -309,21 +312,21 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
           if (concat) {
             // an M = 128 MMA fetches its operands from shared memory at ~64 B/clk: with N = 48 the 4 KB A slice dominates, so
             // two instructions that read A_hi once and A_lo once beat three that read A_hi twice
-            umma_w(tmem_base, a_hi + ko, b_hi + ko, idescC, acc);          // blocks [0,T): hi*hi, blocks [T,2T): hi*lo
-            umma_w(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);           // blocks [0,T) += lo*hi
+            umma(tmem_base, a_hi + ko, b_hi + ko, idescC, acc);          // blocks [0,T): hi*hi, blocks [T,2T): hi*lo
+            umma(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);           // blocks [0,T) += lo*hi
             continue;
           }
-          umma_w(tmem_base, a_hi + ko, b_hi + ko, idescA, acc);
+          umma(tmem_base, a_hi + ko, b_hi + ko, idescA, acc);
           if (NSPLIT == 2) {
-            umma_w(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);
-            umma_w(tmem_base, a_hi + ko, b_lo + ko, idescA, 1u);
+            umma(tmem_base, a_lo + ko, b_hi + ko, idescA, 1u);
+            umma(tmem_base, a_hi + ko, b_lo + ko, idescA, 1u);
           }
           if (nA < T) {
             const uint64_t t4 = (uint64_t)(nA * BT_BYTES / 16);
-            umma_w(tmem_base + nA * TN, a_hi + ko, b_hi + t4 + ko, idescR, acc);
+            umma(tmem_base + nA * TN, a_hi + ko, b_hi + t4 + ko, idescR, acc);
             if (NSPLIT == 2) {
-              umma_w(tmem_base + nA * TN, a_lo + ko, b_hi + t4 + ko, idescR, 1u);
-              umma_w(tmem_base + nA * TN, a_hi + ko, b_lo + t4 + ko, idescR, 1u);
+              umma(tmem_base + nA * TN, a_lo + ko, b_hi + t4 + ko, idescR, 1u);
+              umma(tmem_base + nA * TN, a_hi + ko, b_lo + t4 + ko, idescR, 1u);
             }
           }
         }
@@ -332,17 +335,18 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
 #pragma unroll
         for (int k = 0; k < TC_K / TC_UMMA_K; ++k) {
           const uint64_t ko = (uint64_t)(k * TC_UMMA_K * 2 / 16);
-          umma_w(d, a_hi + ko, b_hi + ko, idescB, (first && k == 0) ? 0u : 1u);
+          umma(d, a_hi + ko, b_hi + ko, idescB, (first && k == 0) ? 0u : 1u);
           if (NSPLIT == 2) {
-            umma_w(d, a_lo + ko, b_hi + ko, idescB, 1u);
-            umma_w(d, a_hi + ko, b_lo + ko, idescB, 1u);
+            umma(d, a_lo + ko, b_hi + ko, idescB, 1u);
+            umma(d, a_hi + ko, b_lo + ko, idescB, 1u);
           }
         }
       }
-      if (CL > a.cluster_n) umma_commit_mc_w(&sh->empty[s], cmask); else umma_commit_w(&sh->empty[s]);   // the stage is free in a CTA once ALL cluster consumers released it
+      if (CL > a.cluster_n) umma_commit_mc(&sh->empty[s], cmask); else umma_commit(&sh->empty[s]);   // the stage is free in a CTA once ALL cluster consumers released it
     }
-    umma_commit_w(&sh->tmem_full);
-    if (lane == 0) TC_T(3);
+    umma_commit(&sh->tmem_full);
+    TC_T(3);
+    }
   }
   __syncwarp();
   griddep_wait();                 // everything below may read the previous kernels' outputs (residuals)

@@ -139,16 +139,16 @@ __global__ void __launch_bounds__(ST_THREADS, 3) stem_conv_kernel(const StemArgs
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of A -> visible to the tensor core
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 0 && elect_one()) {
       if (tile == (int)blockIdx.x) mbar_wait(&sh->wbar, 0);
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < ST_KSTEPS; ++ks) {
         const uint64_t ad = umma_desc(smem_u32(A) + (ks >> 2) * ST_A_CHUNK) + (uint64_t)((ks & 3) * 2);
         const uint64_t bd = umma_desc(smem_u32(Bw) + (ks >> 2) * ST_B_CHUNK) + (uint64_t)((ks & 3) * 2);
-        umma_w(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        umma(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
       }
-      umma_commit_w(&sh->mma_bar);
+      umma_commit(&sh->mma_bar);
     }
     mbar_wait(&sh->mma_bar, phase);
     phase ^= 1u;

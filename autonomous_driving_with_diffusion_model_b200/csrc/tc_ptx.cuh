@@ -81,28 +81,17 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Warp-collective forms: the WHOLE warp runs the issue loop (descriptor arithmetic stays warp-uniform) and one elected lane — always
-// the same one for a full mask — issues the instruction / the commit.  Measured (scripts/ts_mma_test.cu): ~105 cycles per M=128, K=16
-// instruction against 115-140 when a single divergent thread runs the loop; the instruction costs the same for every N <= 192.
-__device__ __forceinline__ void umma_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc_w(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+// One lane of a converged warp (the same one every time for a full mask).  The issue loops of the tcgen05 kernels run INSIDE an
+// `if (elect_one())` region: nvcc then keeps descriptors, idesc and the accumulate flag in uniform registers and emits the UTCHMMAs back to
+// back, which is what reaches the hardware's issue rate.  Measured on B200 (scripts/mma_rate.cu, M = 128, K = 16, cycles per instruction):
+//   N                                        48     96     192    256
+//   elected lane runs the whole loop          45     57      97    129     (= max(~40, N/2): the tensor pipe's own rate)
+//   elect.sync + predicated MMA per call     101    101     101     -      (round-2 code until this change: R2UR moves and a divergence
+//                                                                           check per instruction made the SOFTWARE issue path the pacer)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+  return e != 0;
 }
 // arrive on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far have retired
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
