@@ -772,8 +772,9 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
         if (nsplit == 2 && (rc = tc_make_act_map(&m.a[sidx][1], lo_ptr(ins[sidx]), rows, op.Lin, cs[sidx], op.Lin, lstride, box_b))) return h->fail(rc, "tensor map (A lo)");
       }
       const __nv_bfloat16* P16 = reinterpret_cast<const __nv_bfloat16*>(h->d_pack16);
-      if ((rc = tc_make_weight_map(&m.w[0], P16 + (aux ? h->aux_hi : op.tcW_hi), aux ? 6 : op.taps, op.Cout, op.C0 + op.C1, t.T, t.tile_n))) return h->fail(rc, "tensor map (W)");
-      if (nsplit == 2 && (rc = tc_make_weight_map(&m.w[1], P16 + (aux ? h->aux_lo : op.tcW_lo), aux ? 6 : op.taps, op.Cout, op.C0 + op.C1, t.T, t.tile_n))) return h->fail(rc, "tensor map (W lo)");
+      const int wbox_t = t.cluster_m > 1 ? 1 : t.T;   // weight multicast: one box per tap, dealt to the CTAs of the cluster
+      if ((rc = tc_make_weight_map(&m.w[0], P16 + (aux ? h->aux_hi : op.tcW_hi), aux ? 6 : op.taps, op.Cout, op.C0 + op.C1, wbox_t, t.tile_n))) return h->fail(rc, "tensor map (W)");
+      if (nsplit == 2 && (rc = tc_make_weight_map(&m.w[1], P16 + (aux ? h->aux_lo : op.tcW_lo), aux ? 6 : op.taps, op.Cout, op.C0 + op.C1, wbox_t, t.tile_n))) return h->fail(rc, "tensor map (W lo)");
       if (op.resW != NPOS) {
         if (op.tcRW_hi != NPOS) {
           t.RC[0] = op.RC0; t.RC[1] = op.RC1; t.resB = P + op.resB;

@@ -201,6 +201,11 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   const int crank = lrank & (a.cluster_n - 1);     // rank inside the GroupNorm sub-group
   const int cbase = lrank - crank;                 // first cluster rank of the sub-group
   const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  // weight multicast: cluster = (CM, 1, 1) consecutive ROW tiles of the same column tile (only with CL == 1)
+  const int CM = a.cluster_m;
+  const bool wm = CM > 1;
+  const int mrank = blockIdx.x & (CM - 1);
+  const uint16_t wmask = (uint16_t)((1u << CM) - 1u);
   const int b0 = tile_m * a.samples_per_tile;
 
   const int chunks0 = a.C[0] / TC_K, chunks1 = a.C[1] / TC_K;
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
 
   if (threadIdx.x == 0) {
     TC_T(0);
-    for (int s = 0; s < stages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], (CL > a.cluster_n) ? CL : 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], wm ? CM : ((CL > a.cluster_n) ? CL : 1)); }
     mbar_init(&sh->tmem_full, 1);
     mbar_init(&sh->gn_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   tc_fence_after();
   if (a.cluster_n > 1 && a.gn_gamma) cluster_sync_all();   // every peer's GroupNorm mbarrier is ready before anyone sends (in the prologue: off the dependency chain)
   const bool mcast = CL > a.cluster_n;             // activation multicast active (off by default: measured slower)
-  if (mcast) cluster_sync_all();                   // peers' barriers are initialised before anyone multicasts / commits into them
+  if (mcast || wm) cluster_sync_all();             // peers' barriers are initialised before anyone multicasts / commits into them
   const uint32_t tmem_base = sh->tmem_base;
 
   if (warp == 0) {
@@ -257,6 +262,17 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       const int kglob = (src == 0 ? 0 : (res_phase ? a.RC[0] : a.C[0])) + c0;
       if (do_w) {
         mbar_expect_tx(&sh->full[s], res_phase ? NSPLIT * (A_BYTES + BT_BYTES) : stage_bytes);
+        if (wm) {   // one box per (plane, tap), dealt round-robin to the CTAs of the cluster; each box lands in every CTA
+#pragma unroll
+          for (int h = 0; h < NSPLIT; ++h) {
+            if (res_phase) {
+              if ((h & (CM - 1)) == mrank) tma_load_2d_mc(sb + h * T * BT_BYTES, &maps.rw[h], &sh->full[s], kglob, n0, wmask);
+            } else {
+              for (int t = 0; t < T; ++t)
+                if (((h * T + t) & (CM - 1)) == mrank) tma_load_3d_mc(sb + (h * T + t) * BT_BYTES, &maps.w[h], &sh->full[s], kglob, n0, a.tap0 + t, wmask);
+            }
+          }
+        } else
 #pragma unroll
         for (int h = 0; h < NSPLIT; ++h) {
           if (res_phase) tma_load_2d(sb + h * T * BT_BYTES, &maps.rw[h], &sh->full[s], kglob, n0);
@@ -342,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
           }
         }
       }
-      if (CL > a.cluster_n) umma_commit_mc(&sh->empty[s], cmask); else umma_commit(&sh->empty[s]);   // the stage is free in a CTA once ALL cluster consumers released it
+      if (wm) umma_commit_mc(&sh->empty[s], wmask); else if (CL > a.cluster_n) umma_commit_mc(&sh->empty[s], cmask); else umma_commit(&sh->empty[s]);   // the stage is free in a CTA once ALL cluster consumers released it
     }
     umma_commit(&sh->tmem_full);
     TC_T(3);
@@ -596,7 +612,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     if (threadIdx.x == 64) { TC_T(6); TC_T(7); }
     if (threadIdx.x == 96) TC_TG(8, true);
   }
-  if (mcast) cluster_sync_all();                   // no CTA may exit while peers can still signal its barriers / write its smem
+  if (mcast || wm) cluster_sync_all();             // no CTA may exit while peers can still signal its barriers / write its smem
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -682,7 +698,7 @@ static int launch_t(const TcMaps& maps, const TcArgs& a_in, dim3 grid, cudaStrea
   cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = a.cluster_l; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = a.cluster_m; attr[0].val.clusterDim.y = a.cluster_l; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   static int pdl = -1;
@@ -740,6 +756,17 @@ int tc_configure(TcArgs& a) {
   const int ntiles = a.Cout / TN;
   while (cl * 2 <= mc && cl * 2 <= 8 && ntiles % (cl * 2) == 0 && a.samples_per_tile % (cl * 2) == 0) cl *= 2;
   a.cluster_l = cl;
+  // weight multicast along M (B2P_TC_WMCAST = cluster size, default below): only for launches of several waves whose column tiles need no
+  // cluster of their own; the caller encodes per-tap weight boxes when cluster_m > 1
+  static int wmc = -1;
+  if (wmc < 0) { const char* e = getenv("B2P_TC_WMCAST"); wmc = e ? atoi(e) : 1; }
+  a.cluster_m = 1;
+  const int mt = (a.nrows + TC_M - 1) / TC_M;
+  if (cl == 1 && wmc > 1 && mt * ntiles > 148) {
+    int cm = 1;
+    while (cm * 2 <= wmc && cm * 2 <= 8 && mt % (cm * 2) == 0) cm *= 2;
+    a.cluster_m = cm;
+  }
   return (ntiles % a.cluster_l) ? B2P_ERR_INVALID_ARG : B2P_OK;
 }
 
@@ -770,6 +797,8 @@ int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStrea
   if (a.n_out == 2 && (a.RC[0] || a.RC[1])) return tc_fail(__LINE__, a, "invalid layer shape");
   if (a.cluster_n < 1 || a.cluster_l < a.cluster_n || a.cluster_l % a.cluster_n || (a.cluster_n & (a.cluster_n - 1)) || (a.cluster_l & (a.cluster_l - 1))) return tc_fail(__LINE__, a, "tc_configure() was not applied");
   if ((a.Cout / TN) % a.cluster_l) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (a.cluster_m < 1 || (a.cluster_m & (a.cluster_m - 1)) || a.cluster_m > 8 || (a.cluster_m > 1 && (a.cluster_l != 1 || ((a.nrows + TC_M - 1) / TC_M) % a.cluster_m)))
+    return tc_fail(__LINE__, a, "tc_configure() was not applied");
   dim3 grid((a.nrows + TC_M - 1) / TC_M, a.Cout / TN, 1);
   if (nsplit == 2) {
     if (TN == 64) return launch_t<2, 64>(maps, a, grid, s);

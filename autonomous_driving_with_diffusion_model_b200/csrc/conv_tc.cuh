@@ -44,6 +44,8 @@ struct TcArgs {
   int tile_n;             // column-tile width: 64, 32 or 16 (tc_pick_tile_n)
   int cluster_n;          // set by launch_conv_tc: CTAs along N sharing one GroupNorm group
   int cluster_l;          // set by launch_conv_tc: cluster size along N (activation-tile multicast), multiple of cluster_n
+  int cluster_m;          // set by tc_configure: cluster size along M (row tiles sharing a column tile): every CTA loads 1/cluster_m of the WEIGHT stage and
+                          // multicasts it to the others (large batch: the weight tile re-read by every row tile is most of the L2 traffic); 1 = off
   int ring;               // set by launch_conv_tc: bytes of the operand ring in dynamic shared memory
   int stages;             // set by launch_conv_tc: ring stages = min(ring / stage bytes, 8)
   int concat;             // set by launch_conv_tc (bf16x3): hi x [W_hi | W_lo] as ONE MMA of N = 2*T*tile_n; the hi*lo products get their own TMEM block
