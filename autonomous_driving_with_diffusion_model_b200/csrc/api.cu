@@ -1012,6 +1012,8 @@ int b2p_finalize_weights(b2p_handle h) {
         size_t bytes = h->pack16_host.size() * sizeof(uint16_t);
         if (bytes > (size_t)prop.accessPolicyMaxWindowSize) bytes = (size_t)prop.accessPolicyMaxWindowSize;
         size_t lim = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+        if (getenv("B2P_L2_DEBUG")) fprintf(stderr, "[b2p] L2 %d B, persisting max %d B, window max %d B, pack16 %zu B\n", prop.l2CacheSize, prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize, bytes);
+        if (getenv("B2P_L2_CARVE_MB")) lim = (size_t)atoi(getenv("B2P_L2_CARVE_MB")) << 20;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess) h->l2_window_bytes = bytes;
         else cudaGetLastError();
       }

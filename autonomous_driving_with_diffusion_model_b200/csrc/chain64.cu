@@ -27,7 +27,9 @@
 namespace b2p {
 
 constexpr int CH_EPI_THREADS = 512;                  // 16 epilogue warps: 4 per TMEM lane quadrant
-constexpr int CH_THREADS = CH_EPI_THREADS;           // warp 1 also issues the MMAs (a 17th, MMA-only warp measured no faster: the epilogue is what an op costs)
+constexpr int CH_MMA_WARP = 16;                      // a 17th warp issues the MMAs AND, the moment they have retired, the next op's weight copy: an epilogue warp
+                                                     // got to that copy only after its own half-0 epilogue, 1.5-2.5 k cycles later, and the copy (~5 k cycles in situ) was exposed
+constexpr int CH_THREADS = CH_EPI_THREADS + 32;
 constexpr int CH_EC = 8;                             // columns per epilogue thread and column half: one GroupNorm group, one 16-byte chunk
 constexpr int CH_SL = 4;                             // column slices per half (4 warps per TMEM lane quadrant)
 constexpr int CH_HCOLS = 160;                        // TMEM column stride between the two column halves (5 taps x 32 channels)
@@ -51,6 +53,8 @@ struct __align__(16) ChainShared {
   float mo[CH_NS * CH_MAX_HD];   // model output of the CTA's trajectories (head result)
   float xw[8 * 64 + 64];         // 1x1 projection of x: [D][64] + bias
   float headw[8 * 64 + 8];       // head weights [d][64] + bias
+  ChainOp ops[CH_MAXOPS];        // the op table, copied out of the kernel-parameter constant bank in the prologue: an indexed read of a.ops[oi]
+                                 // is a constant-cache miss the first time an op's line is touched, and those misses sat on the op-to-op critical path
 };
 
 static_assert(CH_OFF_MISC + sizeof(ChainShared) + 1024 <= 227 * 1024, "shared memory budget");
@@ -146,13 +150,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
-  if (warp == 1) {
+  if (warp == CH_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // rows that no trajectory of this CTA owns are never written: start from zero so the tensor core never reads stale bit patterns
   for (int i = tid; i < 3 * CH_ACT_BYTES / 16; i += CH_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   // weights-only tables: independent of the preceding kernels
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.ops);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sh->ops);
+    for (int i = tid; i < (int)(a.n_ops * sizeof(ChainOp) / 4); i += CH_THREADS) dst[i] = src[i];
+  }
   if (a.xprojW)
     for (int i = tid; i < a.D * 64 + 64; i += CH_THREADS) sh->xw[i] = i < a.D * 64 ? __ldg(a.xprojW + i) : __ldg(a.xprojB + i - a.D * 64);
   if (a.headW) {   // [64][head_dim] -> [d][64]
@@ -166,13 +175,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
   const uint32_t tmem_base = sh->tmem_base;
 
   auto issue_weights = [&](int oi) {   // one thread: pre-swizzled image, one bulk copy per tap and plane
-    const ChainOp& op = a.ops[oi];
+    const ChainOp& op = sh->ops[oi];
     const uint32_t plane = (uint32_t)op.T * CH_TAP_BYTES;
     mbar_expect_tx(&sh->wbar, NSPLIT * plane);
     const uint8_t* src = a.wpack + op.w_off;
     for (int i = 0; i < NSPLIT * op.T; ++i) bulk_g2s(wbuf + (size_t)i * CH_TAP_BYTES, src + (size_t)i * CH_TAP_BYTES, CH_TAP_BYTES, &sh->wbar);
   };
-  if (tid == 0) issue_weights(0);
+  if (warp == CH_MMA_WARP && elect_one()) issue_weights(0);
   griddep_launch_dependents();      // the next kernel may become resident and prefetch ITS weights
   griddep_wait();                   // everything below reads what the preceding kernels wrote
 
@@ -206,7 +215,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
 
 #pragma unroll 1
   for (int oi = 0; oi < a.n_ops; ++oi) {
-    const ChainOp& op = a.ops[oi];
+    const ChainOp& op = sh->ops[oi];
     const int L = op.L;
     if (op.in_buf == CH_IN_IM2COL) {
       // A[row (s, l)][k = j * D + c] = x[s, l + j - pad, c]  (zero outside the trajectory, zero for k >= T_im2col * D)
@@ -240,8 +249,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     __syncthreads();
     if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 1] = clock64();
 
-    if (warp == 1) {
-      // =============================== MMA issue (one elected lane of warp 1 runs the whole loop: tc_ptx.cuh elect_one) ===============================
+    if (warp == CH_MMA_WARP) {
+      // =============================== MMA issue (one elected lane of the 17th warp runs the whole loop: tc_ptx.cuh elect_one) ===============================
       if (elect_one()) {
       mbar_wait(&sh->wbar, wpar);
       tc_fence_after();
@@ -269,7 +278,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
         umma_commit(&sh->mma_bar[hf]);
       }
       if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 3] = clock64();
+      if (oi + 1 < a.n_ops) {          // the weight buffer is free once every MMA of this op has retired
+        mbar_wait(&sh->mma_bar[1], mpar);
+        if (a.trace && blockIdx.x == 0) a.trace[(oi + 1) * 16 + 12] = clock64();
+        issue_weights(oi + 1);
       }
+      }
+      __syncwarp();
     }
     wpar ^= 1;
     __syncwarp();
@@ -326,7 +341,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       mbar_wait_sleep(&sh->mma_bar[hf], mpar);
       tc_fence_after();
       if (hf == 0 && a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 5] = clock64();
-      if (hf == 1 && tid == 0 && oi + 1 < a.n_ops) issue_weights(oi + 1);   // the weight buffer is free: every MMA of this op has retired
       if (!epi || ((quad * 32) >> op.log2L) >= nb) continue;   // the MMA warp; or none of this warp's 32 rows belongs to a trajectory (L = 8 ops, last CTA)
 #pragma unroll 1
       for (int o = 0; o < n_out; ++o) {
@@ -441,7 +455,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
   if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[a.n_ops * 16] = clock64();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == CH_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }

@@ -84,7 +84,9 @@ inline int add_l2_window_attr(cudaLaunchAttribute* attr, int n) {
   attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
   attr[n].val.accessPolicyWindow.base_ptr = const_cast<void*>(w.base);
   attr[n].val.accessPolicyWindow.num_bytes = w.bytes;
-  attr[n].val.accessPolicyWindow.hitRatio = 1.0f;
+  static float ratio = -1.f;
+  if (ratio < 0.f) { const char* e = getenv("B2P_L2_HITRATIO"); ratio = e ? (float)atof(e) : 1.0f; }
+  attr[n].val.accessPolicyWindow.hitRatio = ratio;
   attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
   attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
   return n + 1;

@@ -24,7 +24,8 @@ tot = 0
 for i in range(10):
     r = t[i]
     nxt = t[i + 1][0] if i < 9 else t[10][0]
-    extra = f"   {r[9]-r[8]} {r[10]-r[9]} {r[11]-r[10]} {r[6]-r[11]}" if r[9] else ""
+    wl = f"  [weights: issued {r[12]-t[i-1][0] if i else 0} into the previous op, landed {r[2]-r[12] if r[12] else 0} cycles later]"
+    extra = wl + f"   {r[9]-r[8]} {r[10]-r[9]} {r[11]-r[10]} {r[6]-r[11]}" if r[9] else wl
     print(f"{i:2d}  {r[1]-r[0]:8d}  {r[2]-r[1]:8d}  {r[3]-r[2]:8d}  {r[4]-r[1]:8d}  {r[5]-r[4]:8d}  {r[8]-r[5]:8d}  {r[6]-r[5]:8d}  {nxt-r[0]:8d}{extra}")
     tot += nxt - r[0]
 print("sum", tot, "cycles =", tot / 1.965e3, "us")
