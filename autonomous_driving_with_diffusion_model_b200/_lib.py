@@ -47,7 +47,7 @@ class ControlConfig(C.Structure):
                 ("brake_ratio", C.c_double), ("clip_delta", C.c_double), ("max_throttle", C.c_double)]
 
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 SCHED_KINDS = {"guidance_ddim": 0, "guidance_ddpm": 1, "inpainting_ddim": 2, "inpainting_ddpm": 3}
 PRED_TYPES = {"epsilon": 0, "sample": 1, "v_prediction": 2}
 BETA_SCHEDULES = {"squaredcos_cap_v2": 0, "linear": 1, "scaled_linear": 2}
@@ -73,6 +73,7 @@ SYMBOLS = {
     "b2p_preprocess_frames": (C.c_int, [_VP, _VP, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), _VP]),
     "b2p_encoder_stem_bf16": (C.c_int, [_VP, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP]),
     "b2p_maxpool3x3s2_nhwc_bf16": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP]),
+    "b2p_encoder_conv_bf16": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "b2p_unet_forward": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "b2p_state_pred": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "b2p_state_pred_vjp": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),

@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 TRACE = os.environ.get("B2P_TRACE_BUILD") == "1"   # developer build with in-kernel stage clocks (scripts/tc_trace.py)
 LIB_PATH = os.path.join(PKG_DIR, "libb200plan_trace.so" if TRACE else "libb200plan.so")
-SOURCES = ["api.cu", "sched.cu", "embed.cu", "conv_ffma.cu", "conv_gemv.cu", "conv_tc.cu", "chain64.cu", "trajpred.cu", "preprocess.cu", "control.cu", "encoder_stem.cu"]
+SOURCES = ["api.cu", "sched.cu", "embed.cu", "conv_ffma.cu", "conv_gemv.cu", "conv_tc.cu", "chain64.cu", "trajpred.cu", "preprocess.cu", "control.cu", "encoder_stem.cu", "encoder_conv.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -159,10 +159,15 @@ class ImageEncoder(_Tree):
     compute_dtype = "fp32"   # "fp32" (TF32 follows torch.backends.cudnn.allow_tf32) or "bf16" (bf16 channels-last;
     #                           feature error <= 3e-2 of its max-abs vs the fp32 golden, tests/test_gpu_parity.py) — set_precision()
 
-    def set_precision(self, precision: str) -> "ImageEncoder":
+    bf16_body = "tcgen05"    # "tcgen05": layer1..layer4 by csrc/encoder_conv.cu (hand-written implicit GEMM);  "cudnn": torch's fused cuDNN calls (A/B timing)
+
+    def set_precision(self, precision: str, body: str = "tcgen05") -> "ImageEncoder":
         if precision not in ("fp32", "bf16"):
             raise ValueError("encoder precision must be 'fp32' or 'bf16'")
+        if body not in ("tcgen05", "cudnn"):
+            raise ValueError("encoder body must be 'tcgen05' or 'cudnn'")
         object.__setattr__(self, "compute_dtype", precision)
+        object.__setattr__(self, "bf16_body", body)
         self.invalidate()
         return self
 
@@ -192,6 +197,28 @@ class ImageEncoder(_Tree):
         scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + 1e-5)
         w = (conv_w.detach().float() * scale.view(-1, 1, 1, 1)).to(dt).contiguous(memory_format=torch.channels_last)
         return w, (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).to(dt).contiguous()
+
+    def _fold_packed(self, conv_w, bn):
+        """conv + BatchNorm as the operands ``b2p_encoder_conv_bf16`` takes: bf16 [k*k][C_out][C_in] with the BatchNorm scale folded in, fp32 bias."""
+        scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + 1e-5)
+        w = conv_w.detach().float() * scale.view(-1, 1, 1, 1)
+        co, ci, kh, kw = w.shape
+        wp = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16).contiguous()
+        return wp, (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
+
+    @staticmethod
+    def _conv_tc(x, wp, bias, res, ksize, stride, relu):
+        """One folded convolution on NHWC bf16 activations by csrc/encoder_conv.cu (x: [N,H,W,C_in] contiguous)."""
+        from . import _lib
+        import ctypes as C
+        n, h, w, ci = x.shape
+        co = wp.shape[1]
+        out = torch.empty((n, (h - 1) // stride + 1, (w - 1) // stride + 1, co), dtype=torch.bfloat16, device=x.device)
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().b2p_encoder_conv_bf16(_lib.ptr(x), n, h, w, ci, _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(res) if res is not None else None,
+                                                         _lib.ptr(out), co, ksize, stride, 1 if relu else 0, stream), None, "b2p_encoder_conv_bf16")
+        return out
 
     def _stem_operands(self):
         """conv1 with bn1 folded, as the operand image ``b2p_encoder_stem_bf16`` takes (include/b200plan.h): K index
@@ -248,17 +275,18 @@ class ImageEncoder(_Tree):
         return (getattr(self, "_gen", 0), sum([t._version for t in self._tensors()]))
 
     def _folded(self):
-        key = (self.compute_dtype,) + tuple([(t.data_ptr(), t._version) for t in self._tensors()])
+        key = (self.compute_dtype, self.bf16_body) + tuple([(t.data_ptr(), t._version) for t in self._tensors()])
         cache = getattr(self, "_fold_cache", None)
         if cache is None or cache[0] != key:
             stem = self._stem_operands() if self.compute_dtype == "bf16" else self._fold(self.conv1.weight, self.bn1)
             blocks = []
+            fold = self._fold_packed if (self.compute_dtype == "bf16" and self.bf16_body == "tcgen05") else self._fold
             for blk, stride in self._blocks():
                 ds = None
                 if "downsample" in blk._modules:
                     d = blk.downsample._modules
-                    ds = self._fold(d["0"].weight, d["1"])
-                blocks.append((stride, self._fold(blk.conv1.weight, blk.bn1), self._fold(blk.conv2.weight, blk.bn2), ds))
+                    ds = fold(d["0"].weight, d["1"])
+                blocks.append((stride, fold(blk.conv1.weight, blk.bn1), fold(blk.conv2.weight, blk.bn2), ds))
             cache = (key, stem, blocks)
             object.__setattr__(self, "_fold_cache", cache)
             object.__setattr__(self, "_graphs", {})
@@ -269,6 +297,13 @@ class ImageEncoder(_Tree):
         one, zero = [1, 1], [0, 0]
         if self.compute_dtype == "bf16":
             x = self._stem_bf16(img, w, b)
+            if self.bf16_body == "tcgen05":     # every convolution of layer1..layer4 hand-written (csrc/encoder_conv.cu), NHWC bf16 throughout
+                x = x.permute(0, 2, 3, 1)       # the stem's channels-last tensor viewed as [N,H,W,C] (contiguous)
+                for stride, (w1, b1), (w2, b2), ds in blocks:
+                    y = self._conv_tc(x, w1, b1, None, 3, stride, True)
+                    r = self._conv_tc(x, ds[0], ds[1], None, 1, stride, False) if ds is not None else x
+                    x = self._conv_tc(y, w2, b2, r, 3, 1, True)
+                return F.linear(x.float().mean((1, 2)), self.fc.weight.float(), self.fc.bias.float())   # pooling and fc in fp32
         else:
             x = torch.cudnn_convolution_relu(img.contiguous(memory_format=torch.channels_last), w, b, [2, 2], [3, 3], one, 1)
             x = F.max_pool2d(x, 3, 2, 1)
@@ -281,7 +316,7 @@ class ImageEncoder(_Tree):
 
     def _forward_graphed(self, img: torch.Tensor) -> torch.Tensor:
         self._folded()   # (re)builds the folded weights and drops stale graphs when a parameter changed
-        key = (tuple(img.shape), img.device, torch.backends.cudnn.allow_tf32, self.compute_dtype)
+        key = (tuple(img.shape), img.device, torch.backends.cudnn.allow_tf32, self.compute_dtype, self.bf16_body)
         g = self._graphs.get(key)
         if g is None:
             static_in = torch.empty_like(img, memory_format=torch.channels_last)

@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define B2P_ABI_VERSION 7
+#define B2P_ABI_VERSION 8
 
 typedef enum {
   B2P_OK = 0,
@@ -146,6 +146,15 @@ int b2p_encoder_stem_bf16(const float* img, int64_t stride_n, int64_t stride_c, 
                           int32_t W, const void* weight_image, const float* bias, void* out_nhwc_bf16, void* stream);
 /* MaxPool2d(kernel 3, stride 2, padding 1) on bf16 [N,H,W,C] -> [N,(H-1)/2+1,(W-1)/2+1,C], C a multiple of 8, 16-byte aligned. */
 int b2p_maxpool3x3s2_nhwc_bf16(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* ---- image-encoder body (bf16 mode): one convolution of ResNet-34's layer1..layer4 with its BatchNorm folded in, the residual add and the
+ * ReLU (modeling/resnet.py:56-102: conv3x3 -> bn -> relu -> conv3x3 -> bn -> (+ identity | downsample(x)) -> relu; 199-214, 283-286).
+ * in: bf16 [N,H,W,Cin] (channels-last);  ksize/stride: 3/1 (pad 1), 3/2 (pad 1) or 1/2 (pad 0, the projection shortcut);
+ * w_packed: bf16 [ksize*ksize][Cout][Cin] = weight.permute(2,3,0,1) with the BatchNorm scale folded in;  bias: fp32 [Cout] (folded);
+ * res: bf16 [N,OH,OW,Cout] added before the ReLU, or NULL;  out: bf16 [N,OH,OW,Cout], OH = (H-1)/stride+1, OW likewise;  relu: 0/1.
+ * Cin, Cout multiples of 64 (Cout > 256: a multiple of 256); all pointers 16-byte aligned.  bf16 products, fp32 accumulation, one rounding
+ * of the result to bf16. */
+int b2p_encoder_conv_bf16(const void* in_nhwc, int32_t N, int32_t H, int32_t W, int32_t Cin, const void* w_packed, const float* bias, const void* res_nhwc,
+                          void* out_nhwc, int32_t Cout, int32_t ksize, int32_t stride, int32_t relu, void* stream);
 
 /* ---- denoiser: replaces TemporalMapUnet.forward (modeling/temporal.py:197-245) with the image feature hoisted --
  * x        [B, H, D]            noisy trajectories

@@ -14,8 +14,8 @@ m = m.to(dev).eval()
 img = torch.randn(scenes, 3, 256, 900, device=dev)
 for bench in (False, True):
     torch.backends.cudnn.benchmark = bench
-    for prec in ("fp32", "bf16"):
-        m.perception.set_precision(prec)
+    for prec, body in (("fp32", "cudnn"), ("bf16", "cudnn"), ("bf16", "tcgen05")):
+        m.perception.set_precision(prec, body)
         for _ in range(2):
             m.perception(img)
         torch.cuda.synchronize()
@@ -24,8 +24,8 @@ for bench in (False, True):
         for _ in range(3):
             m.perception(img)
         e1.record(); torch.cuda.synchronize()
-        print(f"benchmark={bench} {prec}: {e0.elapsed_time(e1) / 3:.2f} ms for {scenes} scenes", flush=True)
-        if "--profile" in sys.argv and bench:
+        print(f"benchmark={bench} {prec} body={body}: {e0.elapsed_time(e1) / 3:.2f} ms for {scenes} scenes", flush=True)
+        if "--profile" in sys.argv and bench and body == "tcgen05":
             from torch.profiler import profile, ProfilerActivity
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
                 m.perception(img); torch.cuda.synchronize()

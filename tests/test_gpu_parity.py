@@ -937,6 +937,63 @@ def test_image_encoder_bf16_channels_last_bound(golden_dir):
         assert float((model.perception(img).cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("case", [
+    # N, H, W, C_in, C_out, ksize, stride                      (layer shapes of ResNet-34 on a 256 x 900 frame, then ragged / tiny maps)
+    (3, 64, 225, 64, 64, 3, 1), (2, 32, 113, 128, 128, 3, 1), (2, 16, 57, 256, 256, 3, 1), (3, 8, 29, 512, 512, 3, 1),
+    (2, 64, 225, 64, 128, 3, 2), (2, 32, 113, 128, 256, 3, 2), (3, 16, 57, 256, 512, 3, 2), (2, 64, 225, 64, 128, 1, 2), (2, 16, 57, 256, 512, 1, 2),
+    (1, 5, 3, 64, 64, 3, 1), (1, 17, 9, 64, 64, 3, 2), (5, 16, 8, 128, 64, 3, 1), (37, 8, 16, 64, 64, 3, 1), (1, 1, 1, 64, 64, 3, 1)])
+@pytest.mark.parametrize("epilogue", [(False, True), (True, True), (False, False)])
+def test_encoder_conv_kernel_vs_torch(case, epilogue):
+    """csrc/encoder_conv.cu (one folded convolution of ResNet-34's layer1..layer4 with bias, residual add and ReLU; modeling/resnet.py:56-102)
+    against torch in fp32 on the SAME bf16 operands: the fp32 summation order and the single bf16 rounding of the result differ, so the bound is
+    one bf16 ulp of the value (2^-7 relative) + 2e-3 absolute.  Covers the 3x3/1, 3x3/2 and 1x1/2 forms, every channel width, both tile
+    orientations (maps of height <= 8 use 8 x 16 tiles), images smaller than a tile and a tile group running past the last image."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from autonomous_driving_with_diffusion_model_b200 import _lib
+    n, h, w, cin, cout, k, stride = case
+    use_res, relu = epilogue
+    g = torch.Generator().manual_seed(n * 1000 + h * 10 + cin + k + stride)
+    x = torch.randn(n, h, w, cin, generator=g).to(DEV).bfloat16()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV).bfloat16()
+    bias = torch.randn(cout, generator=g).to(DEV)
+    oh, ow = (h - 1) // stride + 1, (w - 1) // stride + 1
+    res = torch.randn(n, oh, ow, cout, generator=g).to(DEV).bfloat16() if use_res else None
+    wp = wt.permute(2, 3, 0, 1).reshape(k * k, cout, cin).contiguous()
+    got = P.modeling.ImageEncoder._conv_tc(x, wp, bias, res, k, stride, relu)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        want = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), bias, stride, 1 if k == 3 else 0)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    if res is not None:
+        want = want + res.permute(0, 3, 1, 2).float()
+    if relu:
+        want = F.relu(want)
+    want = want.permute(0, 2, 3, 1)
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    diff = (got.float() - want).abs()
+    bound = want.abs() * 2.0 ** -7 + 2e-3
+    assert bool((diff <= bound).all()), float((diff - bound).max())
+
+
+def test_image_encoder_bf16_handwritten_body_matches_the_cudnn_body():
+    """The bf16 encoder with layer1..layer4 on csrc/encoder_conv.cu against the same encoder on torch's cuDNN calls: both round every
+    activation to bf16, so the features agree to a small multiple of the bf16 noise (<= 2e-2 of the feature's max-abs)."""
+    model, _ = get_model("NO_GUIDANCE")
+    img = W.synth_image(2, seed=5).to(DEV)
+    try:
+        with torch.no_grad():
+            model.perception.set_precision("bf16", "cudnn")
+            a = model.perception(img).float()
+            model.perception.set_precision("bf16", "tcgen05")
+            b = model.perception(img).float()
+        assert float((a - b).abs().max()) <= 2e-2 * float(a.abs().max())
+    finally:
+        model.perception.set_precision("fp32")
+
+
 @pytest.mark.parametrize("shape", [(3, 37, 53), (2, 64, 130), (1, 256, 900)])
 @pytest.mark.parametrize("channels_last", [False, True])
 def test_encoder_stem_kernels_vs_torch(shape, channels_last):
