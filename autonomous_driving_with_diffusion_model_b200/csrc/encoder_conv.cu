@@ -32,10 +32,12 @@ constexpr int EC_PW = 10, EC_PH = 18;                 // halo patch: (8 + 2) x (
 constexpr int EC_PATCH = EC_PW * EC_PH * 128;         // 23,040 B written by one TMA box
 constexpr int EC_ASLOT = 23 * 1024;                   // patch slot (1024-aligned)
 constexpr int EC_MAX_A = 8, EC_MAX_W = 4;
+constexpr int EC_STG = 128 * 128;                     // one staged slab: 128 pixels x 64 channels bf16
 
 struct EncMaps {
   CUtensorMap a[4];     // input: one map (stride 1) or the four parity sub-images (stride 2), dims (C, W, H, N)
   CUtensorMap w;        // weights (C_in, C_out, taps)
+  CUtensorMap out, res; // output / residual (C_out, W, H, N): 64 channels x one tile per box (the epilogue's TMA store / load)
 };
 
 struct EncArgs {
@@ -47,6 +49,7 @@ struct EncArgs {
   int map_dx[4], map_dy[4];     // patch origin of map m relative to the tile origin (in that map's pixel grid)
   int tap_map[9], tap_off[9], tap_w[9];   // patch of the tap, byte offset of its window inside the patch, weight-map tap coordinate
   int na, nw, sets;             // patch slots, weight slots, accumulator sets
+  int nstg;                     // epilogue staging buffers (16 KB each, for the output and for the residual): 1 or 2
   int relu;
   int transposed;               // 0: tile = 16 rows x 8 columns, patch stored [row][column];  1: tile = 8 rows x 16 columns, patch stored [column][row]
                                 // (the input map lists H before W): for feature maps of height <= 8, where a 16-row tile would be half empty
@@ -59,6 +62,7 @@ struct __align__(16) EncShared {
   uint64_t a_full[EC_MAX_A], a_empty[EC_MAX_A];
   uint64_t w_full[EC_MAX_W], w_empty[EC_MAX_W];
   uint64_t t_full[2], t_empty[2];
+  uint64_t res_full[2];
   uint32_t tmem_base;
 };
 
@@ -66,6 +70,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const void* src, const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -89,13 +98,15 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_conv_kernel(const __grid_co
   uint8_t* sA = smem;
   const int wslot_bytes = a.NB * 128;
   uint8_t* sW = smem + a.na * EC_ASLOT;
-  EncShared* sh = reinterpret_cast<EncShared*>(sW + a.nw * wslot_bytes);
+  uint8_t* sOut = sW + a.nw * wslot_bytes;            // nstg x 16 KB: a tile's 64-channel slab on its way out (swizzled, TMA store)
+  uint8_t* sRes = sOut + a.nstg * EC_STG;             // nstg x 16 KB: the residual slab on its way in (TMA load)
+  EncShared* sh = reinterpret_cast<EncShared*>(sRes + a.nstg * EC_STG);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < a.na; ++i) { mbar_init(&sh->a_full[i], 1); mbar_init(&sh->a_empty[i], 1); }
     for (int i = 0; i < a.nw; ++i) { mbar_init(&sh->w_full[i], 1); mbar_init(&sh->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], 1); mbar_init(&sh->t_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->t_full[i], 1); mbar_init(&sh->t_empty[i], 8); mbar_init(&sh->res_full[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -193,92 +204,108 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_conv_kernel(const __grid_co
       }
     }
   } else if (warp >= 4) {
-    // =============================== epilogue (warps 4..11: TMEM lane quadrant = warp & 3, two warps per quadrant) ===============================
-    // An item is G tiles x NB / 32 blocks of 32 channels; the two warps of a quadrant take alternate blocks.  The residual of the NEXT block
-    // is loaded before the current one is processed (and the first one before the accumulators are ready): the HBM latency of those
-    // loads was the epilogue's whole cost, and with one accumulator set (NB = 256) the epilogue is not overlapped with the MMAs.
+    // =============================== epilogue (warps 4..11) ===============================
+    // An item is G tiles x NB / 64 slabs of 128 pixels x 64 channels.  A thread owns one pixel (its TMEM lane) and 32 of the slab's channels
+    // (warps 4..7: the lower half, 8..11: the upper half).  Neither the residual nor the result is touched with per-thread global accesses
+    // (a warp would hit 32 different 128-byte lines per instruction: that made the first version LSU-bound): the residual slab arrives by TMA
+    // into a swizzled staging buffer two slabs ahead, the result is written into a second swizzled buffer and leaves by a TMA store, which
+    // also clips ragged tiles.
     const int q = warp & 3, e = (warp - 4) >> 2;
     const int m = q * 32 + lane;
-    const int r = a.transposed ? (m & 7) : (m >> 3), c = a.transposed ? (m >> 3) : (m & 7);
     const int th = a.transposed ? 8 : 16, tw = a.transposed ? 16 : 8;
-    const int cbn = a.NB >> 5, nblk = a.G * cbn;
+    const int spt = a.NB >> 6, nsl = a.G * spt;                    // slabs per tile / per item
+    const bool leader = warp == 4 && lane == 0;
+    const uint32_t swz = (uint32_t)(m & 7);
+    uint32_t rpar = 0u;                                            // bit b: phase parity of res_full[b]
     int it = 0;
+    // origin of slab ls of the current item: false when its tile lies past the last image (warp-uniform)
+    auto slab_origin = [&](int gi, int nb, int ls, int* cc, int* x0, int* y0, int* n) -> bool {
+      const int g = ls / spt, sb = ls - g * spt;
+      const int tile = gi * a.G + g;
+      if (tile >= a.n_tiles) return false;
+      *n = tile / tiles_per_img;
+      const int rem = tile - *n * tiles_per_img;
+      const int ty = rem / a.tiles_x;
+      *y0 = ty * th; *x0 = (rem - ty * a.tiles_x) * tw;
+      *cc = nb * a.NB + sb * 64;
+      return true;
+    };
+    auto load_res = [&](int gi, int nb, int ls, int buf) {         // leader only
+      int cc, x0, y0, n;
+      if (ls < nsl && slab_origin(gi, nb, ls, &cc, &x0, &y0, &n)) {
+        mbar_expect_tx(&sh->res_full[buf], EC_STG);
+        if (a.transposed) tma_load_4d(sRes + buf * EC_STG, &maps.res, &sh->res_full[buf], cc, y0, x0, n);
+        else tma_load_4d(sRes + buf * EC_STG, &maps.res, &sh->res_full[buf], cc, x0, y0, n);
+      }
+    };
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
       const int set = it & (a.sets - 1);
       const uint32_t tpar = (uint32_t)((it / a.sets) & 1);
       const int nb = item / a.n_groups, gi = item - nb * a.n_groups;
       const float* bias = a.bias + nb * a.NB;
-      // block bidx -> (tile g, channel block cb): element offset of this thread's 32 channels, validity
-      auto locate = [&](int bidx, size_t* off) -> bool {
-        if (bidx >= nblk) return false;
-        const int g = bidx / cbn, cb = bidx - g * cbn;
-        const int tile = gi * a.G + g;
-        if (tile >= a.n_tiles) return false;
-        const int n = tile / tiles_per_img;
-        const int rem = tile - n * tiles_per_img;
-        const int ty = rem / a.tiles_x;
-        const int y = ty * th + r, x = (rem - ty * a.tiles_x) * tw + c;
-        *off = (((size_t)n * a.H + y) * a.W + x) * a.Cout + nb * a.NB + cb * 32;
-        return y < a.H && x < a.W;
-      };
-      uint4 rres[4];
-      size_t off = 0;
-      bool ok = locate(e, &off);
-      if (ok && a.res) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rres[j] = __ldg(reinterpret_cast<const uint4*>(a.res + off) + j);
+      if (leader && a.res) {                                        // the first residual slabs travel while the MMAs of the item still run
+        load_res(gi, nb, 0, 0);
+        if (a.nstg == 2) load_res(gi, nb, 1, 1);
       }
       mbar_wait_sleep(&sh->t_full[set], tpar);
       tc_fence_after();
-      for (int bidx = e; bidx < nblk; bidx += 2) {
-        const int g = bidx / cbn, cb = bidx - g * cbn;
+      for (int ls = 0; ls < nsl; ++ls) {
+        int cc, x0, y0, n;
+        if (!slab_origin(gi, nb, ls, &cc, &x0, &y0, &n)) break;
+        const int buf = a.nstg == 2 ? (ls & 1) : 0;
+        const int g = ls / spt, sb = ls - g * spt;
         float v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * a.G * a.NB + g * a.NB + cb * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * a.G * a.NB + g * a.NB + sb * 64 + e * 32);
         tmem_ld<16, false>(taddr, v);
         tmem_ld<16, false>(taddr + 16, v + 16);
-        uint4 rcur[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rcur[j] = rres[j];
-        const size_t off_cur = off;
-        const bool ok_cur = ok;
-        ok = locate(bidx + 2, &off);                 // issue the next block's residual loads before touching this block's data
-        if (ok && a.res) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rres[j] = __ldg(reinterpret_cast<const uint4*>(a.res + off) + j);
-        }
         tmem_ld_wait();
-        if (ok_cur) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cb * 32 + i));
-            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-          }
-          if (a.res) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&rcur[j]);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) v[8 * j + k] += __bfloat162float(rb[k]);
-            }
-          }
-          if (a.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          uint4* op = reinterpret_cast<uint4*>(a.out + off_cur);
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + sb * 64 + e * 32 + i));
+          v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+        }
+        if (a.res) {
+          mbar_wait(&sh->res_full[buf], (rpar >> buf) & 1u);
+          rpar ^= 1u << buf;
+          const uint8_t* rrow = sRes + buf * EC_STG + m * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack2(v[8 * j], v[8 * j + 1]); o.y = pack2(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack2(v[8 * j + 4], v[8 * j + 5]); o.w = pack2(v[8 * j + 6], v[8 * j + 7]);
-            op[j] = o;
+            const uint4 rv = *reinterpret_cast<const uint4*>(rrow + (((uint32_t)(e * 4 + j) ^ swz) << 4));
+            const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&rv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[8 * j + k] += __bfloat162float(rb[k]);
           }
         }
+        if (a.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        uint8_t* orow = sOut + buf * EC_STG + m * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack2(v[8 * j], v[8 * j + 1]); o.y = pack2(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack2(v[8 * j + 4], v[8 * j + 5]); o.w = pack2(v[8 * j + 6], v[8 * j + 7]);
+          *reinterpret_cast<uint4*>(orow + (((uint32_t)(e * 4 + j) ^ swz) << 4)) = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the TMA store
+        epi_bar();                                                      // A: the slab is staged, the residual buffer has been read
+        if (leader) {
+          if (a.transposed) tma_store_4d(sOut + buf * EC_STG, &maps.out, cc, y0, x0, n);
+          else tma_store_4d(sOut + buf * EC_STG, &maps.out, cc, x0, y0, n);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (a.res) load_res(gi, nb, ls + a.nstg, buf);
+          // the buffer the NEXT slab writes must have been read by its store: with two buffers that is the store before this one
+          if (a.nstg == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        epi_bar();                                                      // B: the other staging buffer is free
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->t_empty[set]);
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores have been written before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -318,17 +345,35 @@ extern "C" int b2p_encoder_conv_bf16(const void* in_nhwc, int32_t N, int32_t H, 
   memset(&a, 0, sizeof(a));
   memset(&m, 0, sizeof(m));
   a.N = N; a.H = (H - 1) / stride + 1; a.W = (W - 1) / stride + 1;
-  a.Cin = Cin; a.Cout = Cout; a.NB = Cout < 256 ? Cout : 256;
+  a.Cin = Cin; a.Cout = Cout;
   a.relu = relu; a.bias = bias; a.res = reinterpret_cast<const __nv_bfloat16*>(res_nhwc); a.out = reinterpret_cast<__nv_bfloat16*>(out_nhwc);
   a.transposed = (stride == 1 && a.H <= 8) ? 1 : 0;
   a.tiles_x = a.transposed ? (a.W + 15) / 16 : (a.W + 7) / 8; a.tiles_y = a.transposed ? (a.H + 7) / 8 : (a.H + 15) / 16;
   const long long nt = (long long)N * a.tiles_x * a.tiles_y;
   if (nt >= (1LL << 30)) return B2P_ERR_INVALID_ARG;
   a.n_tiles = (int)nt;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  a.n_maps = (ksize == 3 && stride == 2) ? 4 : 1;
+  // tiles per item (G), channel-block width (NB), accumulator sets, ring depths.  Shared memory: na patch slots of 23 KB + nw weight slots of
+  // NB * 128 B + 2 nstg staging slabs of 16 KB <= ~224 KB; TMEM: sets * G * NB <= 512 columns.
+  // (measured on 256 frames, 64 -> 64: G = 1: 0.62 ms, G = 2: 0.44, G = 4: 0.44, one accumulator set: 0.60, the 72 KB filter resident with a
+  //  3-patch ring: 0.54 — what counts for that HBM-bound layer is the input bytes in flight and the overlapped epilogue)
+  auto configure = [&](int nb, int g) {
+    a.NB = nb; a.G = g; a.na = 4;
+    if (nb == 256) { a.sets = g == 1 ? 2 : 1; a.nw = 3; a.nstg = 1; }      // 94 + 96 + 32 KB
+    else { a.sets = 2; a.nw = 4; a.nstg = 2; }                              // 94 + 32 / 64 + 64 KB
+    a.n_groups = (a.n_tiles + a.G - 1) / a.G;
+    return (long long)a.n_groups * (Cout / a.NB);
+  };
+  long long items = configure(Cout < 256 ? Cout : 256, a.n_maps == 1 ? 2 : 1);
+  // few frames (a closed-loop tick encodes ONE): the default items would leave most SMs idle and each CTA with a long serial K loop, so
+  // split finer — one tile per item first, then narrower channel blocks — until the launch covers the chip
+  while (items < sms && (a.G > 1 || a.NB > 64)) items = a.G > 1 ? configure(a.NB, 1) : configure(a.NB / 2, 1);
   const char* base = reinterpret_cast<const char*>(in_nhwc);
   const cuuint32_t box[4] = {64, EC_PW, EC_PH, 1}, estr[4] = {1, 1, 1, 1};
   if (stride == 1) {
-    a.n_maps = 1; a.n_taps = 9; a.map_dx[0] = -1; a.map_dy[0] = -1;
+    a.n_taps = 9; a.map_dx[0] = -1; a.map_dy[0] = -1;
     for (int t = 0; t < 9; ++t) { a.tap_map[t] = 0; a.tap_off[t] = (a.transposed ? (t % 3) * EC_PW + t / 3 : (t / 3) * EC_PW + t % 3) * 128; a.tap_w[t] = t; }
     // transposed: the map lists H before W, so the {64, 10, 18} box lands [column][row][channel]
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(a.transposed ? H : W), (cuuint64_t)(a.transposed ? W : H), (cuuint64_t)N};
@@ -337,8 +382,7 @@ extern "C" int b2p_encoder_conv_bf16(const void* in_nhwc, int32_t N, int32_t H, 
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return B2P_ERR_INVALID_ARG;
   } else {
     // parity sub-images: map (py, px) holds the input pixels (2 yy + py, 2 xx + px)
-    const int np = ksize == 3 ? 4 : 1;
-    a.n_maps = np;
+    const int np = a.n_maps;
     for (int p = 0; p < np; ++p) {
       const int py = p >> 1, px = p & 1;
       const int Hp = (H - py + 1) / 2, Wp = (W - px + 1) / 2;
@@ -368,25 +412,20 @@ extern "C" int b2p_encoder_conv_bf16(const void* in_nhwc, int32_t N, int32_t H, 
     if (enc(&m.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims, strides, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return B2P_ERR_INVALID_ARG;
   }
-  // tiles per item, accumulator sets, ring depths (shared memory: na patch slots of 23 KB + nw weight slots of NB * 128 B <= ~224 KB; TMEM: sets * G * NB <= 512)
-  if (a.n_maps == 1) {
-    if (a.NB == 64) { a.G = 4; a.sets = 2; a.na = 8; a.nw = 4; }
-    else if (a.NB == 128) { a.G = 2; a.sets = 2; a.na = 4; a.nw = 4; }
-    else { a.G = 2; a.sets = 1; a.na = 4; a.nw = 3; }
-  } else {
-    a.G = 1; a.sets = 2;
-    if (a.NB <= 128) { a.na = 8; a.nw = 2; } else { a.na = 4; a.nw = 3; }
+  {  // output / residual: one 64-channel slab of a tile per box, same tile orientation as the input patches
+    const int OH = a.H, OW = a.W;
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)(a.transposed ? OH : OW), (cuuint64_t)(a.transposed ? OW : OH), (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)(a.transposed ? OW : 1) * Cout * 2, (cuuint64_t)(a.transposed ? 1 : OW) * Cout * 2, (cuuint64_t)OH * OW * Cout * 2};
+    cuuint32_t obox[4] = {64, 8, 16, 1}, oestr[4] = {1, 1, 1, 1};
+    if (enc(&m.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out_nhwc, dims, strides, obox, oestr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return B2P_ERR_INVALID_ARG;
+    if (res_nhwc && enc(&m.res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(res_nhwc), dims, strides, obox, oestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return B2P_ERR_INVALID_ARG;
   }
-  { static int g_over = -1; if (g_over < 0) { const char* e = getenv("B2P_ENC_G"); g_over = e ? atoi(e) : 0; }
-    if (g_over > 0 && a.n_maps == 1 && g_over * a.NB <= 512 && 2 * g_over <= EC_MAX_A) { a.G = g_over; a.sets = (2 * g_over * a.NB <= 512) ? 2 : 1; a.na = 2 * g_over; } }
-  a.n_groups = (a.n_tiles + a.G - 1) / a.G;
-  const long long items = (long long)a.n_groups * (Cout / a.NB);
   if (items >= (1LL << 31)) return B2P_ERR_INVALID_ARG;
   a.n_items = (int)items;
-  const size_t smem = (size_t)a.na * EC_ASLOT + (size_t)a.nw * a.NB * 128 + sizeof(EncShared) + 1024;
+  const size_t smem = (size_t)a.na * EC_ASLOT + (size_t)a.nw * a.NB * 128 + (size_t)2 * a.nstg * EC_STG + sizeof(EncShared) + 1024;
   if (smem > 227 * 1024 || a.na > EC_MAX_A || a.nw > EC_MAX_W || a.na % (a.G * a.n_maps)) return B2P_ERR_INVALID_ARG;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {     // function attributes are per device
     B2P_CUDA_TRY(cudaFuncSetAttribute(enc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

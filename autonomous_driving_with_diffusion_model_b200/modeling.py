@@ -346,6 +346,10 @@ class ImageEncoder(_Tree):
             with torch.no_grad():
                 if torch.cuda.is_current_stream_capturing():
                     return self._forward_fused(img)
+                if self.compute_dtype == "bf16" and self.bf16_body == "tcgen05" and img.shape[0] >= 16:
+                    # many frames: the 37 launches are GPU-bound, and replaying a graph would first copy the whole batch into its static input
+                    # (0.5 ms for 256 frames); the graph is for the per-tick latency of a few frames
+                    return self._forward_fused(img)
                 return self._forward_graphed(img)
         return self._forward_plain(img)
 

@@ -51,12 +51,14 @@ for (n, h, w_, cin, cout, k, s) in cases:
         bad += err > tol
         print(f"N={n} {h}x{w_} {cin}->{cout} k{k} s{s} res={int(use_res)} relu={relu}: max err {err:.3e} (ref max {r.abs().max().item():.2f}){flag}")
 print("FAILED" if bad else "all cases match")
+only = int(os.environ.get("ENC_ONLY", "0"))
 
 # timing on 256 frames, per layer shape of ResNet-34 at 256 x 900 input
 if len(sys.argv) > 1 and sys.argv[1] == "time":
     N = 256
     for (h, w_, cin, cout, k, s, count) in [(64, 225, 64, 64, 3, 1, 6), (64, 225, 64, 128, 3, 2, 1), (64, 225, 64, 128, 1, 2, 1), (32, 113, 128, 128, 3, 1, 7), (32, 113, 128, 256, 3, 2, 1),
                                             (16, 57, 256, 256, 3, 1, 11), (16, 57, 256, 512, 3, 2, 1), (8, 29, 512, 512, 3, 1, 5)]:
+        if only and (cin != only or cout != only): continue
         x = torch.randn(N, h, w_, cin, device=dev).to(torch.bfloat16)
         w = (torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5).to(torch.bfloat16)
         b = torch.randn(cout, device=dev)
@@ -76,5 +78,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "time":
         for _ in range(5): F.conv2d(xc, wc, bc, s, 1 if k == 3 else 0)
         e1.record(); torch.cuda.synchronize()
         ms_t = e0.elapsed_time(e1) / 5
+        for _ in range(2): run(x, w, b, None, k, s, 1)
+        e0.record()
+        for _ in range(5): run(x, w, b, None, k, s, 1)
+        e1.record(); torch.cuda.synchronize()
+        ms_nores = e0.elapsed_time(e1) / 5
         fl = 2.0 * N * oh * ow * cout * cin * k * k
-        print(f"{h}x{w_} {cin}->{cout} k{k} s{s} (x{count} in ResNet-34): {ms:.3f} ms = {fl / ms / 1e9:.0f} TFLOP/s | torch conv2d {ms_t:.3f} ms = {fl / ms_t / 1e9:.0f} TFLOP/s")
+        print(f"{h}x{w_} {cin}->{cout} k{k} s{s} (x{count} in ResNet-34): {ms:.3f} ms = {fl / ms / 1e9:.0f} TFLOP/s (no residual: {ms_nores:.3f} ms) | torch conv2d {ms_t:.3f} ms = {fl / ms_t / 1e9:.0f} TFLOP/s")
