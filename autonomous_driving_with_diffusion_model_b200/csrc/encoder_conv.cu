@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_conv_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch_dependents();                   // the next convolution may set up (barriers, TMEM, first weight stages) as SMs free up
   const uint32_t tmem_base = sh->tmem_base;
   const int chunks = a.Cin >> 6;
   const int ppc = a.G * a.n_maps;                  // patches per K chunk of an item
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_conv_kernel(const __grid_co
     if (elect_one()) {
       // =============================== patch producer ===============================
       for (int m = 0; m < a.n_maps; ++m) prefetch_tmap(&maps.a[m]);
+      griddep_wait();                            // the input is the previous kernel's output
       int slot = 0; uint32_t par = 0;
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const int gi = item % a.n_groups;
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_conv_kernel(const __grid_co
     const int th = a.transposed ? 8 : 16, tw = a.transposed ? 16 : 8;
     const int spt = a.NB >> 6, nsl = a.G * spt;                    // slabs per tile / per item
     const bool leader = warp == 4 && lane == 0;
+    griddep_wait();                              // residual reads and output writes are ordered behind the previous kernel
     const uint32_t swz = (uint32_t)(m & 7);
     uint32_t rpar = 0u;                                            // bit b: phase parity of res_full[b]
     int it = 0;
@@ -433,6 +436,12 @@ extern "C" int b2p_encoder_conv_bf16(const void* in_nhwc, int32_t N, int32_t H, 
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int grid = a.n_items < sms ? a.n_items : sms;
-  enc_conv_kernel<<<grid, EC_THREADS, smem, (cudaStream_t)stream>>>(m, a);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(EC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // weights do not depend on the previous layer: their first stages overlap its tail
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, enc_conv_kernel, m, a);
 }
