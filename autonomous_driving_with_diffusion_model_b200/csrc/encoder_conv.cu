@@ -369,7 +369,10 @@ extern "C" int b2p_encoder_conv_bf16(const void* in_nhwc, int32_t N, int32_t H, 
     a.n_groups = (a.n_tiles + a.G - 1) / a.G;
     return (long long)a.n_groups * (Cout / a.NB);
   };
-  long long items = configure(Cout < 256 ? Cout : 256, a.n_maps == 1 ? 2 : 1);
+  // widest channel block: 128 with two tiles per item (256 TMEM columns, two sets: the epilogue overlaps the next item's MMAs; 256 -> 256: 0.26 -> 0.24 ms
+  // against 256-wide blocks with one set) — except for the 3x3/2 layers, whose single-tile items would stream the weights twice as often (0.26 -> 0.41 ms)
+  const int nbmax = a.n_maps == 1 ? 128 : 256;
+  long long items = configure(Cout < nbmax ? Cout : nbmax, a.n_maps == 1 ? 2 : 1);
   // few frames (a closed-loop tick encodes ONE): the default items would leave most SMs idle and each CTA with a long serial K loop, so
   // split finer — one tile per item first, then narrower channel blocks — until the launch covers the chip
   while (items < sms && (a.G > 1 || a.NB > 64)) items = a.G > 1 ? configure(a.NB, 1) : configure(a.NB / 2, 1);
