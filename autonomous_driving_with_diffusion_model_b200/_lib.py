@@ -72,6 +72,7 @@ SYMBOLS = {
     "b2p_set_chain": (C.c_int, [_VP, C.c_int]),
     "b2p_preprocess_frames": (C.c_int, [_VP, _VP, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), _VP]),
     "b2p_encoder_stem_bf16": (C.c_int, [_VP, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP]),
+    "b2p_encoder_stem_pool_bf16": (C.c_int, [_VP, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP]),
     "b2p_maxpool3x3s2_nhwc_bf16": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "b2p_encoder_conv_bf16": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "b2p_unet_forward": (C.c_int, [_VP, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP]),

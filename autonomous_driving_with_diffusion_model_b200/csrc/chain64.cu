@@ -133,7 +133,7 @@ __device__ __forceinline__ void group_norm8_mish(float (&v)[CH_EC], const float*
 template <int NSPLIT>
 __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_constant__ ChainArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align1024(smem_raw);
   ChainShared* sh = reinterpret_cast<ChainShared*>(smem + CH_OFF_MISC);
   uint8_t* wbuf = smem + CH_OFF_W;
   float (*headp)[8][TC_M] = reinterpret_cast<float (*)[8][TC_M]>(smem + CH_OFF_HEADP);

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
   constexpr int EC = TN / 4;                        // columns per epilogue thread
   constexpr int BT_BYTES = TN * TC_K * 2;           // one tap's weight tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align1024(smem_raw);
   TcShared* sh = reinterpret_cast<TcShared*>(smem + (TN == 64 ? a.ring : a.ring + 4 * 1024));
 
   const int T = a.T;

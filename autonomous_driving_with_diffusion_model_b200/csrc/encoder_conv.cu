@@ -94,7 +94,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 __global__ void __launch_bounds__(EC_THREADS, 1) enc_conv_kernel(const __grid_constant__ EncMaps maps, const EncArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;
   const int wslot_bytes = a.NB * 128;
   uint8_t* sW = smem + a.na * EC_ASLOT;

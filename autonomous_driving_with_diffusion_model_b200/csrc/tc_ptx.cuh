@@ -14,6 +14,10 @@ constexpr int TC_UMMA_K = 16;
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// First 1024-byte boundary of the dynamic shared memory (swizzled TMA / UMMA tiles need it).  Pointer arithmetic on the __shared__ array, NOT an integer
+// round trip: after a uintptr_t cast nvcc no longer knows the address space and every shared-memory access of the kernel becomes a generic LD.E / ST.E.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

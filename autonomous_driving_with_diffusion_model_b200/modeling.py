@@ -233,8 +233,9 @@ class ImageEncoder(_Tree):
         bias = (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
         return image, bias
 
-    def _stem_bf16(self, img: torch.Tensor, image: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-        """conv1 + bn1 + relu + maxpool (modeling/resnet.py:279-282) by the hand-written kernels of csrc/encoder_stem.cu -> bf16 channels-last."""
+    def _stem_bf16(self, img: torch.Tensor, image: torch.Tensor, bias: torch.Tensor, fused: bool = True) -> torch.Tensor:
+        """conv1 + bn1 + relu + maxpool (modeling/resnet.py:279-282) by the hand-written kernels of csrc/encoder_stem.cu -> bf16 channels-last.
+        ``fused``: one kernel (conv1's output never reaches HBM); otherwise the conv kernel followed by the pool kernel (same bits)."""
         from . import _lib
         import ctypes as C
         n, c, h, w = img.shape
@@ -242,12 +243,16 @@ class ImageEncoder(_Tree):
             raise ValueError("the encoder expects [N,3,H,W] images")
         oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         ph, pw = (oh - 1) // 2 + 1, (ow - 1) // 2 + 1
-        y = torch.empty((n, 64, oh, ow), dtype=torch.bfloat16, device=img.device, memory_format=torch.channels_last)
         x = torch.empty((n, 64, ph, pw), dtype=torch.bfloat16, device=img.device, memory_format=torch.channels_last)
         lib = _lib.load()
         stream = C.c_void_p(torch.cuda.current_stream(img.device).cuda_stream)
         sn, sc, sh, sw = img.stride()
         with torch.cuda.device(img.device):
+            if fused and min(sc, sh, sw) >= 0:
+                _lib.check(lib.b2p_encoder_stem_pool_bf16(_lib.ptr(img), sn, sc, sh, sw, n, h, w, _lib.ptr(image), _lib.ptr(bias), _lib.ptr(x), stream),
+                           None, "b2p_encoder_stem_pool_bf16")
+                return x
+            y = torch.empty((n, 64, oh, ow), dtype=torch.bfloat16, device=img.device, memory_format=torch.channels_last)
             _lib.check(lib.b2p_encoder_stem_bf16(_lib.ptr(img), sn, sc, sh, sw, n, h, w, _lib.ptr(image), _lib.ptr(bias), _lib.ptr(y), stream),
                        None, "b2p_encoder_stem_bf16")
             _lib.check(lib.b2p_maxpool3x3s2_nhwc_bf16(_lib.ptr(y), _lib.ptr(x), n, oh, ow, 64, stream), None, "b2p_maxpool3x3s2_nhwc_bf16")

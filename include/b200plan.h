@@ -144,6 +144,11 @@ int b2p_preprocess_frames(const uint8_t* frames_nhwc, float* out_nhwc, int64_t n
  * out: bf16 [N, OH, OW, 64] (channels-last), OH = (H - 1) / 2 + 1, OW likewise, 16-byte aligned.  bf16 products, fp32 accumulation. */
 int b2p_encoder_stem_bf16(const float* img, int64_t stride_n, int64_t stride_c, int64_t stride_h, int64_t stride_w, int32_t N, int32_t H,
                           int32_t W, const void* weight_image, const float* bias, void* out_nhwc_bf16, void* stream);
+/* conv1 + bn1 + relu + maxpool(3, 2, 1) in one kernel (modeling/resnet.py:279-282): same arguments as b2p_encoder_stem_bf16, but out is the POOLED
+ * tensor bf16 [N, PH, PW, 64] with PH = ((H - 1) / 2) / 2 + 1, PW likewise; bit-identical to b2p_encoder_stem_bf16 followed by
+ * b2p_maxpool3x3s2_nhwc_bf16 (conv1's 1.9 GB output for 256 frames never reaches HBM).  Strides must be non-negative. */
+int b2p_encoder_stem_pool_bf16(const float* img, int64_t stride_n, int64_t stride_c, int64_t stride_h, int64_t stride_w, int32_t N, int32_t H,
+                               int32_t W, const void* weight_image, const float* bias, void* out_nhwc_bf16, void* stream);
 /* MaxPool2d(kernel 3, stride 2, padding 1) on bf16 [N,H,W,C] -> [N,(H-1)/2+1,(W-1)/2+1,C], C a multiple of 8, 16-byte aligned. */
 int b2p_maxpool3x3s2_nhwc_bf16(const void* in, void* out, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
 /* ---- image-encoder body (bf16 mode): one convolution of ResNet-34's layer1..layer4 with its BatchNorm folded in, the residual add and the

@@ -994,7 +994,7 @@ def test_image_encoder_bf16_handwritten_body_matches_the_cudnn_body():
         model.perception.set_precision("fp32")
 
 
-@pytest.mark.parametrize("shape", [(3, 37, 53), (2, 64, 130), (1, 256, 900)])
+@pytest.mark.parametrize("shape", [(3, 37, 53), (2, 64, 130), (1, 256, 900), (2, 7, 5), (1, 121, 123)])
 @pytest.mark.parametrize("channels_last", [False, True])
 def test_encoder_stem_kernels_vs_torch(shape, channels_last):
     """csrc/encoder_stem.cu (conv1 7x7/2 + folded bn1 + relu on tcgen05, then the 3x3/2 max-pool; modeling/resnet.py:279-282) against
@@ -1011,6 +1011,8 @@ def test_encoder_stem_kernels_vs_torch(shape, channels_last):
     image, bias = enc._stem_operands()
     got = enc._stem_bf16(img, image, bias)
     assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
+    # the fused conv1 + pool kernel and the two separate kernels give the same bits
+    assert torch.equal(got, enc._stem_bf16(img, image, bias, fused=False))
     bn = enc.bn1
     scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + 1e-5)
     wf = (enc.conv1.weight.detach().float() * scale.view(-1, 1, 1, 1)).bfloat16().float()
