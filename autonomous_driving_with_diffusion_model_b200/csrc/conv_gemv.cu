@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
   // dynamic shared memory carve-up.  Every region is 32-BYTE aligned: a 16-byte cp.async whose shared-memory destination is 16 but
   // not 32 bytes aligned makes L2 return every 32-byte sector TWICE (measured: scripts/lts_bytes_bench.cu, profiles/r02_lts_bytes_bench.csv;
   // the dynamic block starts after the 3024-byte static block, which is what doubled lts__t_bytes of this path in round 1).
-  float* Wsm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dyn) + 127) & ~(uintptr_t)127);   // [NC][Keff]
+  // (pointer arithmetic on the __shared__ array, not a uintptr_t round trip: after an integer cast nvcc loses the address space and the dot-product
+  //  loop reads its operands with generic LD.E.128 instead of LDS.128)
+  float* Wsm = dyn + (((128u - ((unsigned)__cvta_generic_to_shared(dyn) & 127u)) & 127u) >> 2);   // [NC][Keff]
   float* RWsm = Wsm + gv_pad4(NC * Keff);             // [NC][RCin]
   float* X = RWsm + gv_pad4(NC * RCin);               // [Lin + 1][Cin], last row zero (padding taps read it)
   float* RX = X + gv_pad4((Lin + 1) * Cin);           // [L][RCin]
