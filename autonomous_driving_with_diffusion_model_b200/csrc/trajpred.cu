@@ -1,5 +1,6 @@
 // TrajPredict (classifier-guidance state predictor) forward, and the whole classifier-guidance update with an
-// ANALYTIC backward pass (K7 in SURVEY.md Appendix C).  One CTA per trajectory; all activations of the 2-layer
+// ANALYTIC backward pass (K7 in SURVEY.md Appendix C).  One CTA per trajectory; every linear layer (forward and backward) runs on the
+// tensor cores (mma.sync 3xTF32, see linear()); all activations of the 2-layer
 // post-LN transformer (seq 15, d 64, 4 heads, SiLU FFN 256) stay in shared memory between forward and backward.
 // Replaces: modeling/helpers.py:22-59 (TrajPredict.forward), interact.py:154-160 (state/model_output assembly),
 //           control/guidance_loss.py:10-22 (TargetGuidance, per-sample map of the B=1 rule),
@@ -48,62 +49,87 @@ struct TpSmem {
 };
 static_assert(sizeof(TpSmem) <= 110 * 1024, "two TrajPredict CTAs must fit one SM");
 
-// Y[s][n] = sum_k X[s][k] * Wt[k][n] + b[n].  The weights are read straight from L2 (the 400 KB of weights do not fit beside the
-// saved activations), so what a linear layer costs is L2 round trips: K is therefore SPLIT ACROSS THE LANES of a warp (8 ways
-// for N = 64, 2 ways for N = 192 / 256) and every thread has ALL of its K / KS weights in flight at once (<= 32 loads) — one
-// or two round trips per layer instead of K / 16.  A warp owns 32 / KS output columns; thread (kq, n) accumulates the
-// granules g = j * KS + kq (4 consecutive k each: the KS lanes of a column read consecutive float4 of X, conflict-free), the
-// partial sums are combined by xor shuffles in a fixed order (deterministic), lanes kq == 0 write the result.
+// Y[s][n] = sum_k X[s][k] * Wt[k][n] + b[n] on the tensor cores: the <= 16 token rows of a trajectory are exactly one m16 tile, so every
+// linear layer of the forward AND the backward pass is a row of mma.sync.m16n8k8 TF32 tiles — in the 3xTF32 form (operands split into a
+// TF32 high part and a TF32 residual, products hi*hi + lo*hi + hi*lo accumulated in fp32: fp32-class accuracy, the guidance gradient keeps
+// its 1e-4 parity).  A warp owns N / 8 / 16 (rounded up) column tiles of 8 outputs.  The weights are read straight from L2 (the 400 KB do
+// not fit beside the saved activations) as B fragments, up to 32 values per thread in flight before the first MMA (one L2 round trip per
+// 64 - 128 values of K); the activations come from shared memory as float4 (K is walked in blocks of 16 with the k index permuted inside a
+// block — lane t of a quad holds k0 + 4t .. 4t + 3 — so a row's fragment is one 16-byte load; A and B use the same permutation).
+// Rows >= S hold whatever the buffer held: an output row depends on its own input row only, and rows >= S are never stored.
+__device__ __forceinline__ uint32_t tf32_hi(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 template <bool ACCUM, int N>
 __device__ __forceinline__ void linear(const float* __restrict__ X, int ldx, const float* __restrict__ Wt, const float* __restrict__ b,
                                        float* __restrict__ Y, int ldy, int S, int K) {
-  constexpr int KS = N == 64 ? 8 : 2;
-  constexpr int NL = 32 / KS;                    // output columns per warp
-  constexpr int NW = N / NL;                     // warps with work (16, 12 or 16)
-  static_assert(NW <= TP_NT / 32 && N % NL == 0, "linear: tile mapping");
+  constexpr int NT = N / 8;                        // column tiles
+  constexpr int TPW = (NT + 15) / 16;              // tiles per warp: 1 (N = 64), 2 (N = 192, 256)
+  constexpr int GB = TPW == 1 ? 8 : 4;             // K blocks of 16 whose weights are fetched together (<= 32 values per thread)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp >= NW) return;
-  const int kq = lane / NL, n = warp * NL + (lane % NL);
-  const int NG = K / (4 * KS);                   // granules per thread: <= 8 (K <= 256 with KS = 8, K = 64 with KS = 2)
-  float w[32];
+  const int g = lane >> 2, t = lane & 3;
+  const int tile0 = warp * TPW;
+  if (tile0 >= NT) return;
+  const int ntl = NT - tile0 < TPW ? NT - tile0 : TPW;     // warp-uniform
+  float acc[TPW][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (j < NG) {
-      const float* wp = Wt + (size_t)((j * KS + kq) * 4) * N + n;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) w[j * 4 + e] = __ldg(wp + (size_t)e * N);
-    }
-  }
-  const float b0 = b ? __ldg(b + n) : 0.f;
+  for (int i = 0; i < TPW; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  const float* xr0 = X + g * ldx + 4 * t;
+  const float* xr1 = X + (g + 8) * ldx + 4 * t;
+  const int nblk = K >> 4;
 #pragma unroll 1
-  for (int r0 = 0; r0 < TP_MAXS; r0 += 8) {
-    float acc[8];
+  for (int kb0 = 0; kb0 < nblk; kb0 += GB) {
+    float w[TPW][GB][4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int i = 0; i < TPW; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < NG) {
+      for (int kb = 0; kb < GB; ++kb)
+        if (i < ntl && kb0 + kb < nblk) {
+          const float* wp = Wt + (size_t)((kb0 + kb) * 16 + 4 * t) * N + (tile0 + i) * 8 + g;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float4 x = *reinterpret_cast<const float4*>(X + (r0 + r) * ldx + (j * KS + kq) * 4);
-          acc[r] = fmaf(x.x, w[j * 4], acc[r]);
-          acc[r] = fmaf(x.y, w[j * 4 + 1], acc[r]);
-          acc[r] = fmaf(x.z, w[j * 4 + 2], acc[r]);
-          acc[r] = fmaf(x.w, w[j * 4 + 3], acc[r]);
+          for (int j = 0; j < 4; ++j) w[i][kb][j] = __ldg(wp + (size_t)j * N);
+        }
+#pragma unroll
+    for (int kb = 0; kb < GB; ++kb) {
+      if (kb0 + kb < nblk) {
+        const float4 x0 = *reinterpret_cast<const float4*>(xr0 + (kb0 + kb) * 16);
+        const float4 x1 = *reinterpret_cast<const float4*>(xr1 + (kb0 + kb) * 16);
+        const float xa[2][4] = {{x0.x, x1.x, x0.y, x1.y}, {x0.z, x1.z, x0.w, x1.w}};   // fragment order a0..a3 of the two k8 steps
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t ah[4], al[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { ah[q] = tf32_hi(xa[h][q]); al[q] = tf32_hi(xa[h][q] - __uint_as_float(ah[q])); }
+#pragma unroll
+          for (int i = 0; i < TPW; ++i)
+            if (i < ntl) {
+              const float b0f = w[i][kb][2 * h], b1f = w[i][kb][2 * h + 1];
+              const uint32_t b0h = tf32_hi(b0f), b1h = tf32_hi(b1f);
+              const uint32_t b0l = tf32_hi(b0f - __uint_as_float(b0h)), b1l = tf32_hi(b1f - __uint_as_float(b1h));
+              mma_tf32(acc[i], al, b0h, b1h);      // small terms first
+              mma_tf32(acc[i], ah, b0l, b1l);
+              mma_tf32(acc[i], ah, b0h, b1h);
+            }
         }
       }
     }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-#pragma unroll
-      for (int o = NL; o < 32; o <<= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-    }
-    if (kq == 0) {
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r0 + r < S) { if (ACCUM) Y[(r0 + r) * ldy + n] += acc[r] + b0; else Y[(r0 + r) * ldy + n] = acc[r] + b0; }
-    }
   }
+#pragma unroll
+  for (int i = 0; i < TPW; ++i)
+    if (i < ntl) {
+      const int n = (tile0 + i) * 8 + 2 * t;
+      const float bb0 = b ? __ldg(b + n) : 0.f, bb1 = b ? __ldg(b + n + 1) : 0.f;
+      if (g < S) {
+        float* y = Y + g * ldy + n;
+        if (ACCUM) { y[0] += acc[i][0] + bb0; y[1] += acc[i][1] + bb1; } else { y[0] = acc[i][0] + bb0; y[1] = acc[i][1] + bb1; }
+      }
+      if (g + 8 < S) {
+        float* y = Y + (g + 8) * ldy + n;
+        if (ACCUM) { y[0] += acc[i][2] + bb0; y[1] += acc[i][3] + bb1; } else { y[0] = acc[i][2] + bb0; y[1] = acc[i][3] + bb1; }
+      }
+    }
 }
 
 // y = LN(x) per row of 64; one warp per row.  Saves the normalised value and rstd when xh != null.
