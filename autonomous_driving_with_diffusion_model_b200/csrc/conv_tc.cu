@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     // The weights do not depend on the previous layer: their TMA loads for the first ring pass are issued BEFORE the
     // grid-dependency wait and overlap the tail of the preceding kernel; only the activation loads wait for it.
     const int mc_sub = mcast ? a.samples_per_tile / CL : 0, mc_bytes = mcast ? A_BYTES / CL : 0;   // multicast slices (off the hot path: once)
+    const uint64_t pol_w = l2_policy_evict_last(), pol_a = l2_policy_evict_first();
     auto issue = [&](int it, int s, bool do_w, bool do_a) {   // s = it % stages, tracked by the callers (no runtime division)
       uint8_t* st = smem + s * stage_bytes;
       uint8_t* sb = st + NSPLIT * A_BYTES;
@@ -275,7 +276,10 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
         } else
 #pragma unroll
         for (int h = 0; h < NSPLIT; ++h) {
-          if (res_phase) tma_load_2d(sb + h * T * BT_BYTES, &maps.rw[h], &sh->full[s], kglob, n0);
+          if (a.w_hint) {
+            if (res_phase) tma_load_2d_hint(sb + h * T * BT_BYTES, &maps.rw[h], &sh->full[s], kglob, n0, pol_w);
+            else tma_load_3d_hint(sb + h * T * BT_BYTES, &maps.w[h], &sh->full[s], kglob, n0, a.tap0, pol_w);
+          } else if (res_phase) tma_load_2d(sb + h * T * BT_BYTES, &maps.rw[h], &sh->full[s], kglob, n0);
           else tma_load_3d(sb + h * T * BT_BYTES, &maps.w[h], &sh->full[s], kglob, n0, a.tap0);
         }
       }
@@ -285,6 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
         for (int h = 0; h < NSPLIT; ++h) {
           const CUtensorMap* mp = res_phase ? &maps.r[src][h] : &maps.a[src][h];
           if (mcast) tma_load_3d_mc(st + h * A_BYTES + lrank * mc_bytes, mp, &sh->full[s], c0, 0, b0 + lrank * mc_sub, cmask);
+          else if (a.w_hint == 2) tma_load_3d_hint(st + h * A_BYTES, mp, &sh->full[s], c0, 0, b0, pol_a);
           else tma_load_3d(st + h * A_BYTES, mp, &sh->full[s], c0, 0, b0);
         }
       }
@@ -783,6 +788,7 @@ static int tc_fail(int line, const TcArgs& a, const char* what) {
 int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStream_t s) {
   TcArgs a = a_in;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("B2P_TC_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
+  { static int wh = -1; if (wh < 0) { const char* e = getenv("B2P_TC_WHINT"); wh = e ? atoi(e) : 1; } a.w_hint = wh; }
 #ifdef B2P_TC_TRACE
   a.dbg |= (tc_trace_launch++ & 8191) << 8;
 #endif

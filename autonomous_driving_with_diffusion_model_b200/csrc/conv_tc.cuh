@@ -49,6 +49,7 @@ struct TcArgs {
   int ring;               // set by launch_conv_tc: bytes of the operand ring in dynamic shared memory
   int stages;             // set by launch_conv_tc: ring stages = min(ring / stage bytes, 8)
   int concat;             // set by launch_conv_tc (bf16x3): hi x [W_hi | W_lo] as ONE MMA of N = 2*T*tile_n; the hi*lo products get their own TMEM block
+  int w_hint;             // set by launch_conv_tc (B2P_TC_WHINT): 1 (default) = weight TMA loads carry an L2 evict_last hint (-0.5 % per iteration), 2 = and activation loads evict_first
   int dbg;                // developer bisect switch (B2P_TC_DBG): 1 = skip the TMA/MMA main loop, 2 = skip the epilogue math
 };
 
