@@ -236,6 +236,7 @@ constexpr int SP_PCOLS = 15;                           // pooled columns per str
 constexpr int SP_PATCH_ROWS = 2 * SP_ROWS + 5;         // 13 input rows
 constexpr int SP_PITCH = 208;                          // floats per staged patch row (69 * 3 = 207, padded: 8-byte aligned rows)
 constexpr int SP_PATCH_BYTES = SP_PATCH_ROWS * SP_PITCH * 4;   // 10,816
+constexpr int SP_PRE = (SP_PATCH_ROWS * 207 + ST_THREADS - 1) / ST_THREADS;   // patch values per thread (11)
 constexpr int SP_KEEP_BYTES = SP_COLS * 128;           // last conv row of the previous step: [32 columns][64 ch] bf16
 
 struct StemPoolArgs {
@@ -323,22 +324,32 @@ __global__ void __launch_bounds__(ST_THREADS, 2) stem_pool_kernel(const StemPool
     const int cc0 = 2 * SP_PCOLS * strip - 1;          // first conv column of the strip
     const float* img = a.img + (long long)n * a.sn;
     *reinterpret_cast<uint4*>(keep + tid * 16) = make_uint4(0, 0, 0, 0);   // conv row -1: nothing (256 threads x 16 B = 4 KB)
-    for (int st = st_begin > 0 ? st_begin - 1 : 0; st < st_end; ++st) {
+    const int st_first = st_begin > 0 ? st_begin - 1 : 0;
+    float pre[SP_PRE];
+    auto load_patch = [&](int step, float (&v)[SP_PRE]) {
+      const int iy0 = 2 * SP_ROWS * step - 3, ix0 = 2 * cc0 - 3;
+#pragma unroll
+      for (int j = 0; j < SP_PRE; ++j) {
+        const int i = tid + j * ST_THREADS;
+        const int pr = i / 207, rem = i - pr * 207;
+        const int pc = rem / 3, c = rem - pc * 3;
+        const int iy = iy0 + pr, ix = ix0 + pc;
+        v[j] = (i < SP_PATCH_ROWS * 207 && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) ? __ldg(img + (long long)iy * a.sh + (long long)ix * a.sw + c * a.sc) : 0.f;
+      }
+    };
+    for (int st = st_first; st < st_end; ++st) {
       const bool warm = st < st_begin;                 // the step above a segment: only its last conv row is wanted
       const int cr0 = SP_ROWS * st;                    // first conv row of the step
-      // ---- 1. stage the input patch: rows 2 cr0 - 3 .., columns 2 cc0 - 3 .. ----
-      {
-        const int iy0 = 2 * cr0 - 3, ix0 = 2 * cc0 - 3;
-        for (int i = tid; i < SP_PATCH_ROWS * 207; i += ST_THREADS) {
-          const int pr = i / 207, rem = i - pr * 207;
-          const int pc = rem / 3, c = rem - pc * 3;
-          const int iy = iy0 + pr, ix = ix0 + pc;
-          float v = 0.f;
-          if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v = __ldg(img + (long long)iy * a.sh + (long long)ix * a.sw + c * a.sc);
-          patch[pr * SP_PITCH + rem] = v;
-        }
+      // ---- 1. stage the input patch: rows 2 cr0 - 3 .., columns 2 cc0 - 3 ..  The values were fetched from global memory one step ahead (into
+      //         registers, right after the previous step's patch was staged), so their latency hides behind that step's gather / MMA / epilogue / pool ----
+      if (st == st_first) load_patch(st, pre);
+#pragma unroll
+      for (int j = 0; j < SP_PRE; ++j) {
+        const int i = tid + j * ST_THREADS;
+        if (i < SP_PATCH_ROWS * 207) patch[i + i / 207] = pre[j];      // row pitch 208 = 207 + 1
       }
       __syncthreads();
+      if (st + 1 < st_end) load_patch(st + 1, pre);
       // ---- 2. A operand: this thread's half of the 7x7x3 window of tile pixel (trow, tcol) ----
       {
         const float* p0 = patch + (2 * trow) * SP_PITCH + 6 * tcol;
