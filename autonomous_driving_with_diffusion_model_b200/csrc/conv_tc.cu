@@ -104,8 +104,10 @@ struct EpiScratch {
 // CTAs — and merged with the parallel-variance formula  M2 = sum M2_p + n_p * sum (mean_p - mean)^2, which is as accurate
 // as the reference's two-pass GroupNorm.  Parts are summed in a fixed order so all CTAs get bit-identical statistics.
 // Called by ALL threads of the CTA (contains __syncthreads / a cluster barrier).
+__device__ __forceinline__ float pow2_recip(int p) { return __uint_as_float((uint32_t)(127 - (31 - __clz(p))) << 23); }   // 1 / p for a power of two p
+
 template <int CG, int TN>
-__device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int row, int slice, int crank, int cbase, const EpiScratch& es,
+__device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, float inv_L, int row, int slice, int crank, int cbase, const EpiScratch& es,
                                                 const float* gamma, const float* beta, int tr = -1) {
 #ifdef B2P_TC_TRACE
 #define GN_T(k) do { if (tr >= 0 && threadIdx.x == 64) tc_trace[tr * 16 + (k)] = clock64(); } while (0)
@@ -118,7 +120,9 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
   constexpr int WC = CG < TN ? CG : TN;             // channels of one group inside this CTA
   constexpr int SL = WC / W;                        // slices of this CTA sharing a group
   constexpr int CN = CG / WC;                       // CTAs sharing a group
-  const float inv_np = 1.0f / (float)(W * L);       // elements of one part
+  // W, CG and L are powers of two: their reciprocals are exponent arithmetic (exact), not divisions — the divisions of the four instantiations used
+  // to be hoisted to the point right after the accumulator wait, i.e. onto the critical path of every layer
+  const float inv_np = inv_L * (1.0f / W);           // 1 / elements of one part (inv_L = 1 / L is computed once, before the accumulator wait)
   float mean[NG], m2[NG];
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
@@ -168,7 +172,7 @@ __device__ __forceinline__ void group_norm_mish(float (&v)[TN / 4], int L, int r
     mean[0] = mu; m2[0] = qs;
   }
   GN_T(13);
-  const float inv_n = 1.0f / (float)(CG * L);
+  const float inv_n = inv_L * (1.0f / CG);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     const float r = rsqrtf(m2[g] * inv_n + 1e-5f);
@@ -433,6 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     // fused head: this thread's element of the 1x1 head weights / bias, in flight during the accumulator wait
     const float hw_reg = (a.headW && (int)threadIdx.x < 64 * a.head_dim) ? __ldg(a.headW + threadIdx.x) : 0.f;
     const float hb_reg = (a.headW && (int)threadIdx.x < a.head_dim) ? __ldg(a.headB + threadIdx.x) : 0.f;
+    const float inv_L = pow2_recip(L);
     mbar_wait_sleep(&sh->tmem_full, 0);
     tc_fence_after();
     if (threadIdx.x == 64) TC_T(4);
@@ -531,10 +536,10 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
 #endif
       if (a.gn_gamma) {
         switch (a.cg) {
-          case 8: group_norm_mish<8, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
-          case 16: group_norm_mish<16, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
-          case 32: group_norm_mish<32, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
-          default: group_norm_mish<64, TN>(v, L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
+          case 8: group_norm_mish<8, TN>(v, L, inv_L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
+          case 16: group_norm_mish<16, TN>(v, L, inv_L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
+          case 32: group_norm_mish<32, TN>(v, L, inv_L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
+          default: group_norm_mish<64, TN>(v, L, inv_L, r, slice, crank, cbase, es, sh->gamma + col0, sh->beta + col0, gtr); break;
         }
       }
       const bool ok = row_ok && (l & (a.out_ldiv - 1)) == 0;   // out_ldiv is 1 or 2 (stride of the conv): masks and shifts, not divisions
