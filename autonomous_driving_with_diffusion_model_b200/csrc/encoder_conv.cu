@@ -338,7 +338,7 @@ using namespace b2p;
 extern "C" int b2p_encoder_conv_bf16(const void* in_nhwc, int32_t N, int32_t H, int32_t W, int32_t Cin, const void* w_packed, const float* bias, const void* res_nhwc,
                                      void* out_nhwc, int32_t Cout, int32_t ksize, int32_t stride, int32_t relu, void* stream) {
   if (!in_nhwc || !w_packed || !bias || !out_nhwc || N <= 0 || H < 1 || W < 1) return B2P_ERR_INVALID_ARG;
-  if (Cin < 64 || Cin % 64 || Cout < 64 || Cout % 64 || (Cout > 256 && Cout % 256)) return B2P_ERR_INVALID_ARG;
+  if (Cin < 64 || Cin % 64 || Cout < 64 || Cout % 64) return B2P_ERR_INVALID_ARG;
   if (!((ksize == 3 && (stride == 1 || stride == 2)) || (ksize == 1 && stride == 2))) return B2P_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(in_nhwc) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(out_nhwc) | reinterpret_cast<uintptr_t>(res_nhwc)) & 15) return B2P_ERR_INVALID_ARG;
   EncodeTiledFn enc = enc_get_encode();
@@ -372,7 +372,9 @@ extern "C" int b2p_encoder_conv_bf16(const void* in_nhwc, int32_t N, int32_t H, 
   // widest channel block: 128 with two tiles per item (256 TMEM columns, two sets: the epilogue overlaps the next item's MMAs; 256 -> 256: 0.26 -> 0.24 ms
   // against 256-wide blocks with one set) — except for the 3x3/2 layers, whose single-tile items would stream the weights twice as often (0.26 -> 0.41 ms)
   const int nbmax = a.n_maps == 1 ? 128 : 256;
-  long long items = configure(Cout < nbmax ? Cout : nbmax, a.n_maps == 1 ? 2 : 1);
+  int nb0 = nbmax;
+  while (Cout % nb0) nb0 >>= 1;                    // widest allowed block that divides C_out (64 always does)
+  long long items = configure(nb0, a.n_maps == 1 ? 2 : 1);
   // few frames (a closed-loop tick encodes ONE): the default items would leave most SMs idle and each CTA with a long serial K loop, so
   // split finer — one tile per item first, then narrower channel blocks — until the launch covers the chip
   while (items < sms && (a.G > 1 || a.NB > 64)) items = a.G > 1 ? configure(a.NB, 1) : configure(a.NB / 2, 1);

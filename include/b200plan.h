@@ -156,7 +156,7 @@ int b2p_maxpool3x3s2_nhwc_bf16(const void* in, void* out, int32_t N, int32_t H, 
  * in: bf16 [N,H,W,Cin] (channels-last);  ksize/stride: 3/1 (pad 1), 3/2 (pad 1) or 1/2 (pad 0, the projection shortcut);
  * w_packed: bf16 [ksize*ksize][Cout][Cin] = weight.permute(2,3,0,1) with the BatchNorm scale folded in;  bias: fp32 [Cout] (folded);
  * res: bf16 [N,OH,OW,Cout] added before the ReLU, or NULL;  out: bf16 [N,OH,OW,Cout], OH = (H-1)/stride+1, OW likewise;  relu: 0/1.
- * Cin, Cout multiples of 64 (Cout > 256: a multiple of 256); all pointers 16-byte aligned.  bf16 products, fp32 accumulation, one rounding
+ * Cin, Cout multiples of 64; all pointers 16-byte aligned.  bf16 products, fp32 accumulation, one rounding
  * of the result to bf16. */
 int b2p_encoder_conv_bf16(const void* in_nhwc, int32_t N, int32_t H, int32_t W, int32_t Cin, const void* w_packed, const float* bias, const void* res_nhwc,
                           void* out_nhwc, int32_t Cout, int32_t ksize, int32_t stride, int32_t relu, void* stream);

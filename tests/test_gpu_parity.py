@@ -941,7 +941,8 @@ def test_image_encoder_bf16_channels_last_bound(golden_dir):
     # N, H, W, C_in, C_out, ksize, stride                      (layer shapes of ResNet-34 on a 256 x 900 frame, then ragged / tiny maps)
     (3, 64, 225, 64, 64, 3, 1), (2, 32, 113, 128, 128, 3, 1), (2, 16, 57, 256, 256, 3, 1), (3, 8, 29, 512, 512, 3, 1),
     (2, 64, 225, 64, 128, 3, 2), (2, 32, 113, 128, 256, 3, 2), (3, 16, 57, 256, 512, 3, 2), (2, 64, 225, 64, 128, 1, 2), (2, 16, 57, 256, 512, 1, 2),
-    (1, 5, 3, 64, 64, 3, 1), (1, 17, 9, 64, 64, 3, 2), (5, 16, 8, 128, 64, 3, 1), (37, 8, 16, 64, 64, 3, 1), (1, 1, 1, 64, 64, 3, 1)])
+    (1, 5, 3, 64, 64, 3, 1), (1, 17, 9, 64, 64, 3, 2), (5, 16, 8, 128, 64, 3, 1), (37, 8, 16, 64, 64, 3, 1), (1, 1, 1, 64, 64, 3, 1),
+    (2, 20, 12, 192, 192, 3, 1), (2, 20, 12, 64, 320, 3, 2), (40, 33, 17, 64, 64, 3, 1)])
 @pytest.mark.parametrize("epilogue", [(False, True), (True, True), (False, False)])
 def test_encoder_conv_kernel_vs_torch(case, epilogue):
     """csrc/encoder_conv.cu (one folded convolution of ResNet-34's layer1..layer4 with bias, residual add and ReLU; modeling/resnet.py:56-102)
