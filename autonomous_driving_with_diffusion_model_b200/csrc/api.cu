@@ -807,6 +807,15 @@ int run_unet(b2p_handle_s* h, const float* x, int x_period, const float* feat, i
       if (op.temb_off >= 0) { t.temb = temb_rows + op.temb_off; t.temb_stride = h->temb_total; t.temb2 = ttab_row ? ttab_row + op.temb_off : nullptr; }
       if (op.headW != NPOS) { t.headW = P + op.headW; t.headB = P + op.headB; t.head_dim = op.head_dim; t.head_out = head_out; }
       if (op.headW == NPOS) { t.out_hi = hi_ptr(op.out); t.out_lo = lo_ptr(op.out); }   // the head layer's own output is not materialised
+      {
+        static int tma_out = -1;
+        if (tma_out < 0) { const char* e = getenv("B2P_TC_TMAOUT"); tma_out = e ? atoi(e) : 1; }
+        if (tma_out && t.out_hi && t.n_out == 1 && t.out_ldiv == 1 && !t.headW && t.out_L == t.Lrows && t.out_lmul == 1) {
+          if ((rc = tc_make_out_map(&m.o[0], t.out_hi, t.nrows, op.Cout, t.tile_n))) return h->fail(rc, "tensor map (out)");
+          if (nsplit == 2 && (rc = tc_make_out_map(&m.o[1], t.out_lo, t.nrows, op.Cout, t.tile_n))) return h->fail(rc, "tensor map (out lo)");
+          t.tma_out = 1;
+        }
+      }
       if ((rc = launch_conv_tc(m, t, nsplit, s))) return h->fail(rc, std::string("tcgen05 conv launch failed: ") + tc_last_error());
       ++*launches;
       continue;

@@ -90,6 +90,7 @@ template <int TN> struct SmemPlan {
   static constexpr int min_ctas = 1;   // TN == 16 launches are one wave of <= 148 CTAs with the deep ring (one CTA per SM): the full register file per CTA
 };
 constexpr int EPI_XCHG_BYTES = 2 * TC_M * 4 * 4;
+constexpr int EPI_STAGE_OFF = 8 * 1024;            // output staging tiles (TcArgs.tma_out) in the idle operand ring, past the slice-exchange buffer: 2 planes x 128 rows x TN x 2 B
 struct EpiScratch {
   float (*xchg)[4][TC_M];   // [pass][slice][row]: row fastest, so the lanes of a warp hit distinct banks
   float2 (*cx)[TC_M];       // [source CTA][row] = (mean, M2), written by the peers (st.async)
@@ -553,7 +554,31 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
         for (int c = 0; c < EC; ++c) v[c] += rv[c];
 
       }
-      if (ok) {
+      if (a.tma_out) {
+        // the tile leaves through shared memory: every thread drops its EC channels of its row into a staging tile per plane (the layout a TMA
+        // box {TN channels, 128 rows} has with the 32 / 64 / 128-byte swizzle of a TN x 2-byte row), thread 0 issues one TMA store per plane after
+        // the CTA-wide barrier below.  Rows past nrows are clipped by the store.  (The operand ring is idle: every MMA has retired.)
+        uint8_t* st_hi = smem + EPI_STAGE_OFF;
+        uint8_t* st_lo = st_hi + TC_M * TN * 2;
+#pragma unroll
+        for (int c = 0; c < EC; c += 4) {
+          uint2 hh, ll;
+          __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(&hh);
+          __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(&ll);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float x = v[c + i];
+            hp[i] = __float2bfloat16_rn(x);
+            lp[i] = __float2bfloat16_rn(x - __bfloat162float(hp[i]));
+          }
+          const int byte = (col0 + c) * 2;                          // byte offset inside the TN x 2-byte row
+          const int chunk = byte >> 4;                                // 16-byte chunk of the row
+          const int swz = TN == 64 ? (r & 7) : (TN == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
+          const uint32_t off = (uint32_t)(r * (TN * 2) + ((chunk ^ swz) << 4) + (byte & 15));
+          *reinterpret_cast<uint2*>(st_hi + off) = hh;
+          if (NSPLIT == 2) *reinterpret_cast<uint2*>(st_lo + off) = ll;
+        }
+      } else if (ok && !(a.dbg & 4)) {   // dbg bit 2: skip the global stores (timing experiment)
         const size_t orow = (size_t)b * a.out_L + (size_t)(l >> (a.out_ldiv >> 1)) * a.out_lmul + o;
         if (a.out_hi) {
           __nv_bfloat16* oh = a.out_hi + orow * a.Cout + gcol;
@@ -619,11 +644,17 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
       }
     }
     tc_fence_before();
+    if (a.tma_out) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the TMA store
     if (threadIdx.x == 64) { TC_T(6); TC_T(7); }
     if (threadIdx.x == 96) TC_TG(8, true);
   }
   if (mcast || wm) cluster_sync_all();             // no CTA may exit while peers can still signal its barriers / write its smem
   __syncthreads();
+  if (a.tma_out && threadIdx.x == 0 && !(a.dbg & 4)) {
+    tma_store_2d(smem + EPI_STAGE_OFF, &maps.o[0], n0, tile_m * TC_M);
+    if (NSPLIT == 2) tma_store_2d(smem + EPI_STAGE_OFF + TC_M * TN * 2, &maps.o[1], n0, tile_m * TC_M);
+    tma_store_commit_and_wait_read();            // the CTA may not exit while the store still reads its shared memory
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -677,6 +708,19 @@ int tc_make_weight_map(CUtensorMap* m, const void* base, int taps, int Cout, int
     r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
+  return r == CUDA_SUCCESS ? B2P_OK : B2P_ERR_INVALID_ARG;
+}
+
+// output rows [nrows][Cout] bf16 -> box {tile_n channels, 128 rows}, swizzle = the row width of the box (32 / 64 / 128 bytes)
+int tc_make_out_map(CUtensorMap* m, const void* base, int nrows, int Cout, int tile_n) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return B2P_ERR_NO_DEVICE;
+  cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)nrows};
+  cuuint64_t strides[1] = {(cuuint64_t)Cout * 2};
+  cuuint32_t box[2] = {(cuuint32_t)tile_n, (cuuint32_t)TC_M}, estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = tile_n == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (tile_n == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? B2P_OK : B2P_ERR_INVALID_ARG;
 }
 
@@ -806,6 +850,7 @@ int launch_conv_tc(const TcMaps& maps, const TcArgs& a_in, int nsplit, cudaStrea
   if (a.headW && (a.Cout != 64 || TN != 64 || a.head_dim > 8)) return tc_fail(__LINE__, a, "invalid layer shape");
   if (a.n_out == 2 && a.gn_gamma) return tc_fail(__LINE__, a, "GroupNorm with two outputs per row is not supported (single-use exchange barrier)");
   if (a.n_out == 2 && (a.RC[0] || a.RC[1])) return tc_fail(__LINE__, a, "invalid layer shape");
+  if (a.tma_out && (a.n_out != 1 || a.out_ldiv != 1 || a.headW || !a.out_hi || a.out_L != a.Lrows || a.out_lmul != 1)) return tc_fail(__LINE__, a, "TMA output needs output row == GEMM row");
   if (a.cluster_n < 1 || a.cluster_l < a.cluster_n || a.cluster_l % a.cluster_n || (a.cluster_n & (a.cluster_n - 1)) || (a.cluster_l & (a.cluster_l - 1))) return tc_fail(__LINE__, a, "tc_configure() was not applied");
   if ((a.Cout / TN) % a.cluster_l) return tc_fail(__LINE__, a, "invalid layer shape");
   if (a.cluster_m < 1 || (a.cluster_m & (a.cluster_m - 1)) || a.cluster_m > 8 || (a.cluster_m > 1 && (a.cluster_l != 1 || ((a.nrows + TC_M - 1) / TC_M) % a.cluster_m)))

@@ -11,6 +11,7 @@ struct TcMaps {
   CUtensorMap r[2][2];    // residual-phase activation sources
   CUtensorMap w[2];       // packed conv weights [taps*Cout, Cin]   hi/lo
   CUtensorMap rw[2];      // residual 1x1 weights [Cout, RCin]      hi/lo
+  CUtensorMap o[2];       // output rows [nrows, Cout] hi/lo, box {tile_n channels, 128 rows} (TcArgs.tma_out)
 };
 
 struct TcArgs {
@@ -49,12 +50,16 @@ struct TcArgs {
   int ring;               // set by launch_conv_tc: bytes of the operand ring in dynamic shared memory
   int stages;             // set by launch_conv_tc: ring stages = min(ring / stage bytes, 8)
   int concat;             // set by launch_conv_tc (bf16x3): hi x [W_hi | W_lo] as ONE MMA of N = 2*T*tile_n; the hi*lo products get their own TMEM block
+  int tma_out;            // set by the caller with maps.o: the tile leaves through a swizzled staging buffer and one TMA store per plane instead of per-thread
+                          // 8-byte global stores (a warp's store instruction touched 32 different lines: 5 % of an iteration at B = 256, 19 % at B = 4096).
+                          // Only for n_out == 1, out_ldiv == 1, no fused head (output row == GEMM row)
   int w_hint;             // set by launch_conv_tc (B2P_TC_WHINT): 1 (default) = weight TMA loads carry an L2 evict_last hint (-0.5 % per iteration), 2 = and activation loads evict_first
   int dbg;                // developer bisect switch (B2P_TC_DBG): 1 = skip the TMA/MMA main loop, 2 = skip the epilogue math
 };
 
 int tc_make_act_map(CUtensorMap* m, const void* base, int B, int L, int C, int box_l, int lstride, int box_b);
 int tc_make_weight_map(CUtensorMap* m, const void* base, int taps, int Cout, int K, int box_taps, int box_n);
+int tc_make_out_map(CUtensorMap* m, const void* base, int nrows, int Cout, int tile_n);
 int tc_pick_tile_n(int nrows, int Cout, bool has_head);
 int tc_configure(TcArgs& a);
 int launch_conv_tc(const TcMaps& maps, const TcArgs& a, int nsplit, cudaStream_t s);
