@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(TC_THREADS, SmemPlan<TN>::min_ctas) conv_tc_ke
     float addv[EC];
 #pragma unroll
     for (int c = 0; c < EC; ++c) addv[c] = has_res ? sh->resb[col0 + c] : 0.f;
-    if (row_ok) {
+    if (row_ok && !(a.dbg & 8)) {   // dbg bit 3: skip the addend loads (timing experiment)
       if (a.temb) {
         const float* tp = a.temb + (size_t)b * a.temb_stride + gcol;
 #pragma unroll
