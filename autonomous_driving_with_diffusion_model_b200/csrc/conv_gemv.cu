@@ -181,6 +181,12 @@ __device__ __forceinline__ void gv_dot(const float* __restrict__ wcol, int wstri
   gv_reduce<CW * RT>(acc, lane, 16);
 }
 
+// x / n for a count that is (almost always) a power of two: the exact reciprocal built from the exponent instead of an IEEE division on the
+// critical path between the dot product and the epilogue (same bits as the division)
+__device__ __forceinline__ float gv_div_count(float x, int n) {
+  return (n & (n - 1)) == 0 ? x * __uint_as_float((uint32_t)(127 - (31 - __clz(n))) << 23) : x / (float)n;
+}
+
 __host__ __device__ inline int gv_pad4(int n) { return (n + 7) & ~7; }   // floats; name kept: regions are padded to 32 bytes (see the carve-up)
 
 // NC = channels per CTA (power of two <= 8), cls = CTAs per cluster (= GroupNorm group size / NC, or 1)
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
       for (int i = 0; i < 4; ++i) { v[i] = lane + 32 * i < ne ? st.O[lane + 32 * i] : 0.f; s += v[i]; }
 #pragma unroll
       for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
-      const float mean = s / (float)ne;
+      const float mean = gv_div_count(s, ne);
       float q = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) if (lane + 32 * i < ne) { const float d = v[i] - mean; q = fmaf(d, d, q); }
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
       gv_bar_wait(&st.bar);                                 // all cls parts have landed in this CTA's cx (no CTA exits before that)
       float ms = 0.f;                                       // merge equal-sized parts in a fixed order (parallel-variance formula)
       for (int p = 0; p < cls; ++p) ms += st.cx[p].x;
-      mu = ms / (float)cls;
+      mu = gv_div_count(ms, cls);
       for (int p = 0; p < cls; ++p) { const float d = st.cx[p].x - mu; m2 += st.cx[p].y + (float)ne * d * d; }
     } else {
       __syncthreads();
@@ -338,7 +344,7 @@ __global__ void __launch_bounds__(GV_NT) conv_gemv_kernel(ConvArgs a, int NC, in
   if (eact) {
     float v = e_val;
     if (gn) {
-      const float rstd = 1.0f / sqrtf(m2 / (float)(a.cg * L) + 1e-5f);
+      const float rstd = 1.0f / sqrtf(gv_div_count(m2, a.cg * L) + 1e-5f);
       v = mish_f((v - mu) * rstd * e_gamma + e_beta);
     }
     a.out[((size_t)b * L + er) * a.Cout + ec] = v + e_add + e_res;
