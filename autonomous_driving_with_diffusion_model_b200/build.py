@@ -10,7 +10,8 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 TRACE = os.environ.get("B2P_TRACE_BUILD") == "1"   # developer build with in-kernel stage clocks (scripts/tc_trace.py)
-LIB_PATH = os.path.join(PKG_DIR, "libb200plan_trace.so" if TRACE else "libb200plan.so")
+PREBUILT = os.environ.get("B2P_LIB_PATH")            # developer A/B: load this prebuilt library as is (never rebuilt)
+LIB_PATH = PREBUILT or os.path.join(PKG_DIR, "libb200plan_trace.so" if TRACE else "libb200plan.so")
 SOURCES = ["api.cu", "sched.cu", "embed.cu", "conv_ffma.cu", "conv_gemv.cu", "conv_tc.cu", "chain64.cu", "trajpred.cu", "preprocess.cu", "control.cu", "encoder_stem.cu", "encoder_conv.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -34,7 +35,7 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+    if PREBUILT or (not force and not _stale()):
         return LIB_PATH
     objs = []
     nvcc = _nvcc()

@@ -48,11 +48,13 @@ struct __align__(16) ChainShared {
   uint64_t mma_bar[2];           // MMAs of column half 0 / 1 of the current op have retired
   uint32_t tmem_base;
   uint32_t pad;                  // the float tables below are read as float4: keep them 16-byte aligned
-  float vec[2][3][64];           // bias / gamma / beta of the current op (double-buffered by op parity: the previous op's readers may still run)
+  float vec[CH_MAXOPS][3][64];   // bias / gamma / beta of every op, fetched once in the prologue (a per-op fetch put one global-load latency on every op-to-op hand-over)
   float xs[CH_NS * CH_MAX_HD];   // x_t of the CTA's trajectories
   float mo[CH_NS * CH_MAX_HD];   // model output of the CTA's trajectories (head result)
   float xw[8 * 64 + 64];         // 1x1 projection of x: [D][64] + bias
   float headw[8 * 64 + 8];       // head weights [d][64] + bias
+  SchedK sk;                     // the fused scheduler step's arguments: the out-of-line step function takes them by reference, and a reference into the kernel
+                                 // parameters is a GENERIC pointer whose every field read is a global-path round trip (9 k cycles per launch)
   ChainOp ops[CH_MAXOPS];        // the op table, copied out of the kernel-parameter constant bank in the prologue: an indexed read of a.ops[oi]
                                  // is a constant-cache miss the first time an op's line is touched, and those misses sat on the op-to-op critical path
 };
@@ -162,6 +164,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     uint32_t* dst = reinterpret_cast<uint32_t*>(sh->ops);
     for (int i = tid; i < (int)(a.n_ops * sizeof(ChainOp) / 4); i += CH_THREADS) dst[i] = src[i];
   }
+  if (a.do_sched) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&a.sk);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sh->sk);
+    for (int i = tid; i < (int)(sizeof(SchedK) / 4); i += CH_THREADS) dst[i] = src[i];
+  }
+  for (int i = tid; i < a.n_ops * 192; i += CH_THREADS) {
+    const int o = i / 192, w = (i >> 6) % 3, c = i & 63;
+    const float* p = w == 0 ? a.ops[o].bias : (w == 1 ? a.ops[o].gamma : a.ops[o].beta);
+    sh->vec[o][w][c] = p ? __ldg(p + c) : (w == 1 ? 1.f : 0.f);
+  }
   if (a.xprojW)
     for (int i = tid; i < a.D * 64 + 64; i += CH_THREADS) sh->xw[i] = i < a.D * 64 ? __ldg(a.xprojW + i) : __ldg(a.xprojB + i - a.D * 64);
   if (a.headW) {   // [64][head_dim] -> [d][64]
@@ -227,10 +239,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int k = c8 * 8 + e;
-          const int j = k / D, c = k - j * D;
-          const int pos = l + j - 2;
-          v[e] = (k < KT && s < nb && pos >= 0 && pos < 16) ? sh->xs[s * HD + pos * D + c] : 0.f;
+          // k = j * D + c and pos = l + j - 2, so the element is xs[s][(l - 2) * D + k]; it lies inside the trajectory exactly when that offset does
+          const int k = c8 * 8 + e, off = (l - 2) * D + k;
+          v[e] = (k < KT && s < nb && off >= 0 && off < HD) ? sh->xs[s * HD + off] : 0.f;
         }
         uint4 hi, lo;
         split8(v, &hi, &lo);
@@ -238,20 +249,41 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
         if (NSPLIT == 2) *reinterpret_cast<uint4*>(smem + CH_HALF + swz(row, c8)) = lo;
       }
     }
-    if (tid < 192) {
-      const int w = tid >> 6, c = tid & 63;
-      const float* p = w == 0 ? op.bias : (w == 1 ? op.gamma : op.beta);
-      sh->vec[oi & 1][w][c] = p ? __ldg(p + c) : (w == 1 ? 1.f : 0.f);
+    // ------------- everything added after GroupNorm / Mish comes from global memory and depends on nothing this kernel computes: the loads are
+    // ISSUED here, ahead of the barrier, all of them before the first use (issued after the barrier and consumed half by half they were two to
+    // three serialised L2 round trips, 2.3-3.2 k cycles against the ~1 k of the first column half's MMAs) -------------
+    const int l = r & (L - 1), sidx = r >> op.log2L;
+    const bool epi = warp < CH_EPI_THREADS / 32;             // the extra warp only issues MMAs
+    const bool row_ok = epi && sidx < nb;
+    const int b = b0 + sidx;
+    const bool has_t = row_ok && op.temb_off >= 0, has_q = row_ok && op.res_kind == CH_RES_F32;
+    const float* t2p = a.temb2[op.phase];
+    const bool has_t2 = has_t && t2p != nullptr;
+    float4 raw[2][3][CH_EC / 4];                             // [column half][time row | per-step time vector | fp32 residual]
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int ch0 = hf * 32 + col0;
+#pragma unroll
+      for (int j = 0; j < CH_EC / 4; ++j) {
+        raw[hf][0][j] = raw[hf][1][j] = raw[hf][2][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_t) raw[hf][0][j] = __ldg(reinterpret_cast<const float4*>(a.temb_rows + (size_t)b * a.temb_stride + op.temb_off + ch0) + j);
+        if (has_t2) raw[hf][1][j] = __ldg(reinterpret_cast<const float4*>(t2p + op.temb_off + ch0) + j);
+        if (has_q) raw[hf][2][j] = __ldg(reinterpret_cast<const float4*>(a.res_f32 + ((size_t)b * L + l) * 64 + ch0) + j);
+      }
     }
-    if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 0] = clock64();
+    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 0] = clock64();
     fence_async_smem();              // the A operand was written with ordinary stores: make it visible to the tensor core
     tc_fence_before();               // ... and the previous op's TMEM reads are complete
     __syncthreads();
-    if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 1] = clock64();
+    if (a.trace && blockIdx.x == 0) {   // BAR.SYNC lets the next instruction issue before the warp blocks: a clock read right behind it is the ARRIVAL time
+      __syncwarp();
+      if (tid == 0) a.trace[oi * 16 + 1] = clock64();
+    }
 
     if (warp == CH_MMA_WARP) {
       // =============================== MMA issue (one elected lane of the 17th warp runs the whole loop: tc_ptx.cuh elect_one) ===============================
       if (elect_one()) {
+      if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 14] = clock64();
       mbar_wait(&sh->wbar, wpar);
       tc_fence_after();
       if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 2] = clock64();
@@ -289,46 +321,40 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     wpar ^= 1;
     __syncwarp();
 
-    // ------------- everything added after GroupNorm / Mish is fetched while the tensor core works -------------
-    const int l = r & (L - 1), sidx = r >> op.log2L;
-    const bool epi = warp < CH_EPI_THREADS / 32;             // the extra warp only issues MMAs
-    const bool row_ok = epi && sidx < nb;
-    const int b = b0 + sidx;
+    // ------------- the addends, summed in the order the per-layer kernels use (time row, per-step time vector, residual) -------------
     float addv[2][CH_EC];
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       const int ch0 = hf * 32 + col0;                 // first of this thread's 8 channels in column half hf
 #pragma unroll
       for (int c = 0; c < CH_EC; ++c) addv[hf][c] = 0.f;
-      if (row_ok) {
-        if (op.temb_off >= 0) {
-          const float* tp = a.temb_rows + (size_t)b * a.temb_stride + op.temb_off + ch0;
-          const float* t2 = a.temb2[op.phase] ? a.temb2[op.phase] + op.temb_off + ch0 : nullptr;
+      if (has_t) {
 #pragma unroll
-          for (int c = 0; c < CH_EC; c += 4) {
-            float4 t4v = __ldg(reinterpret_cast<const float4*>(tp + c));
-            addv[hf][c] += t4v.x; addv[hf][c + 1] += t4v.y; addv[hf][c + 2] += t4v.z; addv[hf][c + 3] += t4v.w;
-            if (t2) { float4 u = __ldg(reinterpret_cast<const float4*>(t2 + c)); addv[hf][c] += u.x; addv[hf][c + 1] += u.y; addv[hf][c + 2] += u.z; addv[hf][c + 3] += u.w; }
-          }
+        for (int j = 0; j < CH_EC / 4; ++j) {
+          const float4 t4v = raw[hf][0][j];
+          addv[hf][4 * j] += t4v.x; addv[hf][4 * j + 1] += t4v.y; addv[hf][4 * j + 2] += t4v.z; addv[hf][4 * j + 3] += t4v.w;
+          if (has_t2) { const float4 u = raw[hf][1][j]; addv[hf][4 * j] += u.x; addv[hf][4 * j + 1] += u.y; addv[hf][4 * j + 2] += u.z; addv[hf][4 * j + 3] += u.w; }
         }
-        if (op.res_kind == CH_RES_F32) {
-          const float* q = a.res_f32 + ((size_t)b * L + l) * 64 + ch0;
+      }
+      if (has_q) {
 #pragma unroll
-          for (int c = 0; c < CH_EC; c += 4) { float4 t4v = __ldg(reinterpret_cast<const float4*>(q + c)); addv[hf][c] += t4v.x; addv[hf][c + 1] += t4v.y; addv[hf][c + 2] += t4v.z; addv[hf][c + 3] += t4v.w; }
-        } else if (op.res_kind == CH_RES_XPROJ) {   // residual_conv(x) of the first block: 1x1 conv over the D raw channels, fp32 on CUDA cores
-          const float* xr = sh->xs + sidx * HD + l * a.D;
+        for (int j = 0; j < CH_EC / 4; ++j) {
+          const float4 t4v = raw[hf][2][j];
+          addv[hf][4 * j] += t4v.x; addv[hf][4 * j + 1] += t4v.y; addv[hf][4 * j + 2] += t4v.z; addv[hf][4 * j + 3] += t4v.w;
+        }
+      } else if (row_ok && op.res_kind == CH_RES_XPROJ) {   // residual_conv(x) of the first block: 1x1 conv over the D raw channels, fp32 on CUDA cores
+        const float* xr = sh->xs + sidx * HD + l * a.D;
 #pragma unroll
-          for (int c = 0; c < CH_EC; ++c) addv[hf][c] = sh->xw[a.D * 64 + ch0 + c];
+        for (int c = 0; c < CH_EC; ++c) addv[hf][c] = sh->xw[a.D * 64 + ch0 + c];
 #pragma unroll 1
-          for (int d = 0; d < a.D; ++d) {
-            const float xv = xr[d];
+        for (int d = 0; d < a.D; ++d) {
+          const float xv = xr[d];
 #pragma unroll
-            for (int c = 0; c < CH_EC; ++c) addv[hf][c] = fmaf(xv, sh->xw[d * 64 + ch0 + c], addv[hf][c]);
-          }
+          for (int c = 0; c < CH_EC; ++c) addv[hf][c] = fmaf(xv, sh->xw[d * 64 + ch0 + c], addv[hf][c]);
         }
       }
     }
-    if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 4] = clock64();
+    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 4] = clock64();
 
     // =============================== epilogue (all 16 warps), one column half at a time ===============================
     const int n_out = op.kind == CH_UP ? 2 : 1;
@@ -340,13 +366,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       const int ch0 = hf * 32 + col0, c8 = hf * 4 + slice;
       mbar_wait_sleep(&sh->mma_bar[hf], mpar);
       tc_fence_after();
-      if (hf == 0 && a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 5] = clock64();
+      if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + (hf ? 9 : 5)] = clock64();
       if (!epi || ((quad * 32) >> op.log2L) >= nb) continue;   // the MMA warp; or none of this warp's 32 rows belongs to a trajectory (L = 8 ops, last CTA)
 #pragma unroll 1
       for (int o = 0; o < n_out; ++o) {
         float v[CH_EC];
 #pragma unroll
-        for (int c = 0; c < CH_EC; ++c) v[c] = sh->vec[oi & 1][0][ch0 + c];
+        for (int c = 0; c < CH_EC; ++c) v[c] = sh->vec[oi][0][ch0 + c];
         // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the trajectory) ----
         // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the trajectory); the op kind is uniform over the CTA ----
         const uint32_t tbase = taddr + hf * CH_HCOLS;
@@ -361,8 +387,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
           tap_combine<1>(v, tbase, {0}, {0}, l, L, lane);
         }
         if (op.gn) {
-          if (L == 16) group_norm8_mish<16>(v, sh->vec[oi & 1][1] + ch0, sh->vec[oi & 1][2] + ch0);
-          else group_norm8_mish<8>(v, sh->vec[oi & 1][1] + ch0, sh->vec[oi & 1][2] + ch0);
+          if (L == 16) group_norm8_mish<16>(v, sh->vec[oi][1] + ch0, sh->vec[oi][2] + ch0);
+          else group_norm8_mish<8>(v, sh->vec[oi][1] + ch0, sh->vec[oi][2] + ch0);
         }
 #pragma unroll
         for (int c = 0; c < CH_EC; ++c) v[c] += addv[hf][c];
@@ -414,14 +440,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       }
     }
     mpar ^= 1;
-    if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 8] = clock64();
+    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 8] = clock64();
     if (op.out_buf == CH_OUT_HEAD) {
       const int hd = a.head_dim;
 #pragma unroll
       for (int d = 0; d < 8; ++d)
         if (d < hd && epi) headp[slice][d][r] = hsum[d];
       __syncthreads();
-      if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 10] = clock64();
+      if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 10] = clock64();
       for (int idx = tid; idx < TC_M * hd; idx += CH_THREADS) {   // one (row, d) sum at a time
         const int rr = idx / hd, d = idx - rr * hd;
         const float m = sh->headw[8 * 64 + d] + headp[0][d][rr] + headp[1][d][rr] + headp[2][d][rr] + headp[3][d][rr];
@@ -430,13 +456,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
         if (a.head_out && s2 < nb) a.head_out[((size_t)(b0 + s2) * 16 + (rr & 15)) * hd + d] = m;
       }
       __syncthreads();
-      if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 11] = clock64();
+      if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 11] = clock64();
       if (a.do_sched)
 #pragma unroll 1
         for (int e = tid; e < nb * HD; e += CH_THREADS) {
           // ---- fused scheduler step, one element at a time per thread: the stand-alone kernel's arithmetic and noise counters (group = 4 elements) ----
           const size_t ge = (size_t)b0 * HD + e;                // global element index
-          const SchedK& k = a.sk;
+          const SchedK& k = sh->sk;
           float nz = 0.f;
           if (k.noise) nz = __ldg(k.noise + ge);
           else if (k.seed) { const float4 n4 = philox_group(*k.seed, (unsigned)(ge >> 2), k.noise_step); nz = (ge & 3) == 0 ? n4.x : ((ge & 3) == 1 ? n4.y : ((ge & 3) == 2 ? n4.z : n4.w)); }
@@ -449,10 +475,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
           sh->xs[e] = out;                                      // x_{t-1}: the next evaluation's input (im2col + projection)
         }
     }
-    if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[oi * 16 + 6] = clock64();
+    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 6] = clock64();
   }
 
-  if (a.trace && blockIdx.x == 0 && tid == 64) a.trace[a.n_ops * 16] = clock64();
+  if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[a.n_ops * 16] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == CH_MMA_WARP) {

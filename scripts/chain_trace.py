@@ -18,14 +18,13 @@ lib.b2p_debug_chain_trace.argtypes = [C.c_void_p, C.c_void_p]
 buf = (C.c_uint64 * 256)()
 assert lib.b2p_debug_chain_trace(m._handle_for(dev), buf) == 0
 t = [[buf[i * 16 + j] for j in range(16)] for i in range(16)]
-print(f"B={B}: seam launch, CTA 0, cycles")
-print("op  top->barrier  weights_wait(after barrier)  mma_issue  prefetch  mma_wait(exposed)  taps+GN  epilogue  total   [head: partial, sync1, sum+sync2, sched]")
+print(f"B={B}: seam launch, CTA 0, thread 0 (an epilogue thread of every op) + the MMA lane, cycles")
+print("op   L  barrier_wait  mma_lane:weights_wait  mma_issue | addends  wait_half0  epi_half0(+wait_half1)  epi_half1  [head: partials+sync, sums+sync, scheduler]  next_top   total")
 tot = 0
 for i in range(10):
     r = t[i]
     nxt = t[i + 1][0] if i < 9 else t[10][0]
-    wl = f"  [weights: issued {r[12]-t[i-1][0] if i else 0} into the previous op, landed {r[2]-r[12] if r[12] else 0} cycles later]"
-    extra = wl + f"   {r[9]-r[8]} {r[10]-r[9]} {r[11]-r[10]} {r[6]-r[11]}" if r[9] else wl
-    print(f"{i:2d}  {r[1]-r[0]:8d}  {r[2]-r[1]:8d}  {r[3]-r[2]:8d}  {r[4]-r[1]:8d}  {r[5]-r[4]:8d}  {r[8]-r[5]:8d}  {r[6]-r[5]:8d}  {nxt-r[0]:8d}{extra}")
+    head = f"{r[10]-r[8]:6d} {r[11]-r[10]:6d} {r[6]-r[11]:6d}" if r[10] else " " * 20
+    print(f"{i:2d}  {r[1]-r[0]:8d}  {r[2]-r[14]:8d}  {r[3]-r[2]:8d} | {r[4]-r[1]:8d}  {r[5]-r[4]:8d}  {r[9]-r[5]:8d}  {r[8]-r[9]:8d}  {head}  {nxt-r[6]:8d}  {nxt-r[0]:8d}   [MMA lane past the barrier {r[14]-r[1]} after thread 0; next weights issued {t[i+1][12]-r[1] if i < 9 and t[i+1][12] else 0} after the barrier]")
     tot += nxt - r[0]
 print("sum", tot, "cycles =", tot / 1.965e3, "us")
