@@ -38,9 +38,13 @@ constexpr int CH_ACT_BYTES = 2 * CH_HALF;             // hi | lo
 constexpr int CH_TAP_BYTES = 64 * 64 * 2;             // one tap of one weight plane
 constexpr int CH_OFF_W = 3 * CH_ACT_BYTES;            // weight image of the current op (<= 5 taps x 8 KB x 2 planes)
 constexpr int CH_W_BYTES = 2 * 5 * CH_TAP_BYTES;
-constexpr int CH_OFF_HEADP = CH_OFF_W + CH_W_BYTES;   // head partial sums [slice][8][128 rows]
-constexpr int CH_OFF_MISC = CH_OFF_HEADP + CH_SL * 8 * 128 * 4;
+constexpr int CH_OFF_MISC = CH_OFF_W + CH_W_BYTES;
+constexpr int CH_HEADP_SLOTS = 2 * CH_SL;             // head partial sums [column half x slice][8][128 rows] = 32 KB: they live in an activation buffer that is idle
+static_assert(CH_HEADP_SLOTS * 8 * 128 * 4 <= CH_ACT_BYTES, "head partial sums alias one activation buffer");   // during the head op (neither its A operand nor the next op's)
 static_assert(CH_EPI_THREADS == 512, "the epilogue mapping assumes 16 warps: 4 lane quadrants x 4 column slices of 8 channels per half");
+#ifndef CH_READER_FENCE
+#define CH_READER_FENCE 0   // the writers' fence.proxy.async + the cluster barrier's release/acquire order the remote stores before the MMAs (bitwise test); a reader-side fence cost ~700 cycles per op
+#endif
 constexpr int CH_MAX_HD = 16 * 8;                     // horizon 16 x transition dim <= 8 (im2col K = 5 * D <= 64; one scheduler element per thread)
 
 struct __align__(16) ChainShared {
@@ -132,16 +136,30 @@ __device__ __forceinline__ void group_norm8_mish(float (&v)[CH_EC], const float*
   for (int c = 0; c < 8; ++c) v[c] = mish_fast((v[c] - mean) * rs * gamma[c] + beta[c]);
 }
 
-template <int NSPLIT>
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) { uint32_t ra; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(saddr), "r"(cta)); return ra; }
+__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_1f(uint32_t raddr, float x) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(x) : "memory"); }
+
+// CL = 1: one CTA owns 8 trajectories and all 64 channels (two column-half passes per op).
+// CL = 2: a cluster of two CTAs owns the 8 trajectories; CTA `rank` computes channel half `rank` of every op (half the MMAs, ONE epilogue pass)
+//         and stores its 16-byte chunks of the next A operand into BOTH CTAs' shared memory (st.shared::cluster); the op-to-op barrier is the
+//         cluster barrier.  The epilogue is instruction-issue bound (4 warps per scheduler x ~620 instructions per pass), so splitting the
+//         channels over two SMs is what shortens an op; the arithmetic per element is identical, results are bit-identical to CL = 1.
+template <int NSPLIT, int CL>
 __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_constant__ ChainArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   ChainShared* sh = reinterpret_cast<ChainShared*>(smem + CH_OFF_MISC);
   uint8_t* wbuf = smem + CH_OFF_W;
-  float (*headp)[8][TC_M] = reinterpret_cast<float (*)[8][TC_M]>(smem + CH_OFF_HEADP);
+  constexpr int NH = CL == 2 ? 1 : 2;                   // column-half passes per CTA
+  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const uint32_t peer_base = CL == 2 ? mapa_u32(smem_u32(smem), (uint32_t)(crank ^ 1)) : 0u;   // the other CTA's copy of `smem`
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b0 = blockIdx.x * a.ns;
+  const int b0 = (CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * a.ns;
   const int nb = a.B - b0 < a.ns ? a.B - b0 : a.ns;
   const int HD = a.H * a.D;
 
@@ -189,9 +207,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
   auto issue_weights = [&](int oi) {   // one thread: pre-swizzled image, one bulk copy per tap and plane
     const ChainOp& op = sh->ops[oi];
     const uint32_t plane = (uint32_t)op.T * CH_TAP_BYTES;
-    mbar_expect_tx(&sh->wbar, NSPLIT * plane);
     const uint8_t* src = a.wpack + op.w_off;
-    for (int i = 0; i < NSPLIT * op.T; ++i) bulk_g2s(wbuf + (size_t)i * CH_TAP_BYTES, src + (size_t)i * CH_TAP_BYTES, CH_TAP_BYTES, &sh->wbar);
+    if (CL == 2) {                       // only this CTA's column half of each plane (the image is ordered [plane][column half][tap][32 channels]), same offsets
+      const uint32_t half_bytes = plane / 2, o0 = (uint32_t)crank * half_bytes;
+      mbar_expect_tx(&sh->wbar, NSPLIT * half_bytes);
+      for (int pl = 0; pl < NSPLIT; ++pl)
+        for (int i = 0; i < op.T; ++i) {
+          const uint32_t o = pl * plane + o0 + (uint32_t)i * (CH_TAP_BYTES / 2);
+          bulk_g2s(wbuf + o, src + o, CH_TAP_BYTES / 2, &sh->wbar);
+        }
+    } else {
+      mbar_expect_tx(&sh->wbar, NSPLIT * plane);
+      for (int i = 0; i < NSPLIT * op.T; ++i) bulk_g2s(wbuf + (size_t)i * CH_TAP_BYTES, src + (size_t)i * CH_TAP_BYTES, CH_TAP_BYTES, &sh->wbar);
+    }
   };
   if (warp == CH_MMA_WARP && elect_one()) issue_weights(0);
   griddep_launch_dependents();      // the next kernel may become resident and prefetch ITS weights
@@ -259,10 +287,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     const bool has_t = row_ok && op.temb_off >= 0, has_q = row_ok && op.res_kind == CH_RES_F32;
     const float* t2p = a.temb2[op.phase];
     const bool has_t2 = has_t && t2p != nullptr;
-    float4 raw[2][3][CH_EC / 4];                             // [column half][time row | per-step time vector | fp32 residual]
+    float4 raw[NH][3][CH_EC / 4];                            // [column-half pass][time row | per-step time vector | fp32 residual]
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int ch0 = hf * 32 + col0;
+    for (int hf = 0; hf < NH; ++hf) {
+      const int ch0 = (CL == 2 ? crank : hf) * 32 + col0;
 #pragma unroll
       for (int j = 0; j < CH_EC / 4; ++j) {
         raw[hf][0][j] = raw[hf][1][j] = raw[hf][2][j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -272,9 +300,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       }
     }
     if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 0] = clock64();
-    fence_async_smem();              // the A operand was written with ordinary stores: make it visible to the tensor core
+    if (CL == 2) asm volatile("fence.proxy.async;" ::: "memory");   // ... local AND remote stores
+    else fence_async_smem();         // the A operand was written with ordinary stores: make it visible to the tensor core
     tc_fence_before();               // ... and the previous op's TMEM reads are complete
-    __syncthreads();
+    if (CL == 2) cluster_sync_all(); // both CTAs have written their channel half of this op's A operand into both copies
+    else __syncthreads();
     if (a.trace && blockIdx.x == 0) {   // BAR.SYNC lets the next instruction issue before the warp blocks: a clock read right behind it is the ARRIVAL time
       __syncwarp();
       if (tid == 0) a.trace[oi * 16 + 1] = clock64();
@@ -285,6 +315,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       if (elect_one()) {
       if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 14] = clock64();
       mbar_wait(&sh->wbar, wpar);
+      if (CL == 2 && CH_READER_FENCE) asm volatile("fence.proxy.async;" ::: "memory");   // reader side of the generic-proxy stores the peer CTA made into this CTA's A operand
       tc_fence_after();
       if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 2] = clock64();
       const uint32_t sa = smem_u32(smem + (op.in_buf < 0 ? 0 : op.in_buf) * CH_ACT_BYTES);
@@ -295,8 +326,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       const uint32_t idn = umma_idesc_n(op.T * 32);
       const uint32_t half_bytes = (uint32_t)op.T * (CH_TAP_BYTES / 2);
 #pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        const uint64_t b_hi = umma_desc(sb + hf * half_bytes), b_lo = umma_desc(sb + op.T * CH_TAP_BYTES + hf * half_bytes);
+      for (int hf = 0; hf < NH; ++hf) {
+        const uint32_t hc = CL == 2 ? (uint32_t)crank : (uint32_t)hf;   // channel half
+        const uint64_t b_hi = umma_desc(sb + hc * half_bytes), b_lo = umma_desc(sb + op.T * CH_TAP_BYTES + hc * half_bytes);
         const uint32_t dcol = tmem_base + hf * CH_HCOLS;
 #pragma unroll 1
         for (int k = 0; k < op.ksteps; ++k) {
@@ -311,7 +343,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       }
       if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 3] = clock64();
       if (oi + 1 < a.n_ops) {          // the weight buffer is free once every MMA of this op has retired
-        mbar_wait(&sh->mma_bar[1], mpar);
+        mbar_wait(&sh->mma_bar[NH - 1], mpar);
         if (a.trace && blockIdx.x == 0) a.trace[(oi + 1) * 16 + 12] = clock64();
         issue_weights(oi + 1);
       }
@@ -322,10 +354,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     __syncwarp();
 
     // ------------- the addends, summed in the order the per-layer kernels use (time row, per-step time vector, residual) -------------
-    float addv[2][CH_EC];
+    float addv[NH][CH_EC];
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int ch0 = hf * 32 + col0;                 // first of this thread's 8 channels in column half hf
+    for (int hf = 0; hf < NH; ++hf) {
+      const int ch0 = (CL == 2 ? crank : hf) * 32 + col0;   // first of this thread's 8 channels in this pass's column half
 #pragma unroll
       for (int c = 0; c < CH_EC; ++c) addv[hf][c] = 0.f;
       if (has_t) {
@@ -346,11 +378,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
         const float* xr = sh->xs + sidx * HD + l * a.D;
 #pragma unroll
         for (int c = 0; c < CH_EC; ++c) addv[hf][c] = sh->xw[a.D * 64 + ch0 + c];
-#pragma unroll 1
-        for (int d = 0; d < a.D; ++d) {
-          const float xv = xr[d];
+#pragma unroll 4
+        for (int d = 0; d < 8; ++d) {                       // D <= 8: straight-line code, the shared-memory reads of several d in flight together
+          if (d < a.D) {
+            const float xv = xr[d];
 #pragma unroll
-          for (int c = 0; c < CH_EC; ++c) addv[hf][c] = fmaf(xv, sh->xw[d * 64 + ch0 + c], addv[hf][c]);
+            for (int c = 0; c < CH_EC; ++c) addv[hf][c] = fmaf(xv, sh->xw[d * 64 + ch0 + c], addv[hf][c]);
+          }
         }
       }
     }
@@ -358,12 +392,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
 
     // =============================== epilogue (all 16 warps), one column half at a time ===============================
     const int n_out = op.kind == CH_UP ? 2 : 1;
-    float hsum[8];                                      // fused head: partial dot products of this thread over both halves
+    const int hb = op.in_buf == 2 ? 0 : 2;              // fused head: the partial sums go to an activation buffer that is idle during this op
+    float (*headp)[8][TC_M] = reinterpret_cast<float (*)[8][TC_M]>(smem + hb * CH_ACT_BYTES);
 #pragma unroll
-    for (int d = 0; d < 8; ++d) hsum[d] = 0.f;
+    for (int hf = 0; hf < NH; ++hf) {
+      const int hc = CL == 2 ? crank : hf;
+      const int ch0 = hc * 32 + col0, c8 = hc * 4 + slice;
+      float hsum[8];                                    // fused head: partial dot products of this thread's 8 channels
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int ch0 = hf * 32 + col0, c8 = hf * 4 + slice;
+      for (int d = 0; d < 8; ++d) hsum[d] = 0.f;
       mbar_wait_sleep(&sh->mma_bar[hf], mpar);
       tc_fence_after();
       if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + (hf ? 9 : 5)] = clock64();
@@ -415,6 +452,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
             if (row_ok) split8(v, &hi, &lo);
             *reinterpret_cast<uint4*>(ob + swz(ro, c8)) = hi;
             if (NSPLIT == 2) *reinterpret_cast<uint4*>(ob + CH_HALF + swz(ro, c8)) = lo;
+            if (CL == 2) {             // the same chunks into the peer CTA's copy of the buffer
+              const uint32_t ra = peer_base + (uint32_t)(op.out_buf * CH_ACT_BYTES) + swz(ro, c8);
+              st_cluster_v4(ra, hi);
+              if (NSPLIT == 2) st_cluster_v4(ra + CH_HALF, lo);
+            }
           }
         } else if (op.out_buf == CH_OUT_GLOBAL) {
           const bool emit = row_ok && (op.kind != CH_DOWN || (l & 1) == 0);
@@ -438,22 +480,29 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
           }
         }
       }
+      if (op.out_buf == CH_OUT_HEAD) {   // one partial per (column half, slice): eight of them per (row, d), whichever CTA computed them
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+          if (d < a.head_dim) {
+            headp[c8][d][r] = hsum[d];
+            if (CL == 2) st_cluster_1f(peer_base + (uint32_t)(hb * CH_ACT_BYTES) + (uint32_t)(((c8 * 8 + d) * TC_M + r) * 4), hsum[d]);
+          }
+      }
     }
     mpar ^= 1;
     if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 8] = clock64();
     if (op.out_buf == CH_OUT_HEAD) {
       const int hd = a.head_dim;
-#pragma unroll
-      for (int d = 0; d < 8; ++d)
-        if (d < hd && epi) headp[slice][d][r] = hsum[d];
-      __syncthreads();
+      if (CL == 2) cluster_sync_all(); else __syncthreads();
       if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 10] = clock64();
-      for (int idx = tid; idx < TC_M * hd; idx += CH_THREADS) {   // one (row, d) sum at a time
+      for (int idx = tid; idx < TC_M * hd; idx += CH_THREADS) {   // one (row, d) sum at a time; rows without a trajectory hold whatever the buffer held
         const int rr = idx / hd, d = idx - rr * hd;
-        const float m = sh->headw[8 * 64 + d] + headp[0][d][rr] + headp[1][d][rr] + headp[2][d][rr] + headp[3][d][rr];
+        float m = sh->headw[8 * 64 + d];
+#pragma unroll
+        for (int j = 0; j < CH_HEADP_SLOTS; ++j) m += headp[j][d][rr];
         sh->mo[idx] = m;                      // index rr * hd + d with rr == s * 16 + l: the [NS, H, head_dim] block of this CTA
         const int s2 = rr >> 4;
-        if (a.head_out && s2 < nb) a.head_out[((size_t)(b0 + s2) * 16 + (rr & 15)) * hd + d] = m;
+        if (a.head_out && s2 < nb && crank == 0) a.head_out[((size_t)(b0 + s2) * 16 + (rr & 15)) * hd + d] = m;
       }
       __syncthreads();
       if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 11] = clock64();
@@ -471,7 +520,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
           const int sample = e / HD, pos = e - sample * HD;
           float x0;
           const float out = sched_elem(k, sample, pos, pos % a.D, sh->mo[e], sh->xs[e], nz, tj, mk, &x0);
-          a.x_out[ge] = out;
+          if (crank == 0) a.x_out[ge] = out;
           sh->xs[e] = out;                                      // x_{t-1}: the next evaluation's input (im2col + projection)
         }
     }
@@ -480,7 +529,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
 
   if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[a.n_ops * 16] = clock64();
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all();    // neither CTA leaves while the other may still store into its shared memory
+  else __syncthreads();
   if (warp == CH_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -495,23 +545,45 @@ int launch_chain64(const ChainArgs& a, int nsplit, cudaStream_t s) {
     if (op.out_buf >= 0 && (op.out_buf == op.in_buf || (op.res_kind == CH_RES_SMEM && op.out_buf == op.res_buf))) return B2P_ERR_INVALID_ARG;
     if (op.kind == CH_UP && (op.L != 8 || op.T != 4)) return B2P_ERR_INVALID_ARG;
     if (op.out_buf == CH_OUT_HEAD && (!a.headW || a.head_dim < 1 || a.head_dim > 8 || op.L != 16)) return B2P_ERR_INVALID_ARG;
+    // the head's partial sums alias activation buffer 2 (0 if the A operand is buffer 2): it must not be the residual, and the next op must rebuild its own operand
+    if (op.out_buf == CH_OUT_HEAD && ((op.res_kind == CH_RES_SMEM && op.res_buf == (op.in_buf == 2 ? 0 : 2)) || (i + 1 < a.n_ops && a.ops[i + 1].in_buf != CH_IN_IM2COL))) return B2P_ERR_INVALID_ARG;
     if (op.in_buf == CH_IN_IM2COL && op.L != 16) return B2P_ERR_INVALID_ARG;
   }
   if (a.do_sched && (a.head_dim != a.D || !a.x_out || a.sk.mo_u || a.sk.clip_mode == 3)) return B2P_ERR_INVALID_ARG;
   const size_t smem = chain64_smem_bytes();
+  const int groups = (a.B + a.ns - 1) / a.ns;
+  // two CTAs per trajectory group (each computes one channel half of every op) while the doubled grid still fits the SMs in one wave;
+  // B2P_CHAIN_CL = 1 / 2 forces a variant (developer switch)
+  static int forced = -1, sms = 0;
+  if (forced < 0) {
+    const char* e = getenv("B2P_CHAIN_CL");
+    forced = e ? atoi(e) : 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int cl = forced == 1 || forced == 2 ? forced : (2 * groups <= sms ? 2 : 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((a.B + a.ns - 1) / a.ns); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute attr[2];
+  cfg.gridDim = dim3(groups * cl); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = add_l2_window_attr(attr, 1);
-  if (nsplit == 2) {
-    B2P_CUDA_TRY(cudaFuncSetAttribute(chain64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return (int)cudaLaunchKernelEx(&cfg, chain64_kernel<2>, a);
+  int na = 1;
+  if (cl == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
   }
-  B2P_CUDA_TRY(cudaFuncSetAttribute(chain64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  return (int)cudaLaunchKernelEx(&cfg, chain64_kernel<1>, a);
+  cfg.attrs = attr; cfg.numAttrs = add_l2_window_attr(attr, na);
+#define B2P_CHAIN_LAUNCH(NS_, CL_)                                                                                                  \
+  do {                                                                                                                               \
+    B2P_CUDA_TRY(cudaFuncSetAttribute(chain64_kernel<NS_, CL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    return (int)cudaLaunchKernelEx(&cfg, chain64_kernel<NS_, CL_>, a);                                                               \
+  } while (0)
+  if (nsplit == 2) { if (cl == 2) B2P_CHAIN_LAUNCH(2, 2); else B2P_CHAIN_LAUNCH(2, 1); }
+  if (cl == 2) B2P_CHAIN_LAUNCH(1, 2); else B2P_CHAIN_LAUNCH(1, 1);
+#undef B2P_CHAIN_LAUNCH
 }
 
 }  // namespace b2p

@@ -25,6 +25,6 @@ for i in range(10):
     r = t[i]
     nxt = t[i + 1][0] if i < 9 else t[10][0]
     head = f"{r[10]-r[8]:6d} {r[11]-r[10]:6d} {r[6]-r[11]:6d}" if r[10] else " " * 20
-    print(f"{i:2d}  {r[1]-r[0]:8d}  {r[2]-r[14]:8d}  {r[3]-r[2]:8d} | {r[4]-r[1]:8d}  {r[5]-r[4]:8d}  {r[9]-r[5]:8d}  {r[8]-r[9]:8d}  {head}  {nxt-r[6]:8d}  {nxt-r[0]:8d}   [MMA lane past the barrier {r[14]-r[1]} after thread 0; next weights issued {t[i+1][12]-r[1] if i < 9 and t[i+1][12] else 0} after the barrier]")
+    print(f"{i:2d}  {r[1]-r[0]:8d}  {r[2]-r[14]:8d}  {r[3]-r[2]:8d} | {r[4]-r[1]:8d}  {r[5]-r[4]:8d}  {(r[9] if r[9] else r[8])-r[5]:8d}  {r[8]-r[9] if r[9] else 0:8d}  {head}  {nxt-r[6]:8d}  {nxt-r[0]:8d}   [MMA lane past the barrier {r[14]-r[1]} after thread 0; next weights issued {t[i+1][12]-r[1] if i < 9 and t[i+1][12] else 0} after the barrier]")
     tot += nxt - r[0]
 print("sum", tot, "cycles =", tot / 1.965e3, "us")

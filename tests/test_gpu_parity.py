@@ -1028,3 +1028,43 @@ def test_encoder_stem_kernels_vs_torch(shape, channels_last):
     diff = (got.float() - want).abs()
     bound = want.abs() * 2.0 ** -7 + 1e-3
     assert bool((diff <= bound).all()), float((diff - bound).max())
+
+
+_CHAIN_CL_PROBE = r'''
+import hashlib, sys
+import torch
+import autonomous_driving_with_diffusion_model_b200 as P
+from autonomous_driving_with_diffusion_model_b200 import synthetic as W
+dev = "cuda:0"
+for prec in ("bf16x3", "bf16"):
+    for mode, kind in (("NO_GUIDANCE", "ddim"), ("NO_GUIDANCE", "ddpm"), ("FREE_GUIDANCE", "ddim")):
+        cfg = P.load_cfg(TRAIN=dict(USE_COND=mode), EVAL=dict(SAMPLE_STEPS=5), B200=dict(PRECISION=prec), GUIDANCE=dict(USE_COND=mode, FREE_SCALE=7.5))
+        m = P.build_model(cfg); m.load_state_dict(W.make_state_dict(mode, seed=2)); m = m.to(dev).eval()
+        S = P.GuidanceDDIMScheduler if kind == "ddim" else P.GuidanceDDPMScheduler
+        pl = P.DiffusionPlanner(m, S(cfg=cfg, **P.scheduler_kwargs(cfg)), cfg)
+        for B in (5, 8, 37, 130):
+            x = W.synth_inputs(B, 5, 1)
+            kw = {}
+            if mode != "NO_GUIDANCE": kw["target"] = x["target"].to(dev)
+            if kind == "ddpm": kw["noise"] = x["noise"].to(dev)
+            y = pl.plan(x["x"].to(dev), x["feat"].to(dev), **kw).float().cpu().contiguous()
+            assert bool(torch.isfinite(y).all())
+            print(prec, mode, kind, B, hashlib.sha1(y.numpy().tobytes()).hexdigest())
+'''
+
+
+def test_chain_kernel_two_cta_form_is_bitwise_the_one_cta_form():
+    """csrc/chain64.cu, CL = 2: a cluster of two CTAs owns a group of 8 trajectories, each CTA computes one channel half of every op
+    and stores its chunks of the next A operand into both CTAs' shared memory (modeling/temporal.py:46-55,215-245 are the layers).
+    Per element the arithmetic is the one-CTA form's, so whole plans must agree bit for bit: seam launches (DDIM / DDPM), the
+    classifier-free doubled batch, ragged last groups, both tensor-core precisions.  The variant is chosen per process
+    (B2P_CHAIN_CL), hence the two subprocesses."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for cl in ("1", "2"):
+        env = dict(os.environ, B2P_CHAIN_CL=cl, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        r = subprocess.run([sys.executable, "-c", _CHAIN_CL_PROBE], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines())
+    assert len(outs[0]) == 24 and outs[0] == outs[1]
