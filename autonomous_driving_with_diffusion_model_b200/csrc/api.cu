@@ -436,7 +436,7 @@ int build_program(b2p_handle_s* h) {
 }
 
 // ---- chain kernel: which ops it covers and their pre-swizzled weight images ----
-// image of one op: plane hi = [T*64 rows (column half, tap, 32 out channels)][64 k] bf16, K-major with the 128-byte swizzle applied (what TMA would
+// image of one op: plane hi = [T*64 rows (channel quarter, tap, 16 out channels)][64 k] bf16, K-major with the 128-byte swizzle applied (what TMA would
 // have produced in shared memory), followed by plane lo.  The kernel copies it with plain bulk copies, one per tap.
 uint32_t chain_add_image(b2p_handle_s* h, const float* w, int T, int cin, int ktaps, bool transposed, int im2col_D) {
   const size_t plane = (size_t)T * 64 * 128;
@@ -453,7 +453,7 @@ uint32_t chain_add_image(b2p_handle_s* h, const float* w, int T, int cin, int kt
         } else if (k < cin) {
           v = transposed ? w[((size_t)k * 64 + co) * ktaps + t] : w[((size_t)co * cin + k) * ktaps + t];
         }
-        const int n = (co >> 5) * (T * 32) + t * 32 + (co & 31);   // [column half][tap][32 channels]: the taps of one half are one MMA operand
+        const int n = (co >> 4) * (T * 16) + t * 16 + (co & 15);   // [channel quarter][tap][16 channels]: the taps of one quarter (or of two adjacent quarters = a half) are one MMA operand
         const size_t o = (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
         const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
         memcpy(base + o, &hi, 2);

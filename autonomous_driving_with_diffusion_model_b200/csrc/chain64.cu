@@ -42,9 +42,6 @@ constexpr int CH_OFF_MISC = CH_OFF_W + CH_W_BYTES;
 constexpr int CH_HEADP_SLOTS = 2 * CH_SL;             // head partial sums [column half x slice][8][128 rows] = 32 KB: they live in an activation buffer that is idle
 static_assert(CH_HEADP_SLOTS * 8 * 128 * 4 <= CH_ACT_BYTES, "head partial sums alias one activation buffer");   // during the head op (neither its A operand nor the next op's)
 static_assert(CH_EPI_THREADS == 512, "the epilogue mapping assumes 16 warps: 4 lane quadrants x 4 column slices of 8 channels per half");
-#ifndef CH_READER_FENCE
-#define CH_READER_FENCE 0   // the writers' fence.proxy.async + the cluster barrier's release/acquire order the remote stores before the MMAs (bitwise test); a reader-side fence cost ~700 cycles per op
-#endif
 constexpr int CH_MAX_HD = 16 * 8;                     // horizon 16 x transition dim <= 8 (im2col K = 5 * D <= 64; one scheduler element per thread)
 
 struct __align__(16) ChainShared {
@@ -100,7 +97,7 @@ template <int NT>
 __device__ __forceinline__ void tap_combine(float (&v)[CH_EC], uint32_t tbase, const int (&blk)[NT], const int (&sh)[NT], int l, int L, int lane) {
   float y[NT][CH_EC];
 #pragma unroll
-  for (int i = 0; i < NT; ++i) tmem_ld<CH_EC, false>(tbase + blk[i] * 32, y[i]);   // every tap block in flight at once: ONE exposed TMEM latency per half
+  for (int i = 0; i < NT; ++i) tmem_ld<CH_EC, false>(tbase + blk[i] * 16, y[i]);   // every tap block in flight at once: ONE exposed TMEM latency per half
   tmem_ld_wait();
 #pragma unroll
   for (int i = 0; i < NT; ++i) {
@@ -154,12 +151,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
   uint8_t* smem = smem_align1024(smem_raw);
   ChainShared* sh = reinterpret_cast<ChainShared*>(smem + CH_OFF_MISC);
   uint8_t* wbuf = smem + CH_OFF_W;
-  constexpr int NH = CL == 2 ? 1 : 2;                   // column-half passes per CTA
-  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
-  const uint32_t peer_base = CL == 2 ? mapa_u32(smem_u32(smem), (uint32_t)(crank ^ 1)) : 0u;   // the other CTA's copy of `smem`
+  constexpr int NH = CL == 1 ? 2 : 1;                   // column-half passes per CTA
+  constexpr int NPEER = CL - 1;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  uint32_t peer_base[NPEER > 0 ? NPEER : 1];            // the other CTAs' copies of `smem`
+#pragma unroll
+  for (int pr = 0; pr < NPEER; ++pr) peer_base[pr] = mapa_u32(smem_u32(smem), (uint32_t)(crank ^ (pr + 1)));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b0 = (CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * a.ns;
+  const int b0 = (int)(blockIdx.x / CL) * a.ns;
   const int nb = a.B - b0 < a.ns ? a.B - b0 : a.ns;
   const int HD = a.H * a.D;
 
@@ -208,13 +208,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     const ChainOp& op = sh->ops[oi];
     const uint32_t plane = (uint32_t)op.T * CH_TAP_BYTES;
     const uint8_t* src = a.wpack + op.w_off;
-    if (CL == 2) {                       // only this CTA's column half of each plane (the image is ordered [plane][column half][tap][32 channels]), same offsets
-      const uint32_t half_bytes = plane / 2, o0 = (uint32_t)crank * half_bytes;
-      mbar_expect_tx(&sh->wbar, NSPLIT * half_bytes);
+    if (CL > 1) {                        // only this CTA's channel half / quarter of each plane (the image is ordered [plane][channel quarter][tap][16 channels]), same offsets
+      const uint32_t part_bytes = plane / CL, o0 = (uint32_t)crank * part_bytes;
+      mbar_expect_tx(&sh->wbar, NSPLIT * part_bytes);
       for (int pl = 0; pl < NSPLIT; ++pl)
         for (int i = 0; i < op.T; ++i) {
-          const uint32_t o = pl * plane + o0 + (uint32_t)i * (CH_TAP_BYTES / 2);
-          bulk_g2s(wbuf + o, src + o, CH_TAP_BYTES / 2, &sh->wbar);
+          const uint32_t o = pl * plane + o0 + (uint32_t)i * (CH_TAP_BYTES / CL);
+          bulk_g2s(wbuf + o, src + o, CH_TAP_BYTES / CL, &sh->wbar);
         }
     } else {
       mbar_expect_tx(&sh->wbar, NSPLIT * plane);
@@ -248,9 +248,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     }
   }
 
-  const int quad = warp & 3, slice = warp >> 2, col0 = slice * CH_EC;
+  const int quad = warp & 3, slice = warp >> 2;
   const int r = quad * 32 + lane;                               // tile row == TMEM lane
-  const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + col0;
+  const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+  // this warp's 8-channel chunk (of the 64 channels) in column-half pass hf, and whether the warp has one at all (a quarter is two chunks: slices 0, 1)
+  const bool wactive = warp < CH_EPI_THREADS / 32 && (CL < 4 || slice < 2);
+  auto chunk_of = [&](int hf) { return CL == 1 ? hf * 4 + slice : (CL == 2 ? crank * 4 + slice : crank * 2 + (slice & 1)); };
   uint32_t wpar = 0, mpar = 0;
 
 #pragma unroll 1
@@ -277,11 +280,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
         if (NSPLIT == 2) *reinterpret_cast<uint4*>(smem + CH_HALF + swz(row, c8)) = lo;
       }
     }
+    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 0] = clock64();
+    // the A operand was written with ordinary stores: make the LOCAL ones visible to the tensor core here; the remote ones become visible to the peer through the
+    // cluster barrier's release / acquire, and the peer's MMA lane runs its own proxy fence behind the barrier (a full `fence.proxy.async` here costs a second
+    // GPU-scope membar on top of the one inside barrier.cluster.arrive.release)
+    fence_async_smem();
+    tc_fence_before();               // ... and the previous op's TMEM reads are complete
+    // both CTAs have written their channel half of this op's A operand into both copies: ARRIVE now, wait after the address work and load issue below
+    if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     // ------------- everything added after GroupNorm / Mish comes from global memory and depends on nothing this kernel computes: the loads are
     // ISSUED here, ahead of the barrier, all of them before the first use (issued after the barrier and consumed half by half they were two to
     // three serialised L2 round trips, 2.3-3.2 k cycles against the ~1 k of the first column half's MMAs) -------------
     const int l = r & (L - 1), sidx = r >> op.log2L;
-    const bool epi = warp < CH_EPI_THREADS / 32;             // the extra warp only issues MMAs
+    const bool epi = wactive;                                // the extra warp only issues MMAs; with four CTAs per group half of the epilogue warps have no chunk
     const bool row_ok = epi && sidx < nb;
     const int b = b0 + sidx;
     const bool has_t = row_ok && op.temb_off >= 0, has_q = row_ok && op.res_kind == CH_RES_F32;
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     float4 raw[NH][3][CH_EC / 4];                            // [column-half pass][time row | per-step time vector | fp32 residual]
 #pragma unroll
     for (int hf = 0; hf < NH; ++hf) {
-      const int ch0 = (CL == 2 ? crank : hf) * 32 + col0;
+      const int ch0 = chunk_of(hf) * 8;
 #pragma unroll
       for (int j = 0; j < CH_EC / 4; ++j) {
         raw[hf][0][j] = raw[hf][1][j] = raw[hf][2][j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -299,11 +310,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
         if (has_q) raw[hf][2][j] = __ldg(reinterpret_cast<const float4*>(a.res_f32 + ((size_t)b * L + l) * 64 + ch0) + j);
       }
     }
-    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 0] = clock64();
-    if (CL == 2) asm volatile("fence.proxy.async;" ::: "memory");   // ... local AND remote stores
-    else fence_async_smem();         // the A operand was written with ordinary stores: make it visible to the tensor core
-    tc_fence_before();               // ... and the previous op's TMEM reads are complete
-    if (CL == 2) cluster_sync_all(); // both CTAs have written their channel half of this op's A operand into both copies
+    if (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     else __syncthreads();
     if (a.trace && blockIdx.x == 0) {   // BAR.SYNC lets the next instruction issue before the warp blocks: a clock read right behind it is the ARRIVAL time
       __syncwarp();
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       if (elect_one()) {
       if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 14] = clock64();
       mbar_wait(&sh->wbar, wpar);
-      if (CL == 2 && CH_READER_FENCE) asm volatile("fence.proxy.async;" ::: "memory");   // reader side of the generic-proxy stores the peer CTA made into this CTA's A operand
+      if (CL > 1) fence_async_smem();   // reader side of the generic-proxy stores the peer CTAs made into this CTA's A operand (visible since the cluster barrier)
       tc_fence_after();
       if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 2] = clock64();
       const uint32_t sa = smem_u32(smem + (op.in_buf < 0 ? 0 : op.in_buf) * CH_ACT_BYTES);
@@ -323,11 +330,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + CH_HALF);
       // the weight image is ordered [column half][tap][32 channels]: the taps of one half are ONE instruction of N = 32 * T, and the
       // epilogue of half 0 overlaps the MMAs of half 1
-      const uint32_t idn = umma_idesc_n(op.T * 32);
-      const uint32_t half_bytes = (uint32_t)op.T * (CH_TAP_BYTES / 2);
+      const uint32_t idn = umma_idesc_n(CL == 4 ? op.T * 16 : op.T * 32);
+      const uint32_t half_bytes = (uint32_t)op.T * (CH_TAP_BYTES / (CL == 4 ? 4 : 2));   // one MMA operand: a channel half (a quarter with four CTAs)
 #pragma unroll 1
       for (int hf = 0; hf < NH; ++hf) {
-        const uint32_t hc = CL == 2 ? (uint32_t)crank : (uint32_t)hf;   // channel half
+        const uint32_t hc = CL > 1 ? (uint32_t)crank : (uint32_t)hf;    // which half / quarter
         const uint64_t b_hi = umma_desc(sb + hc * half_bytes), b_lo = umma_desc(sb + op.T * CH_TAP_BYTES + hc * half_bytes);
         const uint32_t dcol = tmem_base + hf * CH_HCOLS;
 #pragma unroll 1
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     float addv[NH][CH_EC];
 #pragma unroll
     for (int hf = 0; hf < NH; ++hf) {
-      const int ch0 = (CL == 2 ? crank : hf) * 32 + col0;   // first of this thread's 8 channels in this pass's column half
+      const int ch0 = chunk_of(hf) * 8;                     // first of this thread's 8 channels in this pass
 #pragma unroll
       for (int c = 0; c < CH_EC; ++c) addv[hf][c] = 0.f;
       if (has_t) {
@@ -396,8 +403,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     float (*headp)[8][TC_M] = reinterpret_cast<float (*)[8][TC_M]>(smem + hb * CH_ACT_BYTES);
 #pragma unroll
     for (int hf = 0; hf < NH; ++hf) {
-      const int hc = CL == 2 ? crank : hf;
-      const int ch0 = hc * 32 + col0, c8 = hc * 4 + slice;
+      const int c8 = chunk_of(hf), ch0 = c8 * 8;
       float hsum[8];                                    // fused head: partial dot products of this thread's 8 channels
 #pragma unroll
       for (int d = 0; d < 8; ++d) hsum[d] = 0.f;
@@ -412,7 +418,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
         for (int c = 0; c < CH_EC; ++c) v[c] = sh->vec[oi][0][ch0 + c];
         // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the trajectory) ----
         // ---- combine the tap blocks: out[l] += Y_t[l + shift] (zero outside the trajectory); the op kind is uniform over the CTA ----
-        const uint32_t tbase = taddr + hf * CH_HCOLS;
+        const uint32_t tbase = taddr + hf * CH_HCOLS + (CL == 4 ? 0 : (slice >> 1) * op.T * 16) + (slice & 1) * 8;   // accumulator columns: [quarter][tap][16]
         if (op.kind == CH_UP) {        // ConvTranspose1d(k4, s2, p1): out[2m] = Y1[m] + Y3[m-1];  out[2m+1] = Y0[m+1] + Y2[m]
           if (o == 0) tap_combine<2>(v, tbase, {1, 3}, {0, -1}, l, L, lane);
           else tap_combine<2>(v, tbase, {0, 2}, {1, 0}, l, L, lane);
@@ -452,8 +458,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
             if (row_ok) split8(v, &hi, &lo);
             *reinterpret_cast<uint4*>(ob + swz(ro, c8)) = hi;
             if (NSPLIT == 2) *reinterpret_cast<uint4*>(ob + CH_HALF + swz(ro, c8)) = lo;
-            if (CL == 2) {             // the same chunks into the peer CTA's copy of the buffer
-              const uint32_t ra = peer_base + (uint32_t)(op.out_buf * CH_ACT_BYTES) + swz(ro, c8);
+#pragma unroll
+            for (int pr = 0; pr < NPEER; ++pr) {   // the same chunks into the peer CTAs' copies of the buffer
+              const uint32_t ra = peer_base[pr] + (uint32_t)(op.out_buf * CH_ACT_BYTES) + swz(ro, c8);
               st_cluster_v4(ra, hi);
               if (NSPLIT == 2) st_cluster_v4(ra + CH_HALF, lo);
             }
@@ -485,7 +492,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
         for (int d = 0; d < 8; ++d)
           if (d < a.head_dim) {
             headp[c8][d][r] = hsum[d];
-            if (CL == 2) st_cluster_1f(peer_base + (uint32_t)(hb * CH_ACT_BYTES) + (uint32_t)(((c8 * 8 + d) * TC_M + r) * 4), hsum[d]);
+#pragma unroll
+            for (int pr = 0; pr < NPEER; ++pr) st_cluster_1f(peer_base[pr] + (uint32_t)(hb * CH_ACT_BYTES) + (uint32_t)(((c8 * 8 + d) * TC_M + r) * 4), hsum[d]);
           }
       }
     }
@@ -493,7 +501,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 8] = clock64();
     if (op.out_buf == CH_OUT_HEAD) {
       const int hd = a.head_dim;
-      if (CL == 2) cluster_sync_all(); else __syncthreads();
+      if (CL > 1) cluster_sync_all(); else __syncthreads();
       if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 10] = clock64();
       for (int idx = tid; idx < TC_M * hd; idx += CH_THREADS) {   // one (row, d) sum at a time; rows without a trajectory hold whatever the buffer held
         const int rr = idx / hd, d = idx - rr * hd;
@@ -529,7 +537,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
 
   if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[a.n_ops * 16] = clock64();
   tc_fence_before();
-  if (CL == 2) cluster_sync_all();    // neither CTA leaves while the other may still store into its shared memory
+  if (CL > 1) cluster_sync_all();     // neither CTA leaves while the other may still store into its shared memory
   else __syncthreads();
   if (warp == CH_MMA_WARP) {
     tc_fence_after();
@@ -552,17 +560,33 @@ int launch_chain64(const ChainArgs& a, int nsplit, cudaStream_t s) {
   if (a.do_sched && (a.head_dim != a.D || !a.x_out || a.sk.mo_u || a.sk.clip_mode == 3)) return B2P_ERR_INVALID_ARG;
   const size_t smem = chain64_smem_bytes();
   const int groups = (a.B + a.ns - 1) / a.ns;
-  // two CTAs per trajectory group (each computes one channel half of every op) while the doubled grid still fits the SMs in one wave;
-  // B2P_CHAIN_CL = 1 / 2 forces a variant (developer switch)
-  static int forced = -1, sms = 0;
+  // CL CTAs per trajectory group (each computes 1/CL of the channels of every op): two while all clusters are resident at once (four measured no
+  // faster than two: the single epilogue pass is latency-bound by then and the barrier among four CTAs costs more); B2P_CHAIN_CL = 1 / 2 / 4 forces a variant
+  static int forced = -1, max_clusters[5] = {0, 0, 0, 0, 0};
   if (forced < 0) {
     const char* e = getenv("B2P_CHAIN_CL");
     forced = e ? atoi(e) : 0;
-    int dev = 0;
+    int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    max_clusters[1] = sms;
+    for (int c = 2; c <= 4; c += 2) {   // how many clusters of c CTAs of this footprint the device holds at once (GPC granularity)
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(c * sms); q.blockDim = dim3(CH_THREADS); q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = c; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int n = 0;
+      cudaError_t e1 = c == 2 ? cudaFuncSetAttribute(chain64_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(chain64_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e1 == cudaSuccess) e1 = c == 2 ? cudaOccupancyMaxActiveClusters(&n, chain64_kernel<2, 2>, &q) : cudaOccupancyMaxActiveClusters(&n, chain64_kernel<2, 4>, &q);
+      if (e1 != cudaSuccess) { cudaGetLastError(); n = 0; }
+      max_clusters[c] = n;
+    }
   }
-  const int cl = forced == 1 || forced == 2 ? forced : (2 * groups <= sms ? 2 : 1);
+  const int cl = forced == 1 || forced == 2 || forced == 4 ? forced : (groups <= max_clusters[2] ? 2 : 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(groups * cl); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -570,9 +594,9 @@ int launch_chain64(const ChainArgs& a, int nsplit, cudaStream_t s) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   int na = 1;
-  if (cl == 2) {
+  if (cl > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    attr[na].val.clusterDim.x = cl; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = add_l2_window_attr(attr, na);
@@ -581,8 +605,8 @@ int launch_chain64(const ChainArgs& a, int nsplit, cudaStream_t s) {
     B2P_CUDA_TRY(cudaFuncSetAttribute(chain64_kernel<NS_, CL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
     return (int)cudaLaunchKernelEx(&cfg, chain64_kernel<NS_, CL_>, a);                                                               \
   } while (0)
-  if (nsplit == 2) { if (cl == 2) B2P_CHAIN_LAUNCH(2, 2); else B2P_CHAIN_LAUNCH(2, 1); }
-  if (cl == 2) B2P_CHAIN_LAUNCH(1, 2); else B2P_CHAIN_LAUNCH(1, 1);
+  if (nsplit == 2) { if (cl == 4) B2P_CHAIN_LAUNCH(2, 4); else if (cl == 2) B2P_CHAIN_LAUNCH(2, 2); else B2P_CHAIN_LAUNCH(2, 1); }
+  if (cl == 4) B2P_CHAIN_LAUNCH(1, 4); else if (cl == 2) B2P_CHAIN_LAUNCH(1, 2); else B2P_CHAIN_LAUNCH(1, 1);
 #undef B2P_CHAIN_LAUNCH
 }
 

@@ -1053,18 +1053,18 @@ for prec in ("bf16x3", "bf16"):
 '''
 
 
-def test_chain_kernel_two_cta_form_is_bitwise_the_one_cta_form():
-    """csrc/chain64.cu, CL = 2: a cluster of two CTAs owns a group of 8 trajectories, each CTA computes one channel half of every op
-    and stores its chunks of the next A operand into both CTAs' shared memory (modeling/temporal.py:46-55,215-245 are the layers).
+def test_chain_kernel_cluster_forms_are_bitwise_the_one_cta_form():
+    """csrc/chain64.cu, CL = 2 / 4: a cluster of two (four) CTAs owns a group of 8 trajectories, each CTA computes one channel half (quarter)
+    of every op and stores its chunks of the next A operand into every CTA's shared memory (modeling/temporal.py:46-55,215-245 are the layers).
     Per element the arithmetic is the one-CTA form's, so whole plans must agree bit for bit: seam launches (DDIM / DDPM), the
     classifier-free doubled batch, ragged last groups, both tensor-core precisions.  The variant is chosen per process
     (B2P_CHAIN_CL), hence the two subprocesses."""
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for cl in ("1", "2"):
+    for cl in ("1", "2", "4"):
         env = dict(os.environ, B2P_CHAIN_CL=cl, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
         r = subprocess.run([sys.executable, "-c", _CHAIN_CL_PROBE], env=env, cwd=root, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines())
-    assert len(outs[0]) == 24 and outs[0] == outs[1]
+    assert len(outs[0]) == 24 and outs[0] == outs[1] and outs[0] == outs[2]
