@@ -42,11 +42,16 @@ constexpr int CH_OFF_MISC = CH_OFF_W + CH_W_BYTES;
 constexpr int CH_HEADP_SLOTS = 2 * CH_SL;             // head partial sums [column half x slice][8][128 rows] = 32 KB: they live in an activation buffer that is idle
 static_assert(CH_HEADP_SLOTS * 8 * 128 * 4 <= CH_ACT_BYTES, "head partial sums alias one activation buffer");   // during the head op (neither its A operand nor the next op's)
 static_assert(CH_EPI_THREADS == 512, "the epilogue mapping assumes 16 warps: 4 lane quadrants x 4 column slices of 8 channels per half");
+#ifndef CH_STASYNC
+#define CH_STASYNC 0   // cluster forms, compile-time experiment: 1 = the next A operand travels as st.async stores that complete a byte count on the CONSUMER's
+#endif                 // mbarrier (no writer-side drain, no cluster barrier per op).  Built, bit-identical, and 0.5 % SLOWER per plan than 0 = st.shared::cluster +
+                       // barrier.cluster release / acquire per op (same-call A/B at B = 256: 241.4 vs 240.2 us per iteration): the STAS stores lengthen the pass
 constexpr int CH_MAX_HD = 16 * 8;                     // horizon 16 x transition dim <= 8 (im2col K = 5 * D <= 64; one scheduler element per thread)
 
 struct __align__(16) ChainShared {
   uint64_t wbar;                 // weight image of the current op has landed
   uint64_t mma_bar[2];           // MMAs of column half 0 / 1 of the current op have retired
+  uint64_t abar[2];              // cluster forms: the peers' chunks of op oi's A operand have landed (by op parity)
   uint32_t tmem_base;
   uint32_t pad;                  // the float tables below are read as float4: keep them 16-byte aligned
   float vec[CH_MAXOPS][3][64];   // bias / gamma / beta of every op, fetched once in the prologue (a per-op fetch put one global-load latency on every op-to-op hand-over)
@@ -138,6 +143,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) { uin
 __device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+               : "memory");
+}
 __device__ __forceinline__ void st_cluster_1f(uint32_t raddr, float x) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(x) : "memory"); }
 
 // CL = 1: one CTA owns 8 trajectories and all 64 channels (two column-half passes per op).
@@ -167,6 +176,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     mbar_init(&sh->wbar, 1);
     mbar_init(&sh->mma_bar[0], 1);
     mbar_init(&sh->mma_bar[1], 1);
+    mbar_init(&sh->abar[0], 1);
+    mbar_init(&sh->abar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -200,7 +211,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     if (tid < hd) sh->headw[8 * 64 + tid] = __ldg(a.headB + tid);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();   // every CTA of the cluster has initialised its barriers and zeroed its buffers before a peer stores into them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
 
@@ -255,6 +267,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
   const bool wactive = warp < CH_EPI_THREADS / 32 && (CL < 4 || slice < 2);
   auto chunk_of = [&](int hf) { return CL == 1 ? hf * 4 + slice : (CL == 2 ? crank * 4 + slice : crank * 2 + (slice & 1)); };
   uint32_t wpar = 0, mpar = 0;
+  uint32_t aph = 0;                 // phase bits of abar[0], abar[1]: a phase completes only on an op that waits for peers' chunks (MMA lane only)
 
 #pragma unroll 1
   for (int oi = 0; oi < a.n_ops; ++oi) {
@@ -287,7 +300,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     fence_async_smem();
     tc_fence_before();               // ... and the previous op's TMEM reads are complete
     // both CTAs have written their channel half of this op's A operand into both copies: ARRIVE now, wait after the address work and load issue below
-    if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (CL > 1 && !CH_STASYNC) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     // ------------- everything added after GroupNorm / Mish comes from global memory and depends on nothing this kernel computes: the loads are
     // ISSUED here, ahead of the barrier, all of them before the first use (issued after the barrier and consumed half by half they were two to
     // three serialised L2 round trips, 2.3-3.2 k cycles against the ~1 k of the first column half's MMAs) -------------
@@ -310,8 +323,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
         if (has_q) raw[hf][2][j] = __ldg(reinterpret_cast<const float4*>(a.res_f32 + ((size_t)b * L + l) * 64 + ch0) + j);
       }
     }
-    if (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    else __syncthreads();
+    if (CL > 1 && !CH_STASYNC) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    else __syncthreads();            // (st.async form: the CTA barrier covers this CTA's own chunks and its TMEM reads; the peers' chunks are counted on abar)
     if (a.trace && blockIdx.x == 0) {   // BAR.SYNC lets the next instruction issue before the warp blocks: a clock read right behind it is the ARRIVAL time
       __syncwarp();
       if (tid == 0) a.trace[oi * 16 + 1] = clock64();
@@ -322,7 +335,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       if (elect_one()) {
       if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 14] = clock64();
       mbar_wait(&sh->wbar, wpar);
-      if (CL > 1) fence_async_smem();   // reader side of the generic-proxy stores the peer CTAs made into this CTA's A operand (visible since the cluster barrier)
+      if (CL > 1 && CH_STASYNC && oi > 0 && op.in_buf >= 0) {
+        // the peers' chunks of this op's A operand: every peer thread that stored sent 16 bytes per plane (and per output row of an upsampling op);
+        // the peers run the same op table on the same trajectories, so the count is the one this CTA's own epilogue warps produced for them
+        const ChainOp& pv = sh->ops[oi - 1];
+        int nq = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nq += (((q * 32) >> pv.log2L) < nb && (pv.kind != CH_UP || q < 2)) ? 1 : 0;
+        const uint32_t per_cta = (uint32_t)nq * (CL == 4 ? 2u : 4u) * 32u * 16u * NSPLIT * (pv.kind == CH_UP ? 2u : 1u);
+        mbar_expect_tx(&sh->abar[oi & 1], (CL - 1) * per_cta);
+        mbar_wait(&sh->abar[oi & 1], (aph >> (oi & 1)) & 1u);
+        aph ^= 1u << (oi & 1);
+      }
+      if (CL > 1) fence_async_smem();   // reader side of the stores the peer CTAs made into this CTA's A operand
       tc_fence_after();
       if (a.trace && blockIdx.x == 0) a.trace[oi * 16 + 2] = clock64();
       const uint32_t sa = smem_u32(smem + (op.in_buf < 0 ? 0 : op.in_buf) * CH_ACT_BYTES);
@@ -461,8 +486,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
 #pragma unroll
             for (int pr = 0; pr < NPEER; ++pr) {   // the same chunks into the peer CTAs' copies of the buffer
               const uint32_t ra = peer_base[pr] + (uint32_t)(op.out_buf * CH_ACT_BYTES) + swz(ro, c8);
-              st_cluster_v4(ra, hi);
-              if (NSPLIT == 2) st_cluster_v4(ra + CH_HALF, lo);
+              if (CH_STASYNC) {
+                const uint32_t rb = peer_base[pr] + (smem_u32(&sh->abar[(oi + 1) & 1]) - smem_u32(smem));
+                st_async_v4(ra, hi, rb);
+                if (NSPLIT == 2) st_async_v4(ra + CH_HALF, lo, rb);
+              } else {
+                st_cluster_v4(ra, hi);
+                if (NSPLIT == 2) st_cluster_v4(ra + CH_HALF, lo);
+              }
             }
           }
         } else if (op.out_buf == CH_OUT_GLOBAL) {
@@ -556,6 +587,7 @@ int launch_chain64(const ChainArgs& a, int nsplit, cudaStream_t s) {
     // the head's partial sums alias activation buffer 2 (0 if the A operand is buffer 2): it must not be the residual, and the next op must rebuild its own operand
     if (op.out_buf == CH_OUT_HEAD && ((op.res_kind == CH_RES_SMEM && op.res_buf == (op.in_buf == 2 ? 0 : 2)) || (i + 1 < a.n_ops && a.ops[i + 1].in_buf != CH_IN_IM2COL))) return B2P_ERR_INVALID_ARG;
     if (op.in_buf == CH_IN_IM2COL && op.L != 16) return B2P_ERR_INVALID_ARG;
+    if (i > 0 && op.in_buf >= 0 && a.ops[i - 1].out_buf != op.in_buf) return B2P_ERR_INVALID_ARG;   // the cluster forms count the previous op's stores as this op's operand
   }
   if (a.do_sched && (a.head_dim != a.D || !a.x_out || a.sk.mo_u || a.sk.clip_mode == 3)) return B2P_ERR_INVALID_ARG;
   const size_t smem = chain64_smem_bytes();
