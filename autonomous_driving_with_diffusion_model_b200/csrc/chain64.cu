@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
     if (tid < hd) sh->headw[8 * 64 + tid] = __ldg(a.headB + tid);
   }
   tc_fence_before();
+  __syncthreads();
   if (CL > 1) cluster_sync_all();   // every CTA of the cluster has initialised its barriers and zeroed its buffers before a peer stores into them
-  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
 
