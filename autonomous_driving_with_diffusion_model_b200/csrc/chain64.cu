@@ -6,6 +6,9 @@
 // K-major, 128-byte swizzle — written by the epilogue in exactly the layout TMA would produce), accumulators in TMEM, weights
 // stream in as pre-swizzled images (one bulk copy per tap, issued as soon as the previous layer's MMAs have retired).
 // No kernel boundary, no dependency release, no first-operand latency between the layers of a chain.
+// While the doubled grid still fits the SMs in one wave the group is owned by a CLUSTER of two CTAs instead (template parameter CL; four is built too):
+// each computes one channel half of every layer and stores its chunks of the next A operand into both CTAs' shared memory, because the epilogue
+// (tap combine + GroupNorm + Mish for 128 rows x 64 channels), not the tensor core, is what an op costs.  All forms give bit-identical results.
 //
 // Chains (modeling/temporal.py:197-245, interact.py:132-164):
 //   head of an evaluation  : downs.0 = im2col'd Conv1dBlock(7->64) [+temb], Conv1dBlock(64->64) [+1x1 projection of x],
@@ -28,7 +31,7 @@ namespace b2p {
 
 constexpr int CH_EPI_THREADS = 512;                  // 16 epilogue warps: 4 per TMEM lane quadrant
 constexpr int CH_MMA_WARP = 16;                      // a 17th warp issues the MMAs AND, the moment they have retired, the next op's weight copy: an epilogue warp
-                                                     // got to that copy only after its own half-0 epilogue, 1.5-2.5 k cycles later, and the copy (~5 k cycles in situ) was exposed
+                                                     // got to that copy only after its own half-0 epilogue, 1.5-2.5 k cycles later (the copy itself lands 1.4-2.0 k cycles after issue)
 constexpr int CH_THREADS = CH_EPI_THREADS + 32;
 constexpr int CH_EC = 8;                             // columns per epilogue thread and column half: one GroupNorm group, one 16-byte chunk
 constexpr int CH_SL = 4;                             // column slices per half (4 warps per TMEM lane quadrant)
