@@ -124,9 +124,11 @@ class DiffusionPlanner:
         requests are sharded by batch across the 8 GPUs of one box with no NCCL on the sampling path"): contiguous split
         (``sharding.shard_bounds``), one C handle + private stream + captured graph per device, inputs staged through pinned
         host memory, all shards enqueued back to back (``b2p_plan_sharded_host``), joined, results concatenated in the
-        pinned output.  Host fp32 tensors in, host tensor out.  The result is bitwise the single-GPU result as long as a
-        shard does not fall into the small-batch GEMV regime (<= ``small_batch_max`` trajectories) while the whole batch
-        does not: no operation of the path crosses samples."""
+        pinned output.  Host fp32 tensors in, host tensor out.  No operation of the path crosses samples, so the result is
+        bitwise the single-GPU result as long as every shard runs the same kernels as the whole batch would: not the
+        small-batch GEMV program (<= ``small_batch_max`` trajectories) against the tile kernels, and the same column-tile
+        widths (the tile kernels widen their tiles once a layer exceeds one wave of CTAs, beyond ~256 trajectories; plans of
+        different tile widths agree to bf16x3 rounding, not bitwise)."""
         m = self.model
         devs = list(range(torch.cuda.device_count())) if devices is None else [torch.device(d).index if not isinstance(d, int) else d for d in devices]
         if not devs:
