@@ -688,6 +688,22 @@ def test_headline_config_b256_t100_bf16x3_vs_oracle():
     assert float(out[:, 0, :3].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("B", [512, 2048])
+def test_wide_tile_batches_t100_bf16x3_vs_oracle(B):
+    """Beyond ~256 trajectories the tile kernels widen their column tiles (conv_tc.cu: tc_pick_tile_n, 16 -> 32 -> 64 columns) and, beyond 592, the
+    chain kernel goes back to its one-CTA form: other GroupNorm exchange paths, other MMA shapes.  The same DDIM-100 plan as the headline test at
+    those sizes, against the oracle on trajectories of the first / middle / last row tiles.  Bound: 1e-3 in normalised units (north_star)."""
+    model, sd = get_tc_model("NO_GUIDANCE", "bf16x3")
+    T = 100
+    planner = P.DiffusionPlanner(model, make_sched("guidance_ddim"), _cfg("NO_GUIDANCE", T))
+    inp = W.synth_inputs(B, 0, 1)
+    out = planner.plan(inp["x"].to(DEV), inp["feat"].to(DEV), postprocess=False).cpu()
+    rows = [0, 63, B // 2 - 1, B // 2, B - 64, B - 1]
+    ref = OP.plan(sd, "NO_GUIDANCE", "guidance_ddim", inp["x"][rows], inp["feat"][rows], T, postprocess=False)
+    err = (out[rows] - ref).abs()
+    assert float(err.max()) <= 1e-3, [float(e.max()) for e in err]
+
+
 def test_cached_graphs_of_different_T_do_not_share_timesteps():
     """a cached plan graph reads its timesteps from a handle-owned buffer at REPLAY time; alternating
     T=100 / T=10 / T=100 on one handle (no buffer growth, no graph drop in between) must reproduce the first result."""
