@@ -538,11 +538,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain64_kernel(const __grid_con
       if (CL > 1) cluster_sync_all(); else __syncthreads();
       if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[oi * 16 + 10] = clock64();
       for (int idx = tid; idx < TC_M * hd; idx += CH_THREADS) {   // one (row, d) sum at a time; rows without a trajectory hold whatever the buffer held
-        const int rr = idx / hd, d = idx - rr * hd;
+        // consecutive threads take consecutive ROWS: headp[j][d][row] is row-fastest, so the loads are conflict-free (d-fastest put the hd threads of a
+        // row on one bank: 7-way conflicts on all eight loads, ~1.5 k cycles per launch) and the row count is a power of two, no division
+        const int d = idx >> 7, rr = idx & (TC_M - 1);
         float m = sh->headw[8 * 64 + d];
 #pragma unroll
         for (int j = 0; j < CH_HEADP_SLOTS; ++j) m += headp[j][d][rr];
-        sh->mo[idx] = m;                      // index rr * hd + d with rr == s * 16 + l: the [NS, H, head_dim] block of this CTA
+        sh->mo[rr * hd + d] = m;              // index rr * hd + d with rr == s * 16 + l: the [NS, H, head_dim] block of this CTA
         const int s2 = rr >> 4;
         if (a.head_out && s2 < nb && crank == 0) a.head_out[((size_t)(b0 + s2) * 16 + (rr & 15)) * hd + d] = m;
       }
