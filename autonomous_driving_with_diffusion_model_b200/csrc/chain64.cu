@@ -622,6 +622,7 @@ int launch_chain64(const ChainArgs& a, int nsplit, cudaStream_t s) {
       if (e1 != cudaSuccess) { cudaGetLastError(); n = 0; }
       max_clusters[c] = n;
     }
+    if (getenv("B2P_CHAIN_DEBUG")) fprintf(stderr, "[b2p] chain kernel: %d SMs, resident clusters of 2 CTAs: %d, of 4 CTAs: %d\n", sms, max_clusters[2], max_clusters[4]);
   }
   const int cl = forced == 1 || forced == 2 || forced == 4 ? forced : (groups <= max_clusters[2] ? 2 : 1);
   cudaLaunchConfig_t cfg;
